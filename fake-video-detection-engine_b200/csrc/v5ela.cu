@@ -1,0 +1,347 @@
+// v5ela.cu — kernels + C ABI (include/v5ela.h) of libv5ela.so. sm_100a only.
+//
+// Launch sequence of one v5ela_analyze call (all on the caller's stream, no host sync, no allocation):
+//   1. cudaMemsetAsync(records)                      records are accumulated with atomics by several CTAs per frame
+//   2. ela_fused_kernel   (persistent, 2 CTAs / SM)  everything per pixel — see v5ela_device.cuh
+//   3. ela_finalize_kernel (1 warp per frame-channel) ela_sum / ela_sumsq / ela_max from the histogram
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "v5ela.h"
+#include "v5ela_host.h"
+#include "v5ela_workitem.cuh"
+
+static_assert(sizeof(v5ela_record) == 3144, "V5F v1 record layout");
+static_assert(sizeof(v5::KParams) <= 4096, "kernel parameters must fit the 4 KB parameter bank");
+static_assert(sizeof(v5::Smem) <= 113 * 1024, "two CTAs per SM");
+
+namespace v5 {
+
+__global__ void __launch_bounds__(NT, 2) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    ThreadAcc acc_store[1];
+    // Work items are equal-sized (same strip/segment shapes in every frame): a static stride is balanced.
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) process_work_item(S, p, work, acc_store);
+}
+
+// One warp per (frame, channel): ela_sum = sum b*hist[b], ela_sumsq = sum b^2*hist[b], ela_max = highest non-empty bin.
+__global__ void __launch_bounds__(96) ela_finalize_kernel(v5ela_record *recs, int n)
+{
+    const int frame = blockIdx.x, c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (frame >= n) return;
+    v5ela_record &r = recs[frame];
+    unsigned long long s = 0, sq = 0;
+    int mx = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int b = lane + 32 * i;
+        const unsigned long long cnt = r.ela_hist[c][b];
+        s += cnt * (unsigned long long)b;
+        sq += cnt * (unsigned long long)(b * b);
+        if (cnt) mx = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        r.ela_sum[c] = s;
+        r.ela_sumsq[c] = sq;
+    }
+    __syncthreads();                       // tex_maxabs shares its 32-bit word with ela_max[0..1]: plain byte stores
+    if (lane == 0) r.ela_max[c] = (uint8_t)mx;
+}
+
+// ImageEnhance.Brightness(diff).enhance(255.0/max_diff) (v5_texture_ela.py:74-78): a per-frame 256-entry float32 LUT.
+__global__ void __launch_bounds__(256) ela_enhance_kernel(const uint8_t *__restrict__ resid, const v5ela_record *recs,
+                                                         uint8_t *__restrict__ out, long long bytes_per_frame)
+{
+    __shared__ uint8_t lut[256];
+    const int frame = blockIdx.y;
+    const v5ela_record &r = recs[frame];
+    int m = max((int)r.ela_max[0], max((int)r.ela_max[1], (int)r.ela_max[2]));
+    if (m == 0) m = 1;
+    const float scale = (float)(255.0 / (double)m);
+    {
+        const float v = (float)threadIdx.x * scale;
+        lut[threadIdx.x] = (uint8_t)(v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (int)v));
+    }
+    __syncthreads();
+    const uint8_t *src = resid + (long long)frame * bytes_per_frame;
+    uint8_t *dst = out + (long long)frame * bytes_per_frame;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const long long nvec = bytes_per_frame >> 4;
+        for (long long v = i; v < nvec; v += stride) {
+            uint4 w = reinterpret_cast<const uint4 *>(src)[v];
+            uint32_t *pw = reinterpret_cast<uint32_t *>(&w);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                pw[k] = lut[pw[k] & 0xff] | (lut[(pw[k] >> 8) & 0xff] << 8) | (lut[(pw[k] >> 16) & 0xff] << 16) |
+                        (lut[pw[k] >> 24] << 24);
+            reinterpret_cast<uint4 *>(dst)[v] = w;
+        }
+        for (long long b = (nvec << 4) + i; b < bytes_per_frame; b += stride) dst[b] = lut[src[b]];
+    } else {
+        for (long long b = i; b < bytes_per_frame; b += stride) dst[b] = lut[src[b]];
+    }
+}
+
+// Per-video aggregation: out[g] = combine(records[g*group .. (g+1)*group)). One CTA per group, 786 32-bit words.
+__global__ void __launch_bounds__(256) ela_reduce_kernel(const v5ela_record *recs, int group, v5ela_record *out)
+{
+    const v5ela_record *src = recs + (long long)blockIdx.x * group;
+    v5ela_record &dst = out[blockIdx.x];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        uint32_t s = 0;
+        for (int k = 0; k < group; k++) s += (&src[k].ela_hist[0][0])[i];
+        (&dst.ela_hist[0][0])[i] = s;
+    }
+    if (threadIdx.x < 8) {                 // ela_sum[3], ela_sumsq[3], tex_sumabs, tex_sumsq are 8 consecutive u64
+        unsigned long long s = 0;
+        for (int k = 0; k < group; k++) s += (&src[k].ela_sum[0])[threadIdx.x];
+        (&dst.ela_sum[0])[threadIdx.x] = s;
+    } else if (threadIdx.x == 8) {
+        int m = 0;
+        for (int k = 0; k < group; k++) m = max(m, (int)src[k].tex_maxabs);
+        dst.tex_maxabs = (uint16_t)m;
+    } else if (threadIdx.x >= 9 && threadIdx.x < 12) {
+        const int c = threadIdx.x - 9;
+        int m = 0;
+        for (int k = 0; k < group; k++) m = max(m, (int)src[k].ela_max[c]);
+        dst.ela_max[c] = (uint8_t)m;
+        dst.pad[c] = 0;
+    }
+}
+
+}  // namespace v5
+
+// ======================================================================================================= C ABI
+struct v5ela_handle {
+    int device = 0;
+    int quality = 90;
+    int sm_count = 0;
+    int seg_rows = 0;                      // 0 = default
+    int ctas_per_sm = 2;
+    int64_t launches = 0;
+    cudaStream_t own_stream = nullptr;     // used by v5ela_analyze_host
+    uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
+    void *d_rec = nullptr;
+    size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
+    uint16_t luma[64], chroma[64];
+    char err[512] = {0};
+};
+
+namespace {
+
+int fail(v5ela_handle *h, int code, const char *fmt, const char *detail = "")
+{
+    if (h) snprintf(h->err, sizeof(h->err), fmt, detail);
+    return code;
+}
+
+#define V5_CUDA(h, call)                                                                    \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) return fail((h), V5ELA_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure(v5ela_handle *h, void **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    V5_CUDA(h, cudaMalloc(ptr, need));
+    *cap = need;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int v5ela_abi_version(void) { return V5ELA_ABI_VERSION; }
+size_t v5ela_record_bytes(void) { return sizeof(v5ela_record); }
+
+const char *v5ela_status_string(int status)
+{
+    switch (status) {
+        case V5ELA_OK: return "ok";
+        case V5ELA_ERR_INVALID: return "invalid argument";
+        case V5ELA_ERR_CUDA: return "CUDA error";
+        case V5ELA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case V5ELA_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+int v5ela_create(int device, v5ela_handle **out)
+{
+    if (!out) return V5ELA_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return V5ELA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return V5ELA_ERR_NO_DEVICE;
+    if (prop.major != 10) return V5ELA_ERR_NO_DEVICE;       // the library carries sm_100a SASS only
+    v5ela_handle *h = new (std::nothrow) v5ela_handle();
+    if (!h) return V5ELA_ERR_NOMEM;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    v5::quant_tables(h->quality, h->luma, h->chroma);
+    DeviceGuard guard(device);
+    if (cudaFuncSetAttribute(v5::ela_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(v5::Smem)) != cudaSuccess) {
+        delete h;
+        return V5ELA_ERR_CUDA;
+    }
+    const char *env = getenv("V5ELA_SEG_ROWS");
+    if (env) h->seg_rows = atoi(env);
+    *out = h;
+    return V5ELA_OK;
+}
+
+int v5ela_destroy(v5ela_handle *h)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaFree(h->d_in);
+    cudaFree(h->d_res);
+    cudaFree(h->d_enh);
+    cudaFree(h->d_rec);
+    delete h;
+    return V5ELA_OK;
+}
+
+const char *v5ela_last_error(const v5ela_handle *h) { return h ? h->err : "null handle"; }
+
+int v5ela_set_quality(v5ela_handle *h, int quality)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (quality < 1 || quality > 100) return fail(h, V5ELA_ERR_INVALID, "quality must be in 1..100%s");
+    h->quality = quality;
+    v5::quant_tables(quality, h->luma, h->chroma);
+    return V5ELA_OK;
+}
+
+int v5ela_get_quality(const v5ela_handle *h) { return h ? h->quality : V5ELA_ERR_INVALID; }
+
+int v5ela_get_quant_tables(const v5ela_handle *h, uint16_t luma_host[64], uint16_t chroma_host[64])
+{
+    if (!h || !luma_host || !chroma_host) return V5ELA_ERR_INVALID;
+    memcpy(luma_host, h->luma, sizeof(h->luma));
+    memcpy(chroma_host, h->chroma, sizeof(h->chroma));
+    return V5ELA_OK;
+}
+
+int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width, int64_t frame_stride_bytes,
+                  int64_t row_stride_bytes, void *d_records, uint8_t *d_residual, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    v5::KParams p;
+    if (v5::fill_params(p, d_rgb, n, height, width, frame_stride_bytes, row_stride_bytes,
+                        static_cast<v5ela_record *>(d_records), d_residual, h->quality, h->seg_rows) != 0)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: bad pointer, size or stride%s");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const long long total = (long long)n * p.n_strips * p.n_segs;
+    if (total > 0x7fffffffLL) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: batch too large%s");
+    V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
+    const int max_ctas = h->sm_count * h->ctas_per_sm;
+    const int grid = total < max_ctas ? (int)total : max_ctas;
+    v5::ela_fused_kernel<<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    V5_CUDA(h, cudaGetLastError());
+    v5::ela_finalize_kernel<<<n, 96, 0, st>>>(static_cast<v5ela_record *>(d_records), n);
+    V5_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    return V5ELA_OK;
+}
+
+int v5ela_enhance(v5ela_handle *h, const uint8_t *d_residual, const void *d_records, int n, int height, int width,
+                  uint8_t *d_enhanced, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!d_residual || !d_records || !d_enhanced || n < 0 || height <= 0 || width <= 0)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_enhance: bad pointer or size%s");
+    DeviceGuard guard(h->device);
+    const long long bytes = (long long)height * width * 3;
+    long long bx = (bytes / 16 + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 4LL * h->sm_count) bx = 4LL * h->sm_count;
+    if (n > 65535) return fail(h, V5ELA_ERR_INVALID, "v5ela_enhance: more than 65535 frames per call%s");
+    v5::ela_enhance_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_residual, static_cast<const v5ela_record *>(d_records), d_enhanced, bytes);
+    V5_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return V5ELA_OK;
+}
+
+int v5ela_reduce_records(v5ela_handle *h, const void *d_records, int n, int group, void *d_out, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!d_records || !d_out || n < 0 || group <= 0 || n % group != 0)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_reduce_records: n must be a positive multiple of group%s");
+    DeviceGuard guard(h->device);
+    v5::ela_reduce_kernel<<<n / group, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const v5ela_record *>(d_records), group, static_cast<v5ela_record *>(d_out));
+    V5_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return V5ELA_OK;
+}
+
+int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int height, int width, void *records_host,
+                       uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!rgb_host || !records_host || n < 0 || height <= 0 || width <= 0)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_host: bad pointer or size%s");
+    DeviceGuard guard(h->device);
+    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    const size_t fbytes = (size_t)height * width * 3, in_bytes = fbytes * n, rec_bytes = sizeof(v5ela_record) * (size_t)n;
+    const bool want_map = residual_host_or_null || enhanced_host_or_null;
+    int rc;
+    if ((rc = ensure(h, (void **)&h->d_in, &h->d_in_cap, in_bytes))) return rc;
+    if ((rc = ensure(h, &h->d_rec, &h->d_rec_cap, rec_bytes))) return rc;
+    if (want_map && (rc = ensure(h, (void **)&h->d_res, &h->d_res_cap, in_bytes))) return rc;
+    if (enhanced_host_or_null && (rc = ensure(h, (void **)&h->d_enh, &h->d_enh_cap, in_bytes))) return rc;
+    cudaStream_t st = h->own_stream;
+    V5_CUDA(h, cudaMemcpyAsync(h->d_in, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = v5ela_analyze(h, h->d_in, n, height, width, (int64_t)fbytes, (int64_t)width * 3, h->d_rec,
+                       want_map ? h->d_res : nullptr, st);
+    if (rc) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(records_host, h->d_rec, rec_bytes, cudaMemcpyDeviceToHost, st));
+    if (residual_host_or_null)
+        V5_CUDA(h, cudaMemcpyAsync(residual_host_or_null, h->d_res, in_bytes, cudaMemcpyDeviceToHost, st));
+    if (enhanced_host_or_null) {
+        rc = v5ela_enhance(h, h->d_res, h->d_rec, n, height, width, h->d_enh, st);
+        if (rc) return rc;
+        V5_CUDA(h, cudaMemcpyAsync(enhanced_host_or_null, h->d_enh, in_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    V5_CUDA(h, cudaStreamSynchronize(st));
+    return V5ELA_OK;
+}
+
+int64_t v5ela_launch_count(const v5ela_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// v5ela_host.h — host-side set-up shared by the C-ABI (v5ela.cu) and the CPU thread emulator (tests/emu).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "v5ela_device.cuh"
+
+namespace v5 {
+
+// JPEG Annex K.1 / K.2 base tables in natural (row-major) order, scaled like libjpeg's jpeg_set_quality with
+// force_baseline — what `Image.save(..., 'JPEG', quality=q)` uses (v5_texture_ela.py:67).
+inline void quant_tables(int quality, uint16_t luma[64], uint16_t chroma[64])
+{
+    static const uint8_t base_l[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                       14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                       18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                       49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const uint8_t base_c[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                       24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99};
+    const int q = quality < 1 ? 1 : (quality > 100 ? 100 : quality);
+    const int scale = q < 50 ? 5000 / q : 200 - 2 * q;
+    for (int i = 0; i < 64; i++) {
+        const int bl = base_l[i], bc = i < 32 ? base_c[i] : 99;
+        int l = (bl * scale + 50) / 100, c = (bc * scale + 50) / 100;
+        luma[i] = (uint16_t)(l < 1 ? 1 : (l > 255 ? 255 : l));
+        chroma[i] = (uint16_t)(c < 1 ? 1 : (c > 255 ? 255 : c));
+    }
+}
+
+// Work decomposition: frames x strips (<= TW_MAX MCUs wide, balanced) x vertical segments of about `seg_rows` MCU rows.
+// seg_rows <= 0 picks the default. Returns 0 or -1 on invalid arguments.
+inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int64_t frame_stride, int64_t row_stride,
+                       v5ela_record *records, uint8_t *residual, int quality, int seg_rows)
+{
+    if (!rgb || !records || n <= 0 || h <= 0 || w <= 0) return -1;
+    if (row_stride < (int64_t)3 * w || (n > 1 && frame_stride < row_stride * (int64_t)h)) return -1;
+    if (quality < 1 || quality > 100) return -1;
+    if ((int64_t)h > 65536 || (int64_t)w > 65536) return -1;
+    memset(&p, 0, sizeof(p));
+    p.rgb = rgb;
+    p.frame_stride = frame_stride;
+    p.row_stride = row_stride;
+    p.records = records;
+    p.residual = residual;
+    p.n = n;
+    p.h = h;
+    p.w = w;
+    p.mw = (w + 15) / 16;
+    p.mh = (h + 15) / 16;
+    p.n_strips = (p.mw + TW_MAX - 1) / TW_MAX;
+    if (seg_rows <= 0) seg_rows = 17;
+    p.n_segs = (p.mh + seg_rows - 1) / seg_rows;
+    p.vec_ok = ((reinterpret_cast<uintptr_t>(rgb) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15) == 0;
+    p.resid_vec_ok = residual && ((reinterpret_cast<uintptr_t>(residual) | (uintptr_t)(3 * w)) & 15) == 0;
+    uint16_t ql[64], qc[64];
+    quant_tables(quality, ql, qc);
+    make_quant(ql, p.q[0]);
+    make_quant(qc, p.q[1]);
+    return 0;
+}
+
+// ela_sum / ela_sumsq / ela_max follow from the histogram (host mirror of finalize_kernel, used by the emulator).
+inline void finalize_record(v5ela_record &r)
+{
+    for (int c = 0; c < 3; c++) {
+        uint64_t s = 0, sq = 0;
+        int mx = 0;
+        for (int b = 0; b < 256; b++) {
+            const uint64_t cnt = r.ela_hist[c][b];
+            s += cnt * (uint64_t)b;
+            sq += cnt * (uint64_t)(b * b);
+            if (cnt) mx = b;
+        }
+        r.ela_sum[c] = s;
+        r.ela_sumsq[c] = sq;
+        r.ela_max[c] = (uint8_t)mx;
+    }
+}
+
+}  // namespace v5

@@ -1,0 +1,117 @@
+// v5ela_workitem.cuh — the per-work-item band loop shared by the CUDA kernel and the CPU thread emulator (tests/emu).
+//
+// V5_FOR_THREADS(body) runs `body` for every thread of the CTA and ends with a CTA-wide barrier:
+//   device : body executes once with tid = threadIdx.x, then __syncthreads()
+//   emu    : body executes NT times in a loop (one pass per emulated thread) — the barrier is the loop end.
+// Per-thread state that must survive a barrier lives in `acc` (a register struct on the device, an array in the emulator).
+#pragma once
+#include "v5ela_device.cuh"
+
+namespace v5 {
+
+#ifdef __CUDA_ARCH__
+#define V5_FOR_THREADS(...)                  \
+    {                                        \
+        const int tid = (int)threadIdx.x;    \
+        ThreadAcc &acc = acc_store[0];       \
+        (void)acc;                           \
+        __VA_ARGS__;                         \
+    }                                        \
+    __syncthreads();
+#else
+#define V5_FOR_THREADS(...)                  \
+    for (int tid = 0; tid < NT; tid++) {     \
+        ThreadAcc &acc = acc_store[tid];     \
+        (void)acc;                           \
+        __VA_ARGS__;                         \
+    }
+#endif
+
+// End of a work item: per-thread texture partials -> shared memory, then shared memory -> the frame's record with
+// global atomics (<= 768 + 3 per CTA per work item). tex_maxabs is a uint16 field; while the fused kernel runs, the
+// aligned 32-bit word that starts at it (its upper half, ela_max[0..1], is still zero) is the atomicMax target — the
+// finalize kernel writes ela_max afterwards.
+#ifdef __CUDA_ARCH__
+V5_DEV void flush_partials(int tid, Smem &S, ThreadAcc &acc)
+{
+    unsigned long long sq = acc.tex_sumsq, sa = acc.tex_sumabs;
+    uint32_t mx = acc.tex_maxabs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd(&S.tex_sumsq, sq);
+        atomicAdd(&S.tex_sumabs, sa);
+        atomicMax(&S.tex_maxabs, mx);
+    }
+}
+V5_DEV void flush_global(int tid, Smem &S, v5ela_record *rec)
+{
+    for (int i = tid; i < 3 * 256; i += NT) {
+        const uint32_t c = (&S.hist[0][0])[i];
+        if (c) atomicAdd(&rec->ela_hist[0][0] + i, c);
+    }
+    if (tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&rec->tex_sumabs), S.tex_sumabs);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&rec->tex_sumsq), S.tex_sumsq);
+        atomicMax(reinterpret_cast<uint32_t *>(&rec->tex_maxabs), S.tex_maxabs);
+    }
+}
+#else
+inline void flush_partials(int, Smem &S, ThreadAcc &acc)
+{
+    S.tex_sumsq += acc.tex_sumsq;
+    S.tex_sumabs += acc.tex_sumabs;
+    if (acc.tex_maxabs > S.tex_maxabs) S.tex_maxabs = acc.tex_maxabs;
+}
+inline void flush_global(int tid, Smem &S, v5ela_record *rec)
+{
+    for (int i = tid; i < 3 * 256; i += NT) (&rec->ela_hist[0][0])[i] += (&S.hist[0][0])[i];
+    if (tid == 0) {
+        rec->tex_sumabs += S.tex_sumabs;
+        rec->tex_sumsq += S.tex_sumsq;
+        if (S.tex_maxabs > rec->tex_maxabs) rec->tex_maxabs = (uint16_t)S.tex_maxabs;
+    }
+}
+#endif
+
+V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *acc_store)
+{
+    Geo g;
+    int frame;
+    make_geo(p, work, g, frame);
+
+    V5_FOR_THREADS({
+        for (int i = tid; i < 3 * 256; i += NT) (&S.hist[0][0])[i] = 0;
+        if (tid == 0) {
+            S.tex_sumabs = 0;
+            S.tex_sumsq = 0;
+            S.tex_maxabs = 0;
+        }
+        acc.tex_sumabs = 0;
+        acc.tex_sumsq = 0;
+        acc.tex_maxabs = 0;
+    })
+
+    // Bands r0-1 and r1 only contribute decoded chroma / original luma to the rows next to them.
+    const int r_first = g.r0 > 0 ? g.r0 - 1 : 0;
+    for (int r = r_first; r <= g.r1; r++) {
+        const bool has_band = r < p.mh;
+        const bool want_y = r >= g.r0 && r < g.r1;
+        if (!has_band && 16 * r - 1 >= p.h) break;          // nothing left below the image
+        if (has_band) {
+            V5_FOR_THREADS(stage_load(tid, S, p, g, r))
+            V5_FOR_THREADS(stage_convert(tid, S, p, g, r))
+            V5_FOR_THREADS(stage_blocks(tid, S, p, g, r, want_y))
+        }
+        V5_FOR_THREADS(stage_residual(tid, S, p, g, acc, r))
+    }
+
+    V5_FOR_THREADS(flush_partials(tid, S, acc))
+    V5_FOR_THREADS(flush_global(tid, S, p.records + frame))
+}
+
+}  // namespace v5

@@ -1,0 +1,24 @@
+"""v5ela — B200-native ELA + texture features for fake-video-detection-engine's V5 node.
+
+Public surface:
+  analyze_batch(frames_u8[N,H,W,3] on cuda) -> {"records", ["residual"], ["enhanced"]}   (v5ela.batch)
+  reduce_records(records, group)                                                           (v5ela.batch)
+  as_records / features / combine                                                          (v5ela.records)
+  gen_frame / gen_batch / gen_batch_torch  (synthetic keyframes)        (v5ela.synth)
+  shard_range / analyze_sharded            (multi-GPU, one process per GPU, NCCL gather)   (v5ela.shard)
+The drop-in node lives in ``nodes/V_nodes/v5_texture_ela.py`` next to this package.
+"""
+from .records import RECORD_BYTES, RECORD_DTYPE, as_records, combine, features  # noqa: F401
+from .synth import gen_batch, gen_batch_torch, gen_frame  # noqa: F401
+
+
+def __getattr__(name):  # lazy: importing the package must not require the CUDA library (CPU-only tooling, tests)
+    if name in ("analyze_batch", "reduce_records", "get_handle"):
+        from . import batch
+
+        return getattr(batch, name)
+    if name in ("shard_range", "analyze_sharded", "gather_records"):
+        from . import shard
+
+        return getattr(shard, name)
+    raise AttributeError(name)

@@ -1,0 +1,133 @@
+"""ctypes binding of libv5ela.so (include/v5ela.h). No CPU fallback: a missing or unloadable library is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libv5ela.so")
+
+# Every symbol include/v5ela.h declares; tests assert the built library exports exactly these.
+EXPORTS = (
+    "v5ela_abi_version", "v5ela_record_bytes", "v5ela_status_string", "v5ela_create", "v5ela_destroy",
+    "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze",
+    "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count",
+)
+
+
+class V5ElaError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"v5ela error {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libv5ela.so, building it in-tree with nvcc when it is absent. Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+
+        _build.build_library()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # loud: there is no other implementation to fall back to
+        raise ImportError(f"cannot load {LIB_PATH}: {e}. Build it with `python __graft_entry__.py` "
+                          f"(nvcc -gencode arch=compute_100a,code=sm_100a).") from e
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.v5ela_abi_version.restype = i32
+    lib.v5ela_record_bytes.restype = ctypes.c_size_t
+    lib.v5ela_status_string.restype = ctypes.c_char_p
+    lib.v5ela_status_string.argtypes = [i32]
+    lib.v5ela_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.v5ela_destroy.argtypes = [vp]
+    lib.v5ela_last_error.restype = ctypes.c_char_p
+    lib.v5ela_last_error.argtypes = [vp]
+    lib.v5ela_set_quality.argtypes = [vp, i32]
+    lib.v5ela_get_quality.argtypes = [vp]
+    lib.v5ela_get_quant_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16)]
+    lib.v5ela_analyze.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
+    lib.v5ela_enhance.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.v5ela_reduce_records.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.v5ela_launch_count.restype = i64
+    lib.v5ela_launch_count.argtypes = [vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ("v5ela_abi_version",):
+            fn.restype = i32
+    if lib.v5ela_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.v5ela_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+class Handle:
+    """Owns one v5ela_handle (one CUDA device, one thread)."""
+
+    def __init__(self, device: int = 0, quality: int = 90):
+        self._lib = load()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.v5ela_create(int(device), ctypes.byref(self._h))
+        if rc != 0:
+            raise V5ElaError(rc, self._lib.v5ela_status_string(rc).decode())
+        self.device = int(device)
+        self._quality = 90
+        if quality != 90:
+            self.set_quality(quality)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.v5ela_last_error(self._h).decode() or self._lib.v5ela_status_string(rc).decode()
+            raise V5ElaError(rc, msg)
+
+    @property
+    def quality(self) -> int:
+        return self._quality
+
+    def set_quality(self, quality: int):
+        self._check(self._lib.v5ela_set_quality(self._h, int(quality)))
+        self._quality = int(quality)
+
+    def quant_tables(self):
+        import numpy as np
+
+        lu, ch = np.zeros(64, np.uint16), np.zeros(64, np.uint16)
+        u16p = ctypes.POINTER(ctypes.c_uint16)
+        self._check(self._lib.v5ela_get_quant_tables(self._h, lu.ctypes.data_as(u16p), ch.ctypes.data_as(u16p)))
+        return lu.reshape(8, 8), ch.reshape(8, 8)
+
+    def analyze(self, d_rgb: int, n: int, h: int, w: int, frame_stride: int, row_stride: int, d_records: int,
+                d_residual: int | None, stream: int | None):
+        self._check(self._lib.v5ela_analyze(self._h, d_rgb, n, h, w, frame_stride, row_stride, d_records,
+                                            d_residual or None, stream or None))
+
+    def enhance(self, d_residual: int, d_records: int, n: int, h: int, w: int, d_enhanced: int, stream: int | None):
+        self._check(self._lib.v5ela_enhance(self._h, d_residual, d_records, n, h, w, d_enhanced, stream or None))
+
+    def reduce_records(self, d_records: int, n: int, group: int, d_out: int, stream: int | None):
+        self._check(self._lib.v5ela_reduce_records(self._h, d_records, n, group, d_out, stream or None))
+
+    def analyze_host(self, rgb_host: int, n: int, h: int, w: int, records_host: int, residual_host: int | None = None,
+                     enhanced_host: int | None = None):
+        self._check(self._lib.v5ela_analyze_host(self._h, rgb_host, n, h, w, records_host, residual_host or None,
+                                                 enhanced_host or None))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.v5ela_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.v5ela_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,85 @@
+"""Batch entry point: ``analyze_batch(frames_u8[N,H,W,3]) -> records (+ residual / enhanced maps)`` on one B200.
+
+PyTorch is plumbing here (device memory, streams); the work is one call into libv5ela.so (include/v5ela.h).
+There is no CPU path: tensors must live on a CUDA device and the library must load.
+"""
+from __future__ import annotations
+
+import threading
+
+from . import _abi
+from .records import RECORD_BYTES
+
+_tls = threading.local()
+
+
+def get_handle(device_index: int) -> "_abi.Handle":
+    """One library handle per (thread, device); handles are not thread-safe (include/v5ela.h)."""
+    cache = getattr(_tls, "handles", None)
+    if cache is None:
+        cache = _tls.handles = {}
+    h = cache.get(device_index)
+    if h is None:
+        h = cache[device_index] = _abi.Handle(device_index)
+    return h
+
+
+def analyze_batch(frames, quality: int = 90, want_residual: bool = False, want_enhanced: bool = False,
+                  records_out=None, residual_out=None, handle=None):
+    """Run the fused ELA + texture kernel over a batch of RGB frames.
+
+    frames : torch.uint8 CUDA tensor, shape (N, H, W, 3), innermost two dims dense (row/frame strides may be padded).
+    Returns a dict: ``records`` uint8 (N, 3144) on the same device (view with ``records.as_records`` on the host),
+    and, when asked, ``residual`` (= the reference's ``diff``, v5_texture_ela.py:70) and ``enhanced``
+    (= ``ImageEnhance.Brightness(diff).enhance(scale)``, v5…:78), both uint8 (N, H, W, 3).
+    Asynchronous on torch's current stream.
+    """
+    import torch
+
+    if not isinstance(frames, torch.Tensor) or frames.dtype != torch.uint8:
+        raise TypeError("frames must be a torch.uint8 tensor")
+    if frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError("frames must have shape (N, H, W, 3)")
+    if not frames.is_cuda:
+        raise ValueError("frames must be a CUDA tensor (this path has no CPU implementation)")
+    if frames.stride(3) != 1 or frames.stride(2) != 3:
+        frames = frames.contiguous()
+    n, h, w, _ = frames.shape
+    dev = frames.device
+    hd = handle or get_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    if hd.quality != quality:
+        hd.set_quality(quality)
+    records = records_out if records_out is not None else torch.empty((n, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    out = {"records": records}
+    residual = None
+    if want_residual or want_enhanced:
+        residual = residual_out if residual_out is not None else torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    if n == 0 or h == 0 or w == 0:
+        if residual is not None:
+            out["residual"] = residual
+            if want_enhanced:
+                out["enhanced"] = torch.empty_like(residual)
+        return out
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    hd.analyze(frames.data_ptr(), n, h, w, frames.stride(0), frames.stride(1), records.data_ptr(),
+               residual.data_ptr() if residual is not None else None, stream)
+    if residual is not None:
+        out["residual"] = residual
+    if want_enhanced:
+        enhanced = torch.empty_like(residual)
+        hd.enhance(residual.data_ptr(), records.data_ptr(), n, h, w, enhanced.data_ptr(), stream)
+        out["enhanced"] = enhanced
+    return out
+
+
+def reduce_records(records, group: int, handle=None):
+    """Per-video aggregation on the device: (N, 3144) -> (N // group, 3144)."""
+    import torch
+
+    n = records.shape[0]
+    dev = records.device
+    hd = handle or get_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    out = torch.empty((n // group, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    if n:
+        hd.reduce_records(records.data_ptr(), n, group, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    return out

@@ -1,0 +1,129 @@
+/*
+ * include/v5ela.h — C ABI of libv5ela.so: the B200 (sm_100a) implementation of the V5 texture/ELA hot path of
+ * MrBottleTree/fake-video-detection-engine.
+ *
+ * The reference has no FFI for this path (it is pure Python); its only interface is the LangGraph node callable
+ * `run(state)` (nodes/V_nodes/v5_texture_ela.py:13, registered at main.py:304). This ABI is what the replacement
+ * node module binds with ctypes (fake-video-detection-engine_b200/v5ela/_abi.py; INTEGRATION.md shows the stub).
+ * Each entry point cites the reference lines whose work it takes over.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative v5ela_status; no exceptions
+ * cross the boundary; v5ela_last_error() gives a handle-owned message. All image/record pointers are DEVICE
+ * pointers owned by the caller unless the name says `host`. Calls are asynchronous on the given CUDA stream and do
+ * not synchronise or allocate after the first call at a given geometry. A handle is bound to one device and is not
+ * thread-safe; the library is (one handle per thread).
+ */
+#ifndef V5ELA_H
+#define V5ELA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V5ELA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define V5ELA_API __attribute__((visibility("default")))
+#else
+#define V5ELA_API
+#endif
+
+typedef enum {
+    V5ELA_OK = 0,
+    V5ELA_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, bad stride, quality outside 1..100) */
+    V5ELA_ERR_CUDA = -2,        /* a CUDA runtime call failed; see v5ela_last_error */
+    V5ELA_ERR_NO_DEVICE = -3,   /* no CUDA device / device is not compute capability 10.x */
+    V5ELA_ERR_NOMEM = -4
+} v5ela_status;
+
+/*
+ * Per-frame feature record "V5F v1" (SURVEY.md §8a), 3144 bytes, little endian, no implicit padding.
+ *   ela_*   : statistics of the residual |orig - jpeg_roundtrip(orig, q)| per RGB channel.
+ *             max over channels of ela_max is the reference's `max_diff` before its 0 -> 1 fix
+ *             (v5_texture_ela.py:72-75); 255.0/max is its `scale` (v5…:76).
+ *   tex_*   : statistics of L = Laplacian(Y) (kernel [0 1 0; 1 -4 1; 0 1 0], BORDER_REFLECT_101) on the libjpeg luma
+ *             of the original frame — build-defined high-pass texture response (north_star), oracle =
+ *             cv2.Laplacian(Y, CV_16S, ksize=1).
+ */
+typedef struct v5ela_record {
+    uint32_t ela_hist[3][256];  /* np.bincount(residual[..., c]) */
+    uint64_t ela_sum[3];        /* sum of residual values */
+    uint64_t ela_sumsq[3];      /* sum of squared residual values */
+    uint64_t tex_sumabs;        /* sum |L| */
+    uint64_t tex_sumsq;         /* sum L^2 */
+    uint16_t tex_maxabs;        /* max |L| */
+    uint8_t  ela_max[3];        /* max residual per channel */
+    uint8_t  pad[3];
+} v5ela_record;
+
+typedef struct v5ela_handle v5ela_handle;
+
+/* Library identification. */
+V5ELA_API int         v5ela_abi_version(void);
+V5ELA_API size_t      v5ela_record_bytes(void);                       /* == sizeof(v5ela_record) == 3144 */
+V5ELA_API const char *v5ela_status_string(int status);
+
+/* Handle life cycle. `device` is a CUDA ordinal. The handle owns quantisation tables and a small workspace. */
+V5ELA_API int         v5ela_create(int device, v5ela_handle **out);
+V5ELA_API int         v5ela_destroy(v5ela_handle *h);
+V5ELA_API const char *v5ela_last_error(const v5ela_handle *h);
+
+/*
+ * JPEG quality of the simulated re-encode. Replaces the literal in `original.save(path, 'JPEG', quality=90)`
+ * (v5_texture_ela.py:67): builds libjpeg's Annex-K tables scaled by `quality` (1..100, baseline-forced) and the exact
+ * reciprocal constants the kernel divides with. Default after create: 90.
+ */
+V5ELA_API int v5ela_set_quality(v5ela_handle *h, int quality);
+V5ELA_API int v5ela_get_quality(const v5ela_handle *h);
+/* Copies the 64+64 table entries (natural order) to HOST arrays; what PIL reports as Image.quantization. */
+V5ELA_API int v5ela_get_quant_tables(const v5ela_handle *h, uint16_t luma_host[64], uint16_t chroma_host[64]);
+
+/*
+ * The hot path. For each of `n` RGB frames (uint8, HWC, `row_stride_bytes` between rows, `frame_stride_bytes`
+ * between frames) performs, in one fused kernel, what the reference does with
+ *   original.save(tmp, 'JPEG', quality=q); compressed = Image.open(tmp)      v5_texture_ela.py:66-68
+ *   diff = ImageChops.difference(original, compressed)                       v5_texture_ela.py:70
+ *   extrema = diff.getextrema(); max_diff = max(...)                         v5_texture_ela.py:72-73
+ * i.e. libjpeg's RGB->YCbCr, h2v2 chroma downsample, 8x8 ISLOW forward DCT, quantise, dequantise, ISLOW inverse DCT,
+ * h2v2 fancy upsample, YCbCr->RGB, abs-diff — bit-exact — and reduces the residual and the luma Laplacian into one
+ * v5ela_record per frame.
+ *   d_records  : n x sizeof(v5ela_record) bytes, overwritten.
+ *   d_residual : optional (may be NULL): n x h x w x 3 tightly packed residual map (`diff`).
+ * No host synchronisation; ordering follows `cuda_stream` (a cudaStream_t passed as void*; NULL = legacy default).
+ */
+V5ELA_API int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width,
+                  int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                  void *d_records, uint8_t *d_residual, void *cuda_stream);
+
+/*
+ * Brightness enhancement of the residual map: `ImageEnhance.Brightness(diff).enhance(255.0 / max_diff)`
+ * (v5_texture_ela.py:74-78) == u8(trunc(f32(x) * f32(scale))) clipped, with max_diff read per frame from the records
+ * produced by v5ela_analyze on the same stream (0 -> 1 fix applied). d_enhanced may alias d_residual.
+ */
+V5ELA_API int v5ela_enhance(v5ela_handle *h, const uint8_t *d_residual, const void *d_records, int n, int height, int width,
+                  uint8_t *d_enhanced, void *cuda_stream);
+
+/*
+ * Per-group aggregation of records (per-video features, BASELINE.json config 4): out[g] = sum of histograms and sums,
+ * max of maxima over records [g*group, (g+1)*group). n must be a multiple of `group`. d_out: (n/group) records.
+ */
+V5ELA_API int v5ela_reduce_records(v5ela_handle *h, const void *d_records, int n, int group, void *d_out, void *cuda_stream);
+
+/*
+ * Convenience for callers without a CUDA runtime of their own (the drop-in node, the e2e benchmark): same as
+ * v5ela_analyze but with HOST buffers; copies in on the handle's stream, runs, copies records (and the optional
+ * residual / enhanced maps) back, and synchronises before returning. Host buffers should be pinned for full speed.
+ */
+V5ELA_API int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int height, int width,
+                       void *records_host, uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null);
+
+/* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches evidence). */
+V5ELA_API int64_t v5ela_launch_count(const v5ela_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V5ELA_H */

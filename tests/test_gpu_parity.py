@@ -1,0 +1,222 @@
+"""GPU: the CUDA path (through the C ABI, via v5ela.analyze_batch) against the oracle and the reference goldens.
+
+Bar: residual maps, histograms and every integer record field bit-exact; derived float statistics within 1e-5 relative
+(they are computed in float64 from identical integers, so they are in fact equal).
+"""
+import numpy as np
+import pytest
+
+from helpers import golden_frame, load_json, record_matches_golden, sha
+from oracle import c_oracle, pil_oracle
+from v5ela.records import as_records, features
+from v5ela.synth import gen_batch, gen_batch_torch, gen_frame
+
+pytestmark = pytest.mark.gpu
+
+FRAMES = load_json("frames_golden.json")
+
+
+def run_gpu(frames_np, q=90, **kw):
+    import torch
+    import v5ela
+
+    t = torch.from_numpy(np.ascontiguousarray(frames_np)).cuda()
+    out = v5ela.analyze_batch(t, quality=q, want_residual=True, **kw)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["records"] = as_records(res["records"])
+    return res
+
+
+def test_native_library_is_loaded():
+    import torch
+    from v5ela import _abi
+
+    lib = _abi.load()
+    assert lib.v5ela_record_bytes() == 3144
+    with open("/proc/self/maps") as f:
+        assert "libv5ela.so" in f.read()
+    h = _abi.Handle(torch.cuda.current_device())
+    lu, ch = h.quant_tables()
+    assert lu[0].tolist() == [3, 2, 2, 3, 5, 8, 10, 12] and ch[0].tolist() == [3, 4, 5, 9, 20, 20, 20, 20]  # q=90, A.1
+    h.close()
+
+
+@pytest.mark.parametrize("case", FRAMES["cases"], ids=lambda c: f"{c['spec'][0]}{c['spec'][1]}_{c['h']}x{c['w']}_q{c['q']}")
+def test_reference_goldens(case):
+    frame = golden_frame(case)
+    out = run_gpu(frame[None], case["q"], want_enhanced=True)
+    assert sha(out["residual"][0]) == case["resid_sha"]
+    assert record_matches_golden(out["records"][0], case) == []
+    assert sha(out["enhanced"][0]) == case["enhanced_sha"]
+
+
+def test_small_batch_vs_oracle_all_fields():
+    frames = gen_batch(10, 6, 211, 173, seed=3)
+    out = run_gpu(frames, 90)
+    recs, resid = c_oracle.analyze(frames, 90, want_residual=True)
+    assert np.array_equal(out["residual"], resid)
+    assert out["records"].tobytes() == recs.tobytes()
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (1, 2), (2, 1), (2, 3), (3, 4), (4, 5), (7, 7), (8, 9), (15, 17), (16, 16), (17, 33),
+                                (32, 48), (33, 497), (500, 31), (100, 1000), (271, 481), (16, 512), (48, 960), (49, 961)])
+@pytest.mark.parametrize("q", [90, 30])
+def test_ragged_sizes_vs_oracle(hw, q):
+    h, w = hw
+    rng = np.random.default_rng(h * 1000 + w)
+    frames = np.stack([gen_frame(4, h, w, 9), rng.integers(0, 256, (h, w, 3), dtype=np.uint8)])
+    out = run_gpu(frames, q)
+    recs, resid = c_oracle.analyze(frames, q, want_residual=True)
+    assert np.array_equal(out["residual"], resid)
+    assert out["records"].tobytes() == recs.tobytes()
+
+
+@pytest.mark.parametrize("q", [1, 10, 50, 75, 85, 90, 95, 100])
+def test_quality_sweep_vs_pil(q):
+    frame = gen_frame(2, 270, 480, 1)
+    out = run_gpu(frame[None], q)
+    rec, resid = pil_oracle.record(frame, q, with_residual=True)
+    assert np.array_equal(out["residual"][0], resid)
+    assert out["records"][0].tobytes() == rec.tobytes()
+
+
+def test_padded_strides_and_unaligned_views():
+    import torch
+    import v5ela
+
+    base = torch.from_numpy(gen_batch(0, 3, 100, 150, seed=2)).cuda()
+    big = torch.zeros((3, 120, 170, 3), dtype=torch.uint8, device="cuda")
+    big[:, 7:107, 5:155] = base
+    view = big[:, 7:107, 5:155]                                  # padded row/frame strides, unaligned start
+    out = v5ela.analyze_batch(view, want_residual=True)
+    ref = v5ela.analyze_batch(base, want_residual=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out["residual"], ref["residual"]) and torch.equal(out["records"], ref["records"])
+    recs, resid = c_oracle.analyze(base.cpu().numpy(), 90, want_residual=True)
+    assert np.array_equal(ref["residual"].cpu().numpy(), resid)
+
+
+def test_records_only_mode_equals_residual_mode():
+    import torch
+    import v5ela
+
+    t = gen_batch_torch(0, 4, 360, 640, seed=5)
+    a = v5ela.analyze_batch(t)
+    b = v5ela.analyze_batch(t, want_residual=True)
+    torch.cuda.synchronize()
+    assert "residual" not in a and torch.equal(a["records"], b["records"])
+
+
+def test_torch_generator_matches_numpy():
+    t = gen_batch_torch(3, 2, 97, 131, seed=4).cpu().numpy()
+    assert np.array_equal(t, gen_batch(3, 2, 97, 131, seed=4))
+
+
+def test_1080p_known_answers_and_properties():
+    """BASELINE.json config 2 shape: 1080p, q=90. Frame 0 == Appendix B hash; size-independent properties on all."""
+    import torch
+    import v5ela
+
+    n = 16
+    t = gen_batch_torch(0, n, 1080, 1920, seed=0)
+    out = v5ela.analyze_batch(t, want_residual=True, want_enhanced=True)
+    torch.cuda.synchronize()
+    recs = as_records(out["records"])
+    resid0 = out["residual"][0].cpu().numpy()
+    assert sha(resid0) == "7c7db2c090891020"                      # SURVEY Appendix B, gen_frame(0,1080,1920,0) q=90
+    assert recs[0]["ela_max"].tolist() == [15, 13, 16]
+    assert recs[0]["ela_sum"].tolist() == [6545756, 5547703, 7120886]
+    assert (int(recs[0]["tex_sumabs"]), int(recs[0]["tex_sumsq"]), int(recs[0]["tex_maxabs"])) == (19016872, 259819512, 40)
+    # properties at full size, every frame: histogram <-> residual map <-> sums consistency (checksum of checksums)
+    res = out["residual"]
+    for i in range(n):
+        for c in range(3):
+            ch = res[i, :, :, c].reshape(-1)
+            hist = torch.bincount(ch.to(torch.int64), minlength=256).cpu().numpy()
+            assert np.array_equal(hist, recs[i]["ela_hist"][c])
+            assert int(recs[i]["ela_hist"][c].sum()) == 1080 * 1920
+            assert int(ch.to(torch.int64).sum()) == int(recs[i]["ela_sum"][c])
+            assert int(ch.max()) == int(recs[i]["ela_max"][c])
+    # three more frames against the C oracle in full
+    for i in (1, 7, 15):
+        o = c_oracle.analyze_frame(t[i].cpu().numpy(), 90)
+        assert np.array_equal(out["residual"][i].cpu().numpy(), o["residual"])
+        assert recs[i].tobytes() == o["record"].tobytes()
+    # idempotence of the enhancement LUT definition: enhanced == lut[max][residual]
+    for i in (0, 5):
+        m = int(recs[i]["ela_max"].max())
+        lut = c_oracle.enhance_lut(m)
+        assert np.array_equal(out["enhanced"][i].cpu().numpy(), lut[out["residual"][i].cpu().numpy()])
+    f = features(recs[0], 1080 * 1920)
+    ref = features(c_oracle.analyze_frame(t[0].cpu().numpy(), 90)["record"], 1080 * 1920)
+    for k, v in f.items():
+        assert np.allclose(v, ref[k], rtol=1e-5, atol=0), k       # north_star tolerance for float statistics
+
+
+def test_4k_frame_known_answer():
+    out = run_gpu(gen_frame(5, 2160, 3840, 0)[None], 90)
+    assert sha(out["residual"][0]) == "3f81ee414328ef0c"
+    assert out["records"][0]["ela_sum"].tolist() == [26182514, 22179221, 28471595]
+    assert int(out["records"][0]["tex_sumsq"]) == 1039975130
+
+
+def test_noise_frames_full_range_residuals():
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 360, 640, 3), dtype=np.uint8)
+    out = run_gpu(frames, 90)
+    recs, resid = c_oracle.analyze(frames, 90, want_residual=True)
+    assert np.array_equal(out["residual"], resid) and out["records"].tobytes() == recs.tobytes()
+    assert int(out["records"]["ela_max"].max()) > 200
+
+
+def test_reduce_records_per_video():
+    import torch
+    import v5ela
+    from v5ela.records import combine
+
+    t = gen_batch_torch(0, 12, 180, 320, seed=1)
+    out = v5ela.analyze_batch(t)
+    agg = v5ela.reduce_records(out["records"], 4)
+    torch.cuda.synchronize()
+    recs, aggr = as_records(out["records"]), as_records(agg)
+    for g in range(3):
+        assert aggr[g].tobytes() == combine(recs[4 * g:4 * g + 4]).tobytes()
+
+
+def test_analyze_host_entry_point():
+    import ctypes
+
+    import torch
+    from v5ela import _abi
+
+    frames = gen_batch(2, 3, 120, 200, seed=6)
+    h = _abi.Handle(torch.cuda.current_device())
+    recs = np.zeros(3, dtype=as_records(np.zeros((1, 3144), np.uint8)).dtype)
+    resid = np.zeros_like(frames)
+    enh = np.zeros_like(frames)
+    h.analyze_host(frames.ctypes.data, 3, 120, 200, recs.ctypes.data, resid.ctypes.data, enh.ctypes.data)
+    orecs, oresid = c_oracle.analyze(frames, 90, want_residual=True)
+    assert np.array_equal(resid, oresid) and recs.tobytes() == orecs.tobytes()
+    for i in range(3):
+        assert np.array_equal(enh[i], pil_oracle.ela_enhanced(frames[i], 90))
+    assert h.launch_count >= 3
+    h.close()
+
+
+def test_error_codes_do_not_raise_cuda_faults():
+    import torch
+    from v5ela import _abi
+
+    h = _abi.Handle(torch.cuda.current_device())
+    with pytest.raises(_abi.V5ElaError):
+        h.set_quality(0)
+    with pytest.raises(_abi.V5ElaError):
+        h.analyze(0, 1, 16, 16, 768, 48, 0, None, None)          # null pointers
+    t = torch.zeros((1, 16, 16, 3), dtype=torch.uint8, device="cuda")
+    r = torch.zeros((1, 3144), dtype=torch.uint8, device="cuda")
+    with pytest.raises(_abi.V5ElaError):
+        h.analyze(t.data_ptr(), 1, 16, 16, 768, 47, r.data_ptr(), None, None)   # row stride < 3*W
+    h.analyze(t.data_ptr(), 1, 16, 16, 768, 48, r.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    h.close()

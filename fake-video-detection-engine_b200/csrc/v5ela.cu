@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "v5ela.h"
 #include "v5ela_host.h"
@@ -133,7 +134,14 @@ struct v5ela_handle {
     int seg_rows = 0;                      // 0 = default
     int ctas_per_sm = 2;
     int64_t launches = 0;
-    cudaStream_t own_stream = nullptr;     // used by v5ela_analyze_host
+    cudaStream_t own_stream = nullptr;     // v5ela_analyze_host with a NULL stream
+    cudaStream_t copy_stream = nullptr, work_stream = nullptr;   // chunk pipeline of v5ela_analyze_host
+    cudaEvent_t ev_fork = nullptr, ev_join_copy = nullptr, ev_join_work = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;     // "chunk c has landed" events
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs (start, stop) around the fused kernel
+    size_t prof_used = 0;
+    int host_chunk_frames = 0;             // 0 = auto
     uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
     void *d_rec = nullptr;
     size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
@@ -213,6 +221,8 @@ int v5ela_create(int device, v5ela_handle **out)
     }
     const char *env = getenv("V5ELA_SEG_ROWS");
     if (env) h->seg_rows = atoi(env);
+    env = getenv("V5ELA_HOST_CHUNK");
+    if (env) h->host_chunk_frames = atoi(env);
     *out = h;
     return V5ELA_OK;
 }
@@ -222,6 +232,12 @@ int v5ela_destroy(v5ela_handle *h)
     if (!h) return V5ELA_ERR_INVALID;
     DeviceGuard guard(h->device);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->work_stream) cudaStreamDestroy(h->work_stream);
+    for (cudaEvent_t e : {h->ev_fork, h->ev_join_copy, h->ev_join_work})
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     cudaFree(h->d_in);
     cudaFree(h->d_res);
     cudaFree(h->d_enh);
@@ -267,8 +283,14 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
     V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
     const int max_ctas = h->sm_count * h->ctas_per_sm;
     const int grid = total < max_ctas ? (int)total : max_ctas;
+    const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
+    if (prof) V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used], st));
     v5::ela_fused_kernel<<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
     V5_CUDA(h, cudaGetLastError());
+    if (prof) {
+        V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used + 1], st));
+        h->prof_used += 2;
+    }
     v5::ela_finalize_kernel<<<n, 96, 0, st>>>(static_cast<v5ela_record *>(d_records), n);
     V5_CUDA(h, cudaGetLastError());
     h->launches += 2;
@@ -310,14 +332,21 @@ int v5ela_reduce_records(v5ela_handle *h, const void *d_records, int n, int grou
 }
 
 int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int height, int width, void *records_host,
-                       uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null)
+                       uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null, void *cuda_stream)
 {
     if (!h) return V5ELA_ERR_INVALID;
     if (n == 0) return V5ELA_OK;
     if (!rgb_host || !records_host || n < 0 || height <= 0 || width <= 0)
         return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_host: bad pointer or size%s");
     DeviceGuard guard(h->device);
-    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream) {
+        V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        V5_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        V5_CUDA(h, cudaStreamCreateWithFlags(&h->work_stream, cudaStreamNonBlocking));
+        V5_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        V5_CUDA(h, cudaEventCreateWithFlags(&h->ev_join_copy, cudaEventDisableTiming));
+        V5_CUDA(h, cudaEventCreateWithFlags(&h->ev_join_work, cudaEventDisableTiming));
+    }
     const size_t fbytes = (size_t)height * width * 3, in_bytes = fbytes * n, rec_bytes = sizeof(v5ela_record) * (size_t)n;
     const bool want_map = residual_host_or_null || enhanced_host_or_null;
     int rc;
@@ -325,20 +354,78 @@ int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int heig
     if ((rc = ensure(h, &h->d_rec, &h->d_rec_cap, rec_bytes))) return rc;
     if (want_map && (rc = ensure(h, (void **)&h->d_res, &h->d_res_cap, in_bytes))) return rc;
     if (enhanced_host_or_null && (rc = ensure(h, (void **)&h->d_enh, &h->d_enh_cap, in_bytes))) return rc;
-    cudaStream_t st = h->own_stream;
-    V5_CUDA(h, cudaMemcpyAsync(h->d_in, rgb_host, in_bytes, cudaMemcpyHostToDevice, st));
-    rc = v5ela_analyze(h, h->d_in, n, height, width, (int64_t)fbytes, (int64_t)width * 3, h->d_rec,
-                       want_map ? h->d_res : nullptr, st);
-    if (rc) return rc;
-    V5_CUDA(h, cudaMemcpyAsync(records_host, h->d_rec, rec_bytes, cudaMemcpyDeviceToHost, st));
-    if (residual_host_or_null)
-        V5_CUDA(h, cudaMemcpyAsync(residual_host_or_null, h->d_res, in_bytes, cudaMemcpyDeviceToHost, st));
-    if (enhanced_host_or_null) {
-        rc = v5ela_enhance(h, h->d_res, h->d_rec, n, height, width, h->d_enh, st);
-        if (rc) return rc;
-        V5_CUDA(h, cudaMemcpyAsync(enhanced_host_or_null, h->d_enh, in_bytes, cudaMemcpyDeviceToHost, st));
+
+    // chunking: ~64 MB of frames per chunk keeps the copy engine and the SMs both busy
+    int chunk = h->host_chunk_frames > 0 ? h->host_chunk_frames : (int)((64u << 20) / fbytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    const int n_chunks = (n + chunk - 1) / chunk;
+    while ((int)h->ev_chunk.size() < n_chunks) {
+        cudaEvent_t e;
+        V5_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
     }
-    V5_CUDA(h, cudaStreamSynchronize(st));
+    cudaStream_t user = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    cudaStream_t cs = h->copy_stream, ws = h->work_stream;
+    V5_CUDA(h, cudaEventRecord(h->ev_fork, user));
+    V5_CUDA(h, cudaStreamWaitEvent(cs, h->ev_fork, 0));
+    V5_CUDA(h, cudaStreamWaitEvent(ws, h->ev_fork, 0));
+    uint8_t *d_rec = static_cast<uint8_t *>(h->d_rec);
+    for (int c = 0; c < n_chunks; c++) {
+        const int f0 = c * chunk, fn = (f0 + chunk <= n ? chunk : n - f0);
+        const size_t off = fbytes * f0, bytes = fbytes * fn, roff = sizeof(v5ela_record) * (size_t)f0;
+        V5_CUDA(h, cudaMemcpyAsync(h->d_in + off, rgb_host + off, bytes, cudaMemcpyHostToDevice, cs));
+        V5_CUDA(h, cudaEventRecord(h->ev_chunk[c], cs));
+        V5_CUDA(h, cudaStreamWaitEvent(ws, h->ev_chunk[c], 0));
+        rc = v5ela_analyze(h, h->d_in + off, fn, height, width, (int64_t)fbytes, (int64_t)width * 3, d_rec + roff,
+                           want_map ? h->d_res + off : nullptr, ws);
+        if (rc) return rc;
+        if (residual_host_or_null)
+            V5_CUDA(h, cudaMemcpyAsync(residual_host_or_null + off, h->d_res + off, bytes, cudaMemcpyDeviceToHost, ws));
+        if (enhanced_host_or_null) {
+            rc = v5ela_enhance(h, h->d_res + off, d_rec + roff, fn, height, width, h->d_enh + off, ws);
+            if (rc) return rc;
+            V5_CUDA(h, cudaMemcpyAsync(enhanced_host_or_null + off, h->d_enh + off, bytes, cudaMemcpyDeviceToHost, ws));
+        }
+    }
+    V5_CUDA(h, cudaMemcpyAsync(records_host, h->d_rec, rec_bytes, cudaMemcpyDeviceToHost, ws));
+    V5_CUDA(h, cudaEventRecord(h->ev_join_copy, cs));
+    V5_CUDA(h, cudaEventRecord(h->ev_join_work, ws));
+    V5_CUDA(h, cudaStreamWaitEvent(user, h->ev_join_copy, 0));
+    V5_CUDA(h, cudaStreamWaitEvent(user, h->ev_join_work, 0));
+    if (!cuda_stream) V5_CUDA(h, cudaStreamSynchronize(user));
+    return V5ELA_OK;
+}
+
+int v5ela_profile_enable(v5ela_handle *h, int enable)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (enable && h->prof_events.empty()) {
+        h->prof_events.resize(8192);
+        for (auto &e : h->prof_events) {
+            e = nullptr;
+            V5_CUDA(h, cudaEventCreate(&e));
+        }
+    }
+    h->profiling = enable != 0;
+    return V5ELA_OK;
+}
+
+int v5ela_profile_read(v5ela_handle *h, double *fused_ms_sum, int64_t *fused_launches, int reset)
+{
+    if (!h || !fused_ms_sum || !fused_launches) return V5ELA_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        V5_CUDA(h, cudaEventSynchronize(h->prof_events[i + 1]));
+        V5_CUDA(h, cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+        sum += ms;
+    }
+    *fused_ms_sum = sum;
+    *fused_launches = (int64_t)(h->prof_used / 2);
+    if (reset) h->prof_used = 0;
     return V5ELA_OK;
 }
 

@@ -39,7 +39,6 @@ constexpr int BAND_PX = BAND_MCUS * 16;     // 512
 constexpr int RGB_PITCH = BAND_PX * 3;      // 1536 bytes per band line
 constexpr int Y_PITCH = BAND_PX;            // 512
 constexpr int C_PITCH = BAND_PX / 2;        // 256
-constexpr int CHROMA_TID0 = ((4 * TW_MAX + 31) / 32) * 32;   // first thread of the chroma block warps (128)
 
 // Exact division constants for one quantisation table entry T (divisor d = 8T), see make_quant():
 //   q_biased = umulhi(c + (c >> 31) + bias, recip);  dequantised = q_biased * t - unbias
@@ -98,8 +97,14 @@ V5_DEV uint32_t pack4(int a, int b, int c, int d)
 }
 
 // ------------------------------------------------------------------------------------------------- shared memory
+struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
+
 struct alignas(16) Smem {
-    uint8_t rgb[2][16][RGB_PITCH];      // band r in rgb[r & 1]
+    QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
+    uint8_t rgb[16][RGB_PITCH];         // the current band
+    uint8_t rgb_carry[2][RGB_PITCH];    // line 15 of band r in rgb_carry[r & 1] (finished one iteration later)
+    uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad), fDCT rows -> columns
+    uint32_t rscratch[NT / 32][8 * 36]; //              and IDCT columns -> rows; 36-word block stride = no conflicts
     uint8_t yorig[32][Y_PITCH];         // luma of the original; band r line l at [16*(r&1) + l]
     uint8_t ydec[32][Y_PITCH];          // luma after the JPEG round trip, same ring
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
@@ -140,39 +145,23 @@ V5_DEV void stage_load(int tid, Smem &S, const KParams &p, const Geo &g, int r)
     if (xe > p.w) xe = p.w;
     const int nbytes = 3 * (xe - xs);
     const int dst0 = 3 * (xs - g.xb0);
-    uint8_t(*dst)[RGB_PITCH] = S.rgb[r & 1];
-    if (p.vec_ok) {
-        const int nvec = nbytes >> 4;                           // 16-byte chunks per line
-        for (int i = tid; i < 16 * nvec; i += NT) {
-            const int l = i / nvec, v = i - l * nvec;
-            int y = 16 * r + l;
-            if (y > p.h - 1) y = p.h - 1;
-            const U4 *src = reinterpret_cast<const U4 *>(g.frame + (int64_t)y * p.row_stride + 3 * xs);
-            *reinterpret_cast<U4 *>(&dst[l][dst0 + 16 * v]) = src[v];
+    const int npad3 = 3 * (xpad_end - p.w);                     // > 0 only in the strip that holds the right edge
+    uint8_t(*dst)[RGB_PITCH] = S.rgb;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int l = warp; l < 16; l += NT / 32) {                  // one warp per band line
+        int y = 16 * r + l;
+        if (y > p.h - 1) y = p.h - 1;
+        const uint8_t *src = g.frame + (int64_t)y * p.row_stride + 3 * xs;
+        int done = 0;
+        if (p.vec_ok) {
+            const int nvec = nbytes >> 4;
+            for (int v = lane; v < nvec; v += 32)
+                *reinterpret_cast<U4 *>(&dst[l][dst0 + 16 * v]) = reinterpret_cast<const U4 *>(src)[v];
+            done = nvec << 4;
         }
-        const int tail = nbytes & 15;
-        for (int i = tid; i < 16 * tail; i += NT) {
-            const int l = i / tail, b = (nvec << 4) + (i - l * tail);
-            int y = 16 * r + l;
-            if (y > p.h - 1) y = p.h - 1;
-            dst[l][dst0 + b] = g.frame[(int64_t)y * p.row_stride + 3 * xs + b];
-        }
-    } else {
-        for (int i = tid; i < 16 * nbytes; i += NT) {
-            const int l = i / nbytes, b = i - l * nbytes;
-            int y = 16 * r + l;
-            if (y > p.h - 1) y = p.h - 1;
-            dst[l][dst0 + b] = g.frame[(int64_t)y * p.row_stride + 3 * xs + b];
-        }
-    }
-    const int npad = xpad_end - p.w;                            // > 0 only in the strip that holds the right edge
-    if (npad > 0) {
-        for (int i = tid; i < 16 * npad * 3; i += NT) {
-            const int l = i / (npad * 3), b = i - l * npad * 3;
-            int y = 16 * r + l;
-            if (y > p.h - 1) y = p.h - 1;
+        for (int b = done + lane; b < nbytes; b += 32) dst[l][dst0 + b] = src[b];
+        for (int b = lane; b < npad3; b += 32)
             dst[l][3 * (p.w - g.xb0) + b] = g.frame[(int64_t)y * p.row_stride + 3 * (p.w - 1) + (b % 3)];
-        }
     }
 }
 
@@ -181,61 +170,50 @@ V5_DEV int rgb_to_y(int r, int g, int b) { return (19595 * r + 38470 * g + 7471 
 V5_DEV int rgb_to_cb(int r, int g, int b) { return (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16; }
 V5_DEV int rgb_to_cr(int r, int g, int b) { return (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16; }
 
-// 16 pixels of two band lines: optional luma (two packed lines) and the 8 downsampled Cb/Cr samples.
+// 8 pixels of two band lines: optional luma (8 bytes per line) and the 4 downsampled Cb/Cr samples.
 template <bool WANT_Y, bool WANT_C>
-V5_DEV void convert16x2(const uint8_t *la, const uint8_t *lb, U4 &y0, U4 &y1, U2 &cbo, U2 &cro)
+V5_DEV void convert8x2(const uint8_t *la, const uint8_t *lb, U2 &y0, U2 &y1, uint32_t &cbo, uint32_t &cro)
 {
-    uint32_t ya[4], yb[4], cbw[2], crw[2];
+    uint32_t a[6], b[6];
 #pragma unroll
-    for (int q4 = 0; q4 < 4; q4++) {                            // 4 pixels = 12 bytes = 3 words per line
-        const uint32_t *wa = reinterpret_cast<const uint32_t *>(la) + 3 * q4;
-        const uint32_t *wb = reinterpret_cast<const uint32_t *>(lb) + 3 * q4;
-        const uint32_t a[3] = {wa[0], wa[1], wa[2]}, b[3] = {wb[0], wb[1], wb[2]};
-        int yy[2][4], cb[2][4], cr[2][4];
+    for (int i = 0; i < 3; i++) {
+        const U2 ta = reinterpret_cast<const U2 *>(la)[i], tb = reinterpret_cast<const U2 *>(lb)[i];
+        a[2 * i] = ta.x; a[2 * i + 1] = ta.y;
+        b[2 * i] = tb.x; b[2 * i + 1] = tb.y;
+    }
+    int yy[2][8], cb[2][8], cr[2][8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int o = 3 * k;
-            const int ra = byte_of(a[o >> 2], o & 3), ga = byte_of(a[(o + 1) >> 2], (o + 1) & 3),
-                      ba = byte_of(a[(o + 2) >> 2], (o + 2) & 3);
-            const int rb = byte_of(b[o >> 2], o & 3), gb = byte_of(b[(o + 1) >> 2], (o + 1) & 3),
-                      bb = byte_of(b[(o + 2) >> 2], (o + 2) & 3);
-            if (WANT_Y) {
-                yy[0][k] = rgb_to_y(ra, ga, ba);
-                yy[1][k] = rgb_to_y(rb, gb, bb);
-            }
-            if (WANT_C) {
-                cb[0][k] = rgb_to_cb(ra, ga, ba);
-                cb[1][k] = rgb_to_cb(rb, gb, bb);
-                cr[0][k] = rgb_to_cr(ra, ga, ba);
-                cr[1][k] = rgb_to_cr(rb, gb, bb);
-            }
-        }
+    for (int k = 0; k < 8; k++) {
+        const int o = 3 * k;
+        const int ra = byte_of(a[o >> 2], o & 3), ga = byte_of(a[(o + 1) >> 2], (o + 1) & 3),
+                  ba = byte_of(a[(o + 2) >> 2], (o + 2) & 3);
+        const int rb = byte_of(b[o >> 2], o & 3), gb = byte_of(b[(o + 1) >> 2], (o + 1) & 3),
+                  bb = byte_of(b[(o + 2) >> 2], (o + 2) & 3);
         if (WANT_Y) {
-            ya[q4] = pack4(yy[0][0], yy[0][1], yy[0][2], yy[0][3]);
-            yb[q4] = pack4(yy[1][0], yy[1][1], yy[1][2], yy[1][3]);
+            yy[0][k] = rgb_to_y(ra, ga, ba);
+            yy[1][k] = rgb_to_y(rb, gb, bb);
         }
-        if (WANT_C) {                                           // h2v2 box filter, bias 1,2,1,2 along x
-            const int c0 = (cb[0][0] + cb[0][1] + cb[1][0] + cb[1][1] + 1) >> 2;
-            const int c1 = (cb[0][2] + cb[0][3] + cb[1][2] + cb[1][3] + 2) >> 2;
-            const int d0 = (cr[0][0] + cr[0][1] + cr[1][0] + cr[1][1] + 1) >> 2;
-            const int d1 = (cr[0][2] + cr[0][3] + cr[1][2] + cr[1][3] + 2) >> 2;
-            const uint32_t cbp = (uint32_t)c0 | ((uint32_t)c1 << 8), crp = (uint32_t)d0 | ((uint32_t)d1 << 8);
-            if (q4 & 1) {
-                cbw[q4 >> 1] |= cbp << 16;
-                crw[q4 >> 1] |= crp << 16;
-            } else {
-                cbw[q4 >> 1] = cbp;
-                crw[q4 >> 1] = crp;
-            }
+        if (WANT_C) {
+            cb[0][k] = rgb_to_cb(ra, ga, ba);
+            cb[1][k] = rgb_to_cb(rb, gb, bb);
+            cr[0][k] = rgb_to_cr(ra, ga, ba);
+            cr[1][k] = rgb_to_cr(rb, gb, bb);
         }
     }
     if (WANT_Y) {
-        y0 = U4{ya[0], ya[1], ya[2], ya[3]};
-        y1 = U4{yb[0], yb[1], yb[2], yb[3]};
+        y0 = U2{pack4(yy[0][0], yy[0][1], yy[0][2], yy[0][3]), pack4(yy[0][4], yy[0][5], yy[0][6], yy[0][7])};
+        y1 = U2{pack4(yy[1][0], yy[1][1], yy[1][2], yy[1][3]), pack4(yy[1][4], yy[1][5], yy[1][6], yy[1][7])};
     }
-    if (WANT_C) {
-        cbo = U2{cbw[0], cbw[1]};
-        cro = U2{crw[0], crw[1]};
+    if (WANT_C) {                                               // h2v2 box filter, bias 1,2,1,2 along x
+        int c[4], d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int bias = 1 + (j & 1);
+            c[j] = (cb[0][2 * j] + cb[0][2 * j + 1] + cb[1][2 * j] + cb[1][2 * j + 1] + bias) >> 2;
+            d[j] = (cr[0][2 * j] + cr[0][2 * j + 1] + cr[1][2 * j] + cr[1][2 * j + 1] + bias) >> 2;
+        }
+        cbo = pack4(c[0], c[1], c[2], c[3]);
+        cro = pack4(d[0], d[1], d[2], d[3]);
     }
 }
 
@@ -245,26 +223,27 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
     const int last_cline = ((p.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
     const int last_line = p.h - 1 - 16 * r;                     // local index of the last real pixel line
-    const uint8_t(*src)[RGB_PITCH] = S.rgb[r & 1];
-    for (int u = tid; u < 8 * BAND_MCUS; u += NT) {
-        const int li = u / BAND_MCUS, ux = u - li * BAND_MCUS;
-        const int mcu = g.m0 - 1 + ux;
-        if (ux >= g.band_mcus || mcu < 0 || mcu >= p.mw) continue;
-        U4 y0, y1;
-        U2 cb, cr;
-        convert16x2<true, true>(&src[2 * li][48 * ux], &src[2 * li + 1][48 * ux], y0, y1, cb, cr);
+    const uint8_t(*src)[RGB_PITCH] = S.rgb;
+    for (int i = tid; i < RGB_PITCH / 16; i += NT)              // keep line 15 for the next iteration's residual stage
+        reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
+    for (int u = tid; u < 8 * 2 * BAND_MCUS; u += NT) {          // unit = 2 lines x 8 px
+        const int li = u / (2 * BAND_MCUS), ox = u - li * (2 * BAND_MCUS);
+        const int mcu = g.m0 - 1 + (ox >> 1);
+        if (ox >= 2 * g.band_mcus || mcu < 0 || mcu >= p.mw) continue;
+        U2 y0, y1;
+        uint32_t cb, cr;
+        convert8x2<true, true>(&src[2 * li][24 * ox], &src[2 * li + 1][24 * ox], y0, y1, cb, cr);
         const int jc = li < last_cline ? li : last_cline;
         int lb = 2 * jc + 1;
         if (lb > last_line) lb = last_line;
-        if (2 * jc != 2 * li || lb != 2 * li + 1) {
-            if (lb < 2 * jc) lb = 2 * jc;                       // (cannot happen: last_line >= 2*last_cline)
-            U4 d0, d1;
-            convert16x2<false, true>(&src[2 * jc][48 * ux], &src[lb][48 * ux], d0, d1, cb, cr);
+        if (jc != li || lb != 2 * li + 1) {                     // only in the band that holds the bottom image edge
+            U2 d0, d1;
+            convert8x2<false, true>(&src[2 * jc][24 * ox], &src[lb][24 * ox], d0, d1, cb, cr);   // rare path
         }
-        *reinterpret_cast<U4 *>(&S.yorig[ring16(r, 2 * li)][16 * ux]) = y0;
-        *reinterpret_cast<U4 *>(&S.yorig[ring16(r, 2 * li + 1)][16 * ux]) = y1;
-        *reinterpret_cast<U2 *>(&S.cenc[0][li][8 * ux]) = cb;
-        *reinterpret_cast<U2 *>(&S.cenc[1][li][8 * ux]) = cr;
+        *reinterpret_cast<U2 *>(&S.yorig[ring16(r, 2 * li)][8 * ox]) = y0;
+        *reinterpret_cast<U2 *>(&S.yorig[ring16(r, 2 * li + 1)][8 * ox]) = y1;
+        *reinterpret_cast<uint32_t *>(&S.cenc[0][li][4 * ox]) = cb;
+        *reinterpret_cast<uint32_t *>(&S.cenc[1][li][4 * ox]) = cr;
     }
 }
 
@@ -351,111 +330,162 @@ V5_DEV void idct8(int *v)
     }
 }
 
-// One 8x8 block held in registers: in[r] = 8 bytes of row r (unsigned samples); out likewise. All indices are compile
-// time after unrolling, so the quantisation constants are read as constant-bank operands straight from the kernel params.
-V5_DEV void block_roundtrip(const QuantTab &q, const uint8_t *in, int in_pitch, uint8_t *out, int out_pitch)
+// The block stage. Four threads share one 8x8 block; thread j owns rows 2j,2j+1 in the row passes and columns 2j,2j+1
+// in the column passes. The two transpositions go through a per-warp shared-memory scratch as int16 pairs (ranges:
+// |fDCT row output| <= 4096, |IDCT column output| <= 21047 by Parseval + quantisation error), laid out so
+// that both the scattered 32-bit stores and the 128-bit loads are bank-conflict free. Only __syncwarp() is needed between
+// the three sub-stages, and the code is ~600 instructions instead of ~1900 for a block-per-thread unrolling (the
+// instruction cache, not the ALUs, was the first version's limit).
+struct BlockTask {
+    const QEntry *q;
+    const uint8_t *in;
+    uint8_t *out;
+    int pitch;
+    bool active;
+};
+
+V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, int r, bool want_y)
 {
-    int v[64];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const U2 w = *reinterpret_cast<const U2 *>(in + r * in_pitch);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            v[8 * r + k] = (int)byte_of(w.x, k);
-            v[8 * r + 4 + k] = (int)byte_of(w.y, k);
-        }
+    BlockTask t;
+    t.active = false;
+    t.q = S.qtab[0];
+    t.in = nullptr;
+    t.out = nullptr;
+    t.pitch = 0;
+    const int tw = g.m1 - g.m0;
+    const int nl = want_y ? 4 * tw : 0;
+    if (blk < nl) {
+        const int br = blk >= 2 * tw ? 1 : 0, bc = blk - br * 2 * tw;
+        // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
+        if (16 * r + 8 * br >= p.h || 16 * g.m0 + 8 * bc >= p.w) return t;
+        const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
+        t.in = &S.yorig[row][col];
+        t.out = &S.ydec[row][col];
+        t.pitch = Y_PITCH;
+        t.active = true;
+    } else {
+        const int c = blk - nl;
+        if (c >= 2 * g.band_mcus) return t;
+        const int comp = c >= g.band_mcus ? 1 : 0, cbk = c - comp * g.band_mcus;
+        const int mcu = g.m0 - 1 + cbk;
+        if (mcu < 0 || mcu >= p.mw) return t;
+        t.q = S.qtab[1];
+        t.in = &S.cenc[comp][0][8 * cbk];
+        t.out = &S.cdec[comp][ring8(r, 0)][8 * cbk];
+        t.pitch = C_PITCH;
+        t.active = true;
     }
-#pragma unroll
-    for (int r = 0; r < 8; r++) fdct8<1, true>(v + 8 * r);
-#pragma unroll
-    for (int c = 0; c < 8; c++) fdct8<8, false>(v + c);
-#pragma unroll
-    for (int i = 0; i < 64; i++) {                              // A.5: round half away from zero of c / (8T), times T
-        const int c = v[i];
-        const uint32_t x = (uint32_t)(c + (c >> 31) + q.bias[i]);
-        v[i] = (int)umulhi32(x, q.recip[i]) * q.t[i] - q.unbias[i];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; c++) idct8<8, false>(v + c);
-#pragma unroll
-    for (int r = 0; r < 8; r++) idct8<1, true>(v + 8 * r);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        U2 w;
-        w.x = pack4(v[8 * r], v[8 * r + 1], v[8 * r + 2], v[8 * r + 3]);
-        w.y = pack4(v[8 * r + 4], v[8 * r + 5], v[8 * r + 6], v[8 * r + 7]);
-        *reinterpret_cast<U2 *>(out + r * out_pitch) = w;
-    }
+    return t;
 }
 
-// Threads [0, 4*TW) take the luma blocks of the strip proper (halo columns need no decoded luma); threads
-// [CHROMA_TID0, CHROMA_TID0 + 2*(TW+2)) take the Cb and Cr blocks including the halo columns. `want_y` is false for
-// the halo bands above/below a segment (only their chroma is needed).
-V5_DEV void stage_blocks(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y)
+V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
+
+V5_DEV uint32_t pack_s16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+V5_DEV int s16_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
+
+// sub-stage 1: forward row pass of rows 2j, 2j+1 -> tscratch (column-major pairs)
+V5_DEV void blocks_rows_fwd(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
 {
-    const int tw = g.m1 - g.m0;
-    if (tid < CHROMA_TID0) {
-        if (!want_y || tid >= 4 * tw) return;
-        const int br = tid / (2 * tw), bc = tid - br * 2 * tw;
-        // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
-        if (16 * r + 8 * br >= p.h || 16 * g.m0 + 8 * bc >= p.w) return;
-        const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
-        block_roundtrip(p.q[0], &S.yorig[row][col], Y_PITCH, &S.ydec[row][col], Y_PITCH);
-    } else {
-        const int c = tid - CHROMA_TID0;
-        if (c >= 2 * BAND_MCUS) return;
-        const int comp = c / BAND_MCUS, cbk = c - comp * BAND_MCUS;
-        const int mcu = g.m0 - 1 + cbk;
-        if (cbk >= g.band_mcus || mcu < 0 || mcu >= p.mw) return;
-        block_roundtrip(p.q[1], &S.cenc[comp][0][8 * cbk], C_PITCH, &S.cdec[comp][ring8(r, 0)][8 * cbk], C_PITCH);
+    const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
+    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
+    if (!t.active) return;
+    int a[8], b[8];
+    const U2 wa = *reinterpret_cast<const U2 *>(t.in + (2 * j) * t.pitch);
+    const U2 wb = *reinterpret_cast<const U2 *>(t.in + (2 * j + 1) * t.pitch);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        a[k] = (int)byte_of(wa.x, k); a[4 + k] = (int)byte_of(wa.y, k);
+        b[k] = (int)byte_of(wb.x, k); b[4 + k] = (int)byte_of(wb.y, k);
     }
+    fdct8<1, true>(a);
+    fdct8<1, true>(b);
+    uint32_t *ts = &S.tscratch[warp][36 * bw];
+#pragma unroll
+    for (int c = 0; c < 8; c++) ts[4 * c + j] = pack_s16(a[c], b[c]);
+}
+
+// sub-stage 2: columns 2j, 2j+1: forward column pass, quantise + dequantise (A.5), inverse column pass -> rscratch
+V5_DEV void blocks_cols(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+{
+    const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
+    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
+    if (!t.active) return;
+    const uint32_t *ts = &S.tscratch[warp][36 * bw];
+    const U4 w0 = *reinterpret_cast<const U4 *>(ts + 8 * j), w1 = *reinterpret_cast<const U4 *>(ts + 8 * j + 4);
+    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
+    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
+    fdct8<1, false>(a);
+    fdct8<1, false>(b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                               // coefficient (row k, column 2j / 2j+1)
+        const QEntry ea = t.q[8 * k + 2 * j], eb = t.q[8 * k + 2 * j + 1];
+        const uint32_t xa = (uint32_t)(a[k] + (a[k] >> 31) + ea.bias), xb = (uint32_t)(b[k] + (b[k] >> 31) + eb.bias);
+        a[k] = (int)umulhi32(xa, ea.recip) * ea.t - ea.unbias;
+        b[k] = (int)umulhi32(xb, eb.recip) * eb.t - eb.unbias;
+    }
+    idct8<1, false>(a);
+    idct8<1, false>(b);
+    uint32_t *rs = &S.rscratch[warp][36 * bw];
+#pragma unroll
+    for (int k = 0; k < 8; k++) rs[4 * k + j] = pack_s16(a[k], b[k]);
+}
+
+// sub-stage 3: final inverse row pass of rows 2j, 2j+1, +128, clamp, store bytes
+V5_DEV void blocks_rows_inv(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+{
+    const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
+    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
+    if (!t.active) return;
+    const uint32_t *rs = &S.rscratch[warp][36 * bw];
+    const U4 w0 = *reinterpret_cast<const U4 *>(rs + 8 * j), w1 = *reinterpret_cast<const U4 *>(rs + 8 * j + 4);
+    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
+    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
+    idct8<1, true>(a);
+    idct8<1, true>(b);
+    *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
+    *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
 }
 
 // ------------------------------------------------------------------- stage: upsample, reconstruct, residual, Laplacian
-// Horizontal+vertical fancy upsample (A.7) of one chroma component for 16 output pixels of one line.
-// lc / ln: decoded chroma lines (current row, neighbour row), pointing at this unit's first chroma column; columns -1 and
-// 8 are the horizontal neighbours (halo). gcx0 = global chroma column of lc[0]; wc1 = Wc - 1.
-V5_DEV void upsample16(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, bool fancy, int out[16])
+// Horizontal+vertical fancy upsample (A.7) of one chroma component for 8 output pixels of one line.
+// lc / ln: decoded chroma lines (current row, neighbour row), pointing at this unit's first chroma column (4-aligned);
+// columns -1 and 4 are the horizontal neighbours. gcx0 = global chroma column of lc[0]; wc1 = Wc - 1.
+V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, bool fancy, int out[8])
 {
-    int cs[10];                                                 // cs[j+1] = 3*c[r][j] + c[nb][j], j = -1..8
     const uint32_t c0 = *reinterpret_cast<const uint32_t *>(lc - 4), n0 = *reinterpret_cast<const uint32_t *>(ln - 4);
-    const U2 c1 = *reinterpret_cast<const U2 *>(lc), n1 = *reinterpret_cast<const U2 *>(ln);
-    const uint32_t c2 = *reinterpret_cast<const uint32_t *>(lc + 8), n2 = *reinterpret_cast<const uint32_t *>(ln + 8);
+    const uint32_t c1 = *reinterpret_cast<const uint32_t *>(lc), n1 = *reinterpret_cast<const uint32_t *>(ln);
+    const uint32_t c2 = *reinterpret_cast<const uint32_t *>(lc + 4), n2 = *reinterpret_cast<const uint32_t *>(ln + 4);
     if (!fancy) {                                               // Wc <= 2: libjpeg uses plain replication
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            out[2 * j] = out[2 * j + 1] = (int)byte_of(c1.x, j);
-            out[8 + 2 * j] = out[9 + 2 * j] = (int)byte_of(c1.y, j);
-        }
+        for (int j = 0; j < 4; j++) out[2 * j] = out[2 * j + 1] = (int)byte_of(c1, j);
         return;
     }
+    int cs[6];                                                  // cs[j+1] = 3*c[r][j] + c[nb][j], j = -1..4
     cs[0] = 3 * (int)byte_of(c0, 3) + (int)byte_of(n0, 3);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        cs[1 + j] = 3 * (int)byte_of(c1.x, j) + (int)byte_of(n1.x, j);
-        cs[5 + j] = 3 * (int)byte_of(c1.y, j) + (int)byte_of(n1.y, j);
-    }
-    cs[9] = 3 * (int)byte_of(c2, 0) + (int)byte_of(n2, 0);
+    for (int j = 0; j < 4; j++) cs[1 + j] = 3 * (int)byte_of(c1, j) + (int)byte_of(n1, j);
+    cs[5] = 3 * (int)byte_of(c2, 0) + (int)byte_of(n2, 0);
     if (gcx0 == 0) cs[0] = cs[1];                               // left image edge: neighbour clamps to column 0
-    if (gcx0 + 8 > wc1) {                                       // right image edge inside / just after this unit
+    if (gcx0 + 4 > wc1) {                                       // right image edge inside / just after this unit
 #pragma unroll
-        for (int j = 1; j < 10; j++)
+        for (int j = 1; j < 6; j++)
             if (gcx0 + j - 1 > wc1) cs[j] = cs[j - 1];
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < 4; j++) {
         out[2 * j] = (3 * cs[j + 1] + cs[j] + 8) >> 4;
         out[2 * j + 1] = (3 * cs[j + 1] + cs[j + 2] + 7) >> 4;
     }
 }
 
-template <bool FULL>
-V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ux)
+// 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
+V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
 {
-    const int y = 16 * r + l;                                   // global pixel row, l in [-1, 14]
-    const int gx0 = 16 * (g.m0 + ux);                           // global pixel column of this unit
-    const int col = 16 + 16 * ux;                               // band smem column
-    const int nvalid = FULL ? 16 : (p.w - gx0);                 // pixels of this unit inside the image
+    const int y = 16 * r + l;                                   // global pixel row
+    const int gx0 = 16 * g.m0 + 8 * ox;                         // global pixel column of this unit
+    const int col = 16 + 8 * ox;                                // band smem column
+    const int nvalid = p.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8)
 
     // ---- chroma upsample (A.7)
     const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = ((p.w + 1) >> 1) - 1;
@@ -465,25 +495,24 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const int lcur = ring8(r, crow - 8 * r), lnb = ring8(r, nrow - 8 * r);
     const int ccol = col >> 1, gcx0 = gx0 >> 1;
     const bool fancy = wc1 > 1;
-    int cb[16], cr[16];
-    upsample16(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
-    upsample16(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    int cb[8], cr[8];
+    upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
+    upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
 
     // ---- reconstruct (A.8), residual (A.9), histogram
-    const U4 yd = *reinterpret_cast<const U4 *>(&S.ydec[ring16(r, l)][col]);
-    const uint8_t *orig = l < 0 ? &S.rgb[(r - 1) & 1][15][3 * col] : &S.rgb[r & 1][l][3 * col];
-    const uint32_t ydw[4] = {yd.x, yd.y, yd.z, yd.w};
-    uint32_t ow[12];
+    const U2 yd = *reinterpret_cast<const U2 *>(&S.ydec[ring16(r, l)][col]);
+    const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[l][3 * col];
+    const uint32_t ydw[2] = {yd.x, yd.y};
+    uint32_t ow[6], dw[6];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const U4 t = reinterpret_cast<const U4 *>(orig)[i];
-        ow[4 * i] = t.x; ow[4 * i + 1] = t.y; ow[4 * i + 2] = t.z; ow[4 * i + 3] = t.w;
+        const U2 t = reinterpret_cast<const U2 *>(orig)[i];
+        ow[2 * i] = t.x; ow[2 * i + 1] = t.y;
     }
-    uint32_t dw[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) dw[i] = 0;
+    for (int i = 0; i < 6; i++) dw[i] = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < 8; k++) {
         const int yy = (int)byte_of(ydw[k >> 2], k & 3);
         const int cbv = cb[k], crv = cr[k];
         const int rr = clamp255(yy + ((91881 * crv + (32768 - 91881 * 128)) >> 16));
@@ -496,7 +525,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
         dr = dr < 0 ? -dr : dr;
         dg = dg < 0 ? -dg : dg;
         db = db < 0 ? -db : db;
-        if (FULL || k < nvalid) {
+        if (k < nvalid) {
             smem_inc(&S.hist[0][dr]);
             smem_inc(&S.hist[1][dg]);
             smem_inc(&S.hist[2][db]);
@@ -507,13 +536,12 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     }
     if (g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
-        if (FULL && p.resid_vec_ok) {
+        if (nvalid >= 8 && p.resid_vec_ok) {
 #pragma unroll
-            for (int i = 0; i < 3; i++)
-                reinterpret_cast<U4 *>(dst)[i] = U4{dw[4 * i], dw[4 * i + 1], dw[4 * i + 2], dw[4 * i + 3]};
+            for (int i = 0; i < 3; i++) reinterpret_cast<U2 *>(dst)[i] = U2{dw[2 * i], dw[2 * i + 1]};
         } else {
 #pragma unroll
-            for (int b = 0; b < 48; b++)
+            for (int b = 0; b < 24; b++)
                 if (b < 3 * nvalid) dst[b] = (uint8_t)byte_of(dw[b >> 2], b & 3);
         }
     }
@@ -523,32 +551,39 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     if (y == 0) lu = p.h > 1 ? l + 1 : l;
     if (y == p.h - 1) ld = p.h > 1 ? l - 1 : l;
     const uint8_t *yc = &S.yorig[ring16(r, l)][col];
-    const U4 cw = *reinterpret_cast<const U4 *>(yc);
-    const U4 uw = *reinterpret_cast<const U4 *>(&S.yorig[ring16(r, lu)][col]);
-    const U4 lw = *reinterpret_cast<const U4 *>(&S.yorig[ring16(r, ld)][col]);
-    const uint32_t cww[4] = {cw.x, cw.y, cw.z, cw.w}, uww[4] = {uw.x, uw.y, uw.z, uw.w}, lww[4] = {lw.x, lw.y, lw.z, lw.w};
-    int c[18];                                                  // c[k+1] = luma at column k, k = -1..16
-    c[0] = yc[-1];
-    c[17] = yc[16];
+    const U2 cw = *reinterpret_cast<const U2 *>(yc);
+    const U2 uw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, lu)][col]);
+    const U2 lw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, ld)][col]);
+    const uint32_t cww[2] = {cw.x, cw.y}, uww[2] = {uw.x, uw.y}, lww[2] = {lw.x, lw.y};
+    // Reflection at the left/right image edge: the left neighbour of column 0 comes from a selected address; the single
+    // pixel in column W-1 is left out of the vector loop (nacc) and done on its own below.
+    const int wide = p.w > 1;
+    const int edge = nvalid <= 8 ? nvalid - 1 : -1;             // index of the pixel in image column W-1, if in this unit
+    const int nacc = edge >= 0 ? edge : 8;
+    int c[10];                                                  // c[k+1] = luma at column k, k = -1..8
+    c[0] = gx0 == 0 ? yc[wide] : yc[-1];
+    c[9] = yc[8];
 #pragma unroll
-    for (int k = 0; k < 16; k++) c[k + 1] = (int)byte_of(cww[k >> 2], k & 3);
-    if (gx0 == 0) c[0] = p.w > 1 ? c[2] : c[1];
-    if (!FULL || gx0 + 16 == p.w) {                             // the unit holds the right image edge
-        const int ke = p.w - 1 - gx0;
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            if (k == ke) c[k + 2] = p.w > 1 ? c[k] : c[k + 1];
-    }
+    for (int k = 0; k < 8; k++) c[k + 1] = (int)byte_of(cww[k >> 2], k & 3);
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < 8; k++) {
         int lap = c[k] + c[k + 2] + (int)byte_of(uww[k >> 2], k & 3) + (int)byte_of(lww[k >> 2], k & 3) - 4 * c[k + 1];
         lap = lap < 0 ? -lap : lap;
-        if (FULL || k < nvalid) {
+        if (k < nacc) {
             sabs += (uint32_t)lap;
             ssq += (uint32_t)(lap * lap);
             mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
         }
+    }
+    if (edge >= 0) {
+        const int ctr = yc[edge];
+        const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;   // W-2 mirrors onto W
+        int lap = 2 * side + (int)S.yorig[ring16(r, lu)][col + edge] + (int)S.yorig[ring16(r, ld)][col + edge] - 4 * ctr;
+        lap = lap < 0 ? -lap : lap;
+        sabs += (uint32_t)lap;
+        ssq += (uint32_t)(lap * lap);
+        mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
     }
     acc.tex_sumabs += sabs;
     acc.tex_sumsq += ssq;
@@ -558,31 +593,28 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
 // Iteration r finishes pixel rows 16r-1 .. 16r+14 (clipped to the segment and the image).
 V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r)
 {
-    const int tw = g.m1 - g.m0;
+    const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
+    const uint32_t inv = 65536u / (uint32_t)n8 + 1u;            // exact u / n8 for u < 16 * 60
     const int ylo = 16 * g.r0, yhi = 16 * g.r1 < p.h ? 16 * g.r1 : p.h;
-    for (int u = tid; u < 16 * tw; u += NT) {
-        const int wl = u / tw, ux = u - wl * tw;
+    for (int u = tid; u < 16 * n8; u += NT) {
+        const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
-        const int gx0 = 16 * (g.m0 + ux);
-        if (y < ylo || y >= yhi || gx0 >= p.w) continue;
-        if (gx0 + 16 <= p.w)
-            residual_unit<true>(S, p, g, acc, r, l, ux);
-        else
-            residual_unit<false>(S, p, g, acc, r, l, ux);
+        if (y < ylo || y >= yhi || 16 * g.m0 + 8 * ox >= p.w) continue;
+        residual_unit(S, p, g, acc, r, l, ox);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ work item set-up
 V5_DEV void make_geo(const KParams &p, int work, Geo &g, int &frame)
 {
-    const int per_frame = p.n_strips * p.n_segs;
-    frame = work / per_frame;
-    const int rem = work - frame * per_frame;
-    const int seg = rem / p.n_strips, strip = rem - seg * p.n_strips;
-    g.m0 = (int)(((int64_t)strip * p.mw) / p.n_strips);
-    g.m1 = (int)(((int64_t)(strip + 1) * p.mw) / p.n_strips);
-    g.r0 = (int)(((int64_t)seg * p.mh) / p.n_segs);
-    g.r1 = (int)(((int64_t)(seg + 1) * p.mh) / p.n_segs);
+    const uint32_t per_frame = (uint32_t)(p.n_strips * p.n_segs);
+    frame = (int)((uint32_t)work / per_frame);
+    const uint32_t rem = (uint32_t)work - (uint32_t)frame * per_frame;
+    const uint32_t seg = rem / (uint32_t)p.n_strips, strip = rem - seg * (uint32_t)p.n_strips;
+    g.m0 = (int)((strip * (uint32_t)p.mw) / (uint32_t)p.n_strips);          // mw, mh <= 4096: no overflow
+    g.m1 = (int)(((strip + 1) * (uint32_t)p.mw) / (uint32_t)p.n_strips);
+    g.r0 = (int)((seg * (uint32_t)p.mh) / (uint32_t)p.n_segs);
+    g.r1 = (int)(((seg + 1) * (uint32_t)p.mh) / (uint32_t)p.n_segs);
     g.xb0 = 16 * (g.m0 - 1);
     g.band_mcus = g.m1 - g.m0 + 2;
     g.frame = p.rgb + (int64_t)frame * p.frame_stride;

@@ -9,7 +9,14 @@
 
 namespace v5 {
 
+// V5_FOR_WARP(body): same, but the ordering point is only warp-wide (device: __syncwarp()).
 #ifdef __CUDA_ARCH__
+#define V5_FOR_WARP(...)                     \
+    {                                        \
+        const int tid = (int)threadIdx.x;    \
+        __VA_ARGS__;                         \
+    }                                        \
+    __syncwarp();
 #define V5_FOR_THREADS(...)                  \
     {                                        \
         const int tid = (int)threadIdx.x;    \
@@ -19,6 +26,8 @@ namespace v5 {
     }                                        \
     __syncthreads();
 #else
+#define V5_FOR_WARP(...) \
+    for (int tid = 0; tid < NT; tid++) { __VA_ARGS__; }
 #define V5_FOR_THREADS(...)                  \
     for (int tid = 0; tid < NT; tid++) {     \
         ThreadAcc &acc = acc_store[tid];     \
@@ -86,6 +95,11 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 
     V5_FOR_THREADS({
         for (int i = tid; i < 3 * 256; i += NT) (&S.hist[0][0])[i] = 0;
+        for (int i = tid; i < 2 * 64; i += NT) {
+            const QuantTab &q = p.q[i >> 6];
+            const int k = i & 63;
+            S.qtab[i >> 6][k] = QEntry{q.recip[k], q.bias[k], q.t[k], q.unbias[k]};
+        }
         if (tid == 0) {
             S.tex_sumabs = 0;
             S.tex_sumsq = 0;
@@ -105,7 +119,13 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
         if (has_band) {
             V5_FOR_THREADS(stage_load(tid, S, p, g, r))
             V5_FOR_THREADS(stage_convert(tid, S, p, g, r))
-            V5_FOR_THREADS(stage_blocks(tid, S, p, g, r, want_y))
+            const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
+            for (int round = 0; round < rounds; round++) {
+                V5_FOR_WARP(blocks_rows_fwd(tid, S, p, g, r, want_y, round))
+                V5_FOR_WARP(blocks_cols(tid, S, p, g, r, want_y, round))
+                V5_FOR_WARP(blocks_rows_inv(tid, S, p, g, r, want_y, round))
+            }
+            V5_FOR_THREADS((void)0)
         }
         V5_FOR_THREADS(stage_residual(tid, S, p, g, acc, r))
     }

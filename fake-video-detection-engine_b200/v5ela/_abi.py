@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libv5ela.so")
 EXPORTS = (
     "v5ela_abi_version", "v5ela_record_bytes", "v5ela_status_string", "v5ela_create", "v5ela_destroy",
     "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze",
-    "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count",
+    "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
+    "v5ela_profile_read",
 )
 
 
@@ -53,7 +54,9 @@ def load() -> ctypes.CDLL:
     lib.v5ela_analyze.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
     lib.v5ela_enhance.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.v5ela_reduce_records.argtypes = [vp, vp, i32, i32, vp, vp]
-    lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.v5ela_profile_enable.argtypes = [vp, i32]
+    lib.v5ela_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     lib.v5ela_launch_count.restype = i64
     lib.v5ela_launch_count.argtypes = [vp]
     for name in EXPORTS:
@@ -113,9 +116,19 @@ class Handle:
         self._check(self._lib.v5ela_reduce_records(self._h, d_records, n, group, d_out, stream or None))
 
     def analyze_host(self, rgb_host: int, n: int, h: int, w: int, records_host: int, residual_host: int | None = None,
-                     enhanced_host: int | None = None):
+                     enhanced_host: int | None = None, stream: int | None = None):
+        """Host-buffer entry point; synchronous when `stream` is None, else asynchronous on that stream."""
         self._check(self._lib.v5ela_analyze_host(self._h, rgb_host, n, h, w, records_host, residual_host or None,
-                                                 enhanced_host or None))
+                                                 enhanced_host or None, stream or None))
+
+    def profile_enable(self, enable: bool = True):
+        self._check(self._lib.v5ela_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset: bool = True):
+        """-> (summed fused-kernel milliseconds, launches) since the last reset (waits for the recorded events)."""
+        ms, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
+        self._check(self._lib.v5ela_profile_read(self._h, ctypes.byref(ms), ctypes.byref(cnt), 1 if reset else 0))
+        return ms.value, cnt.value
 
     @property
     def launch_count(self) -> int:

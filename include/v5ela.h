@@ -113,12 +113,25 @@ V5ELA_API int v5ela_enhance(v5ela_handle *h, const uint8_t *d_residual, const vo
 V5ELA_API int v5ela_reduce_records(v5ela_handle *h, const void *d_records, int n, int group, void *d_out, void *cuda_stream);
 
 /*
- * Convenience for callers without a CUDA runtime of their own (the drop-in node, the e2e benchmark): same as
- * v5ela_analyze but with HOST buffers; copies in on the handle's stream, runs, copies records (and the optional
- * residual / enhanced maps) back, and synchronises before returning. Host buffers should be pinned for full speed.
+ * The reference-facing entry point for callers that hold HOST memory (the drop-in node, the end-to-end benchmark):
+ * same work as v5ela_analyze, but copies the frames in, and the records (and the optional residual / enhanced maps)
+ * back. The batch is cut into chunks whose host->device copies overlap the kernels of the previous chunk (two internal
+ * streams forked from / joined to `cuda_stream`). Host buffers should be pinned (cudaHostAlloc / torch pin_memory) for
+ * the copies to be asynchronous and full speed.
+ *   cuda_stream == NULL : runs on an internal stream and SYNCHRONISES before returning (outputs valid on return).
+ *   cuda_stream != NULL : fully asynchronous; outputs are valid once the caller has synchronised that stream.
  */
 V5ELA_API int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int height, int width,
-                       void *records_host, uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null);
+                       void *records_host, uint8_t *residual_host_or_null, uint8_t *enhanced_host_or_null,
+                       void *cuda_stream);
+
+/*
+ * Measurement hook: while enabled, every v5ela_analyze records a CUDA event pair around the fused kernel on the launch
+ * stream. v5ela_profile_read waits for the recorded events, returns the summed kernel time and launch count since the
+ * last reset, and optionally resets. Used by bench.py for the roofline line; off by default.
+ */
+V5ELA_API int v5ela_profile_enable(v5ela_handle *h, int enable);
+V5ELA_API int v5ela_profile_read(v5ela_handle *h, double *fused_ms_sum, int64_t *fused_launches, int reset);
 
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches evidence). */
 V5ELA_API int64_t v5ela_launch_count(const v5ela_handle *h);

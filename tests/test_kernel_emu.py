@@ -1,0 +1,70 @@
+"""CPU: the CUDA kernel's device code (csrc/*.cuh), compiled by g++ with threads emulated per barrier phase
+(tests/emu/v5ela_emu.cpp), against the oracle. Debug aid for band/halo/edge indexing in a container without a GPU;
+the GPU parity tests (-m gpu) are the real gate."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import HERE, golden_frame, load_json, record_matches_golden, sha
+from oracle import c_oracle
+from oracle.pil_oracle import RECORD_DTYPE
+from v5ela.synth import gen_frame
+
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "emu", "libv5ela_emu.so")
+    src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
+    csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"),
+                               "-I", csrc, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    lib.v5emu_analyze.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_void_p, u8p, ctypes.c_int]
+
+    def run(frames, q, seg=0):
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        recs = np.zeros(n, RECORD_DTYPE)
+        res = np.zeros((n, h, w, 3), np.uint8)
+        rc = lib.v5emu_analyze(frames.ctypes.data_as(u8p), n, h, w, h * w * 3, w * 3, q,
+                               recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p), seg)
+        assert rc == 0
+        return recs, res
+
+    run.lib = lib
+    return run
+
+
+def test_exact_division_constants(emu):
+    assert emu.lib.v5emu_quant_selftest() == 0          # every table entry 1..255 x every coefficient -8192..8192
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (2, 3), (9, 1), (16, 16), (17, 33), (31, 9), (33, 497), (100, 1000), (272, 496)])
+@pytest.mark.parametrize("seg", [0, 1, 3])
+def test_emulated_kernel_vs_oracle(emu, hw, seg):
+    h, w = hw
+    rng = np.random.default_rng(h * 7 + w)
+    for q in (90, 25):
+        for frame in (gen_frame(3, h, w, 1), rng.integers(0, 256, (h, w, 3), dtype=np.uint8)):
+            o = c_oracle.analyze_frame(frame, q)
+            recs, res = emu(frame[None], q, seg)
+            assert np.array_equal(res[0], o["residual"])
+            assert recs[0].tobytes() == o["record"].tobytes()
+
+
+def test_emulated_kernel_vs_reference_goldens(emu):
+    cases = [c for c in load_json("frames_golden.json")["cases"] if c["h"] * c["w"] <= 64 * 96]
+    assert len(cases) > 20
+    for case in cases:
+        recs, res = emu(golden_frame(case)[None], case["q"])
+        assert sha(res[0]) == case["resid_sha"]
+        assert record_matches_golden(recs[0], case) == []

@@ -18,15 +18,22 @@
 
 static_assert(sizeof(v5ela_record) == 3144, "V5F v1 record layout");
 static_assert(sizeof(v5::KParams) <= 4096, "kernel parameters must fit the 4 KB parameter bank");
-static_assert(sizeof(v5::Smem) <= 113 * 1024, "two CTAs per SM");
+static_assert(sizeof(v5::Smem) <= (227 * 1024) / v5::MIN_CTAS - 1024, "MIN_CTAS CTAs per SM must fit in shared memory");
 
 namespace v5 {
 
-__global__ void __launch_bounds__(NT, 2) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
+__global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     ThreadAcc acc_store[1];
+    acc_store[0].phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[0]), 1);
+        mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[1]), 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
     // Work items are equal-sized (same strip/segment shapes in every frame): a static stride is balanced.
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) process_work_item(S, p, work, acc_store);
 }
@@ -132,7 +139,7 @@ struct v5ela_handle {
     int quality = 90;
     int sm_count = 0;
     int seg_rows = 0;                      // 0 = default
-    int ctas_per_sm = 2;
+    int ctas_per_sm = v5::MIN_CTAS;
     int64_t launches = 0;
     cudaStream_t own_stream = nullptr;     // v5ela_analyze_host with a NULL stream
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;   // chunk pipeline of v5ela_analyze_host

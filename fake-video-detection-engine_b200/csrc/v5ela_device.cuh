@@ -18,6 +18,7 @@
 // every CUDA-specific construct therefore goes through the small V5_* shims below. The product never runs that build.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "v5ela.h"
 
@@ -32,8 +33,18 @@
 namespace v5 {
 
 // ----------------------------------------------------------------------------------------------- geometry constants
-constexpr int NT = 256;                     // threads per CTA
-constexpr int TW_MAX = 30;                  // strip width, MCUs (16 px)
+#ifndef V5_NT
+#define V5_NT 256
+#endif
+#ifndef V5_TW_MAX
+#define V5_TW_MAX 30
+#endif
+#ifndef V5_MIN_CTAS
+#define V5_MIN_CTAS 2
+#endif
+constexpr int NT = V5_NT;                   // threads per CTA
+constexpr int TW_MAX = V5_TW_MAX;           // strip width, MCUs (16 px)
+constexpr int MIN_CTAS = V5_MIN_CTAS;       // resident CTAs per SM the kernel is built for
 constexpr int BAND_MCUS = TW_MAX + 2;       // + halo MCU column each side
 constexpr int BAND_PX = BAND_MCUS * 16;     // 512
 constexpr int RGB_PITCH = BAND_PX * 3;      // 1536 bytes per band line
@@ -77,40 +88,114 @@ inline void make_quant(const uint16_t tab[64], QuantTab &q)
 }
 
 // ------------------------------------------------------------------------------------------------------- shims
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+struct alignas(8) U2 { uint32_t x, y; };
+
 #ifdef __CUDA_ARCH__
 V5_DEV uint32_t umulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 V5_DEV int clamp255(int v) { return __vimin_s32_relu(v, 255); }
 V5_DEV void smem_inc(uint32_t *p) { atomicAdd(p, 1u); }
+V5_DEV uint32_t absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+// PTX prmt (default mode): result byte i = byte sel[4i+2:4i] of {b,a}; selector bit 3 replicates that byte's sign bit.
+V5_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 #else
 inline uint32_t umulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 inline void smem_inc(uint32_t *p) { *p += 1u; }
+inline uint32_t absdiff4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const int x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff;
+        r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
+}
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (sel >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t)(v >> (8 * (n & 7))) & 0xff;
+        if (n & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 #endif
 
-struct alignas(16) U4 { uint32_t x, y, z, w; };
-struct alignas(8) U2 { uint32_t x, y; };
+// Bulk asynchronous copy (TMA, non-tensor form) global -> shared, completion counted in bytes on an mbarrier.
+#ifdef __CUDA_ARCH__
+V5_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+V5_DEV void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+V5_DEV void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+V5_DEV void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+V5_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+V5_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+V5_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "V5_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra V5_DONE_%=;\n\t"
+        "bra V5_WAIT_%=;\n\t"
+        "V5_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+#else
+inline void mbar_init(uint64_t *, uint32_t) {}
+inline void mbar_init_fence() {}
+inline void async_proxy_fence() {}
+inline void mbar_expect_tx(uint64_t *, uint32_t) {}
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+inline void mbar_wait(uint64_t *, uint32_t) {}
+#endif
 
-V5_DEV uint32_t byte_of(uint32_t w, int k) { return (w >> (8 * k)) & 0xffu; }
+// byte k (compile-time) of w, zero-extended: one PRMT
+V5_DEV uint32_t byte_of(uint32_t w, int k) { return prmt(w, 0u, 0x4440u + (uint32_t)k); }
+// four values 0..255 held in ints -> one word: three PRMTs
 V5_DEV uint32_t pack4(int a, int b, int c, int d)
 {
-    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+    return prmt(prmt((uint32_t)a, (uint32_t)b, 0x0040u), prmt((uint32_t)c, (uint32_t)d, 0x0040u), 0x5410u);
 }
 
 // ------------------------------------------------------------------------------------------------- shared memory
 struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
 
+constexpr int RING = 24;                // luma ring lines: 16 of the current band + the 2 (yorig) / 1 (ydec) carried ones
+
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
-    uint8_t rgb[16][RGB_PITCH];         // the current band
+    uint8_t rgb[2][16][RGB_PITCH];      // band r in rgb[r & 1]; the other buffer receives band r+1 (bulk async copy)
     uint8_t rgb_carry[2][RGB_PITCH];    // line 15 of band r in rgb_carry[r & 1] (finished one iteration later)
-    uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad), fDCT rows -> columns
-    uint32_t rscratch[NT / 32][8 * 36]; //              and IDCT columns -> rows; 36-word block stride = no conflicts
-    uint8_t yorig[32][Y_PITCH];         // luma of the original; band r line l at [16*(r&1) + l]
-    uint8_t ydec[32][Y_PITCH];          // luma after the JPEG round trip, same ring
+    uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad): both transpositions;
+                                        // 36-word block stride = conflict-free scattered stores and 128-bit loads
+    uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
+    uint8_t ydec[RING][Y_PITCH];        // luma after the JPEG round trip, same ring
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
     uint8_t cdec[2][16][C_PITCH];       // decoded Cb/Cr; band r chroma line j at [8*(r&1) + j]
     uint32_t hist[3][256];
     unsigned long long tex_sumabs, tex_sumsq;
+    unsigned long long full_bar[2];     // mbarriers: "band has landed in rgb[b]"
     uint32_t tex_maxabs;
     uint32_t pad_[3];
 };
@@ -125,42 +210,76 @@ struct Geo {
     int band_mcus;              // m1 - m0 + 2
 };
 
-struct ThreadAcc {              // per-thread accumulators that live across bands of one work item
+struct ThreadAcc {              // per-thread state that lives across barriers (registers on the device)
     unsigned long long tex_sumsq;
     uint32_t tex_sumabs;
     uint32_t tex_maxabs;
+    uint32_t phase;             // bit b: parity of the next wait on full_bar[b] (persists across work items)
+    int col[16];                // block stage: two columns between the two halves of the column sub-stage
 };
 
-V5_DEV int ring16(int r, int l) { return (16 * (r & 1) + l) & 31; }   // l in [-2, 15]
+V5_DEV int ring16(int r, int l)                                         // l in [-2, 15]
+{
+    int i = 16 * (r % 3) + l;                                           // 16r mod 24 cycles 0,16,8
+    i = i >= RING ? i - RING : i;
+    i = i >= RING ? i - RING : i;
+    return i < 0 ? i + RING : i;
+}
 V5_DEV int ring8(int r, int j) { return (8 * (r & 1) + j) & 15; }     // j in [-1, 7]
 
 // ------------------------------------------------------------------------------------------------ stage: load band
 // Band r, lines 0..15 <- frame rows min(16r + l, H-1), pixel columns [xb0, xb0 + 16*band_mcus) clipped to [0, W);
 // columns W .. Wm-1 replicate pixel W-1 (A.3: edges are replicated in full-resolution colour space).
-V5_DEV void stage_load(int tid, Smem &S, const KParams &p, const Geo &g, int r)
+// With 16-byte aligned frames the 16-byte-multiple prefix of every line is fetched by one bulk asynchronous copy per
+// line (issued by one thread one whole iteration ahead, completion on full_bar[r & 1]); the few remaining bytes of a
+// ragged right edge, the padding columns, and unaligned inputs use ordinary loads.
+struct LoadGeo { int xs, nbytes, dst0, npad3, nbulk; };
+
+V5_DEV LoadGeo load_geo(const KParams &p, const Geo &g)
 {
-    const int xs = g.xb0 < 0 ? 0 : g.xb0;
+    LoadGeo L;
+    L.xs = g.xb0 < 0 ? 0 : g.xb0;
     int xe = g.xb0 + 16 * g.band_mcus;
     const int xpad_end = xe > 16 * p.mw ? 16 * p.mw : xe;       // last padded column (exclusive) inside this band
     if (xe > p.w) xe = p.w;
-    const int nbytes = 3 * (xe - xs);
-    const int dst0 = 3 * (xs - g.xb0);
-    const int npad3 = 3 * (xpad_end - p.w);                     // > 0 only in the strip that holds the right edge
-    uint8_t(*dst)[RGB_PITCH] = S.rgb;
+    L.nbytes = 3 * (xe - L.xs);
+    L.dst0 = 3 * (L.xs - g.xb0);
+    L.npad3 = 3 * (xpad_end - p.w);                             // > 0 only in the strip that holds the right edge
+    L.nbulk = p.vec_ok ? (L.nbytes & ~15) : 0;
+    return L;
+}
+
+V5_DEV bool use_bulk(const KParams &p, const Geo &g) { return load_geo(p, g).nbulk > 0; }
+
+// one thread: arm the barrier with the byte count, then one bulk copy per line
+V5_DEV void stage_prefetch(Smem &S, const KParams &p, const Geo &g, int r)
+{
+    const LoadGeo L = load_geo(p, g);
+    unsigned long long *bar = &S.full_bar[r & 1];
+    async_proxy_fence();                                        // earlier generic accesses to this buffer are done
+    mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
+    for (int l = 0; l < 16; l++) {
+        int y = 16 * r + l;
+        if (y > p.h - 1) y = p.h - 1;
+        bulk_g2s(&S.rgb[r & 1][l][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
+                 reinterpret_cast<uint64_t *>(bar));
+    }
+}
+
+// all threads: whatever the bulk copy does not cover (everything when bulk == false)
+V5_DEV void stage_load_rest(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool bulk)
+{
+    const LoadGeo L = load_geo(p, g);
+    uint8_t(*dst)[RGB_PITCH] = S.rgb[r & 1];
     const int warp = tid >> 5, lane = tid & 31;
+    int done = bulk ? L.nbulk : 0;
+    if (done == L.nbytes && L.npad3 <= 0) return;
     for (int l = warp; l < 16; l += NT / 32) {                  // one warp per band line
         int y = 16 * r + l;
         if (y > p.h - 1) y = p.h - 1;
-        const uint8_t *src = g.frame + (int64_t)y * p.row_stride + 3 * xs;
-        int done = 0;
-        if (p.vec_ok) {
-            const int nvec = nbytes >> 4;
-            for (int v = lane; v < nvec; v += 32)
-                *reinterpret_cast<U4 *>(&dst[l][dst0 + 16 * v]) = reinterpret_cast<const U4 *>(src)[v];
-            done = nvec << 4;
-        }
-        for (int b = done + lane; b < nbytes; b += 32) dst[l][dst0 + b] = src[b];
-        for (int b = lane; b < npad3; b += 32)
+        const uint8_t *src = g.frame + (int64_t)y * p.row_stride + 3 * L.xs;
+        for (int b = done + lane; b < L.nbytes; b += 32) dst[l][L.dst0 + b] = src[b];
+        for (int b = lane; b < L.npad3; b += 32)
             dst[l][3 * (p.w - g.xb0) + b] = g.frame[(int64_t)y * p.row_stride + 3 * (p.w - 1) + (b % 3)];
     }
 }
@@ -223,7 +342,7 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
     const int last_cline = ((p.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
     const int last_line = p.h - 1 - 16 * r;                     // local index of the last real pixel line
-    const uint8_t(*src)[RGB_PITCH] = S.rgb;
+    const uint8_t(*src)[RGB_PITCH] = S.rgb[r & 1];
     for (int i = tid; i < RGB_PITCH / 16; i += NT)              // keep line 15 for the next iteration's residual stage
         reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
     for (int u = tid; u < 8 * 2 * BAND_MCUS; u += NT) {          // unit = 2 lines x 8 px
@@ -378,17 +497,21 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     return t;
 }
 
+V5_DEV BlockTask block_task_of(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+{
+    return block_task(round * (NT / 4) + (tid >> 5) * 8 + ((tid & 31) >> 2), S, p, g, r, want_y);
+}
+
 V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
 
-V5_DEV uint32_t pack_s16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
-V5_DEV int s16_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+V5_DEV uint32_t pack_s16(int lo, int hi) { return prmt((uint32_t)lo, (uint32_t)hi, 0x5410u); }
+V5_DEV int s16_lo(uint32_t w) { return (int)prmt(w, 0u, 0x9910u); }         // sign-extend the low half: one PRMT
 V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
 
 // sub-stage 1: forward row pass of rows 2j, 2j+1 -> tscratch (column-major pairs)
-V5_DEV void blocks_rows_fwd(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
-    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
     if (!t.active) return;
     int a[8], b[8];
     const U2 wa = *reinterpret_cast<const U2 *>(t.in + (2 * j) * t.pitch);
@@ -405,11 +528,10 @@ V5_DEV void blocks_rows_fwd(int tid, Smem &S, const KParams &p, const Geo &g, in
     for (int c = 0; c < 8; c++) ts[4 * c + j] = pack_s16(a[c], b[c]);
 }
 
-// sub-stage 2: columns 2j, 2j+1: forward column pass, quantise + dequantise (A.5), inverse column pass -> rscratch
-V5_DEV void blocks_cols(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+// sub-stage 2a: columns 2j, 2j+1: forward column pass, quantise + dequantise (A.5), inverse column pass -> registers
+V5_DEV void blocks_cols(int tid, Smem &S, const BlockTask &t, int *col)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
-    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
     if (!t.active) return;
     const uint32_t *ts = &S.tscratch[warp][36 * bw];
     const U4 w0 = *reinterpret_cast<const U4 *>(ts + 8 * j), w1 = *reinterpret_cast<const U4 *>(ts + 8 * j + 4);
@@ -426,18 +548,29 @@ V5_DEV void blocks_cols(int tid, Smem &S, const KParams &p, const Geo &g, int r,
     }
     idct8<1, false>(a);
     idct8<1, false>(b);
-    uint32_t *rs = &S.rscratch[warp][36 * bw];
 #pragma unroll
-    for (int k = 0; k < 8; k++) rs[4 * k + j] = pack_s16(a[k], b[k]);
+    for (int k = 0; k < 8; k++) {
+        col[k] = a[k];
+        col[8 + k] = b[k];
+    }
+}
+
+// sub-stage 2b (after every thread of the warp has read its columns): scatter them back row-major into the scratch
+V5_DEV void blocks_cols_store(int tid, Smem &S, const BlockTask &t, const int *col)
+{
+    const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
+    if (!t.active) return;
+    uint32_t *rs = &S.tscratch[warp][36 * bw];
+#pragma unroll
+    for (int k = 0; k < 8; k++) rs[4 * k + j] = pack_s16(col[k], col[8 + k]);
 }
 
 // sub-stage 3: final inverse row pass of rows 2j, 2j+1, +128, clamp, store bytes
-V5_DEV void blocks_rows_inv(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
+V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
-    const BlockTask t = block_task(round * (NT / 4) + warp * 8 + bw, S, p, g, r, want_y);
     if (!t.active) return;
-    const uint32_t *rs = &S.rscratch[warp][36 * bw];
+    const uint32_t *rs = &S.tscratch[warp][36 * bw];
     const U4 w0 = *reinterpret_cast<const U4 *>(rs + 8 * j), w1 = *reinterpret_cast<const U4 *>(rs + 8 * j + 4);
     int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
     int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
@@ -451,6 +584,7 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const KParams &p, const Geo &g, in
 // Horizontal+vertical fancy upsample (A.7) of one chroma component for 8 output pixels of one line.
 // lc / ln: decoded chroma lines (current row, neighbour row), pointing at this unit's first chroma column (4-aligned);
 // columns -1 and 4 are the horizontal neighbours. gcx0 = global chroma column of lc[0]; wc1 = Wc - 1.
+// Outputs are the upsampled samples MINUS 128 (what the colour conversion wants).
 V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, bool fancy, int out[8])
 {
     const uint32_t c0 = *reinterpret_cast<const uint32_t *>(lc - 4), n0 = *reinterpret_cast<const uint32_t *>(ln - 4);
@@ -458,7 +592,7 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
     const uint32_t c2 = *reinterpret_cast<const uint32_t *>(lc + 4), n2 = *reinterpret_cast<const uint32_t *>(ln + 4);
     if (!fancy) {                                               // Wc <= 2: libjpeg uses plain replication
 #pragma unroll
-        for (int j = 0; j < 4; j++) out[2 * j] = out[2 * j + 1] = (int)byte_of(c1, j);
+        for (int j = 0; j < 4; j++) out[2 * j] = out[2 * j + 1] = (int)byte_of(c1, j) - 128;
         return;
     }
     int cs[6];                                                  // cs[j+1] = 3*c[r][j] + c[nb][j], j = -1..4
@@ -474,8 +608,8 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        out[2 * j] = (3 * cs[j + 1] + cs[j] + 8) >> 4;
-        out[2 * j + 1] = (3 * cs[j + 1] + cs[j + 2] + 7) >> 4;
+        out[2 * j] = (3 * cs[j + 1] + cs[j] + (8 - 2048)) >> 4;           // "- 128" folded in: 2048 = 128 << 4
+        out[2 * j + 1] = (3 * cs[j + 1] + cs[j + 2] + (7 - 2048)) >> 4;
     }
 }
 
@@ -500,8 +634,10 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
 
     // ---- reconstruct (A.8), residual (A.9), histogram
+    // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
+    // (Y << 16) + 32768 straight from the packed luma word, the multiply-adds do the rest.
     const U2 yd = *reinterpret_cast<const U2 *>(&S.ydec[ring16(r, l)][col]);
-    const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[l][3 * col];
+    const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[r & 1][l][3 * col];
     const uint32_t ydw[2] = {yd.x, yd.y};
     uint32_t ow[6], dw[6];
 #pragma unroll
@@ -509,31 +645,21 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
         const U2 t = reinterpret_cast<const U2 *>(orig)[i];
         ow[2 * i] = t.x; ow[2 * i + 1] = t.y;
     }
-#pragma unroll
-    for (int i = 0; i < 6; i++) dw[i] = 0;
+    int rec[24];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int yy = (int)byte_of(ydw[k >> 2], k & 3);
+        const int ykr = (int)prmt(ydw[k >> 2], 0x00008000u, 0x4054u + ((uint32_t)(k & 3) << 8));   // bytes: 00 80 Y 00
         const int cbv = cb[k], crv = cr[k];
-        const int rr = clamp255(yy + ((91881 * crv + (32768 - 91881 * 128)) >> 16));
-        const int gg = clamp255(yy + ((-22554 * cbv - 46802 * crv + (32768 + (22554 + 46802) * 128)) >> 16));
-        const int bb = clamp255(yy + ((116130 * cbv + (32768 - 116130 * 128)) >> 16));
-        const int o = 3 * k;
-        int dr = (int)byte_of(ow[o >> 2], o & 3) - rr;
-        int dg = (int)byte_of(ow[(o + 1) >> 2], (o + 1) & 3) - gg;
-        int db = (int)byte_of(ow[(o + 2) >> 2], (o + 2) & 3) - bb;
-        dr = dr < 0 ? -dr : dr;
-        dg = dg < 0 ? -dg : dg;
-        db = db < 0 ? -db : db;
-        if (k < nvalid) {
-            smem_inc(&S.hist[0][dr]);
-            smem_inc(&S.hist[1][dg]);
-            smem_inc(&S.hist[2][db]);
-        }
-        dw[o >> 2] |= (uint32_t)dr << (8 * (o & 3));
-        dw[(o + 1) >> 2] |= (uint32_t)dg << (8 * ((o + 1) & 3));
-        dw[(o + 2) >> 2] |= (uint32_t)db << (8 * ((o + 2) & 3));
+        rec[3 * k] = clamp255((91881 * crv + ykr) >> 16);
+        rec[3 * k + 1] = clamp255((-22554 * cbv + (-46802 * crv + ykr)) >> 16);
+        rec[3 * k + 2] = clamp255((116130 * cbv + ykr) >> 16);
     }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        dw[i] = absdiff4(ow[i], pack4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
+#pragma unroll
+    for (int b = 0; b < 24; b++)
+        if (b < 3 * nvalid) smem_inc(&S.hist[b % 3][byte_of(dw[b >> 2], b & 3)]);
     if (g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
         if (nvalid >= 8 && p.resid_vec_ok) {

@@ -14,6 +14,8 @@ namespace v5 {
 #define V5_FOR_WARP(...)                     \
     {                                        \
         const int tid = (int)threadIdx.x;    \
+        ThreadAcc &acc = acc_store[0];       \
+        (void)acc;                           \
         __VA_ARGS__;                         \
     }                                        \
     __syncwarp();
@@ -26,8 +28,12 @@ namespace v5 {
     }                                        \
     __syncthreads();
 #else
-#define V5_FOR_WARP(...) \
-    for (int tid = 0; tid < NT; tid++) { __VA_ARGS__; }
+#define V5_FOR_WARP(...)                     \
+    for (int tid = 0; tid < NT; tid++) {     \
+        ThreadAcc &acc = acc_store[tid];     \
+        (void)acc;                           \
+        __VA_ARGS__;                         \
+    }
 #define V5_FOR_THREADS(...)                  \
     for (int tid = 0; tid < NT; tid++) {     \
         ThreadAcc &acc = acc_store[tid];     \
@@ -112,18 +118,31 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 
     // Bands r0-1 and r1 only contribute decoded chroma / original luma to the rows next to them.
     const int r_first = g.r0 > 0 ? g.r0 - 1 : 0;
+    const bool bulk = use_bulk(p, g);
+    V5_FOR_THREADS(if (bulk && tid == 0) stage_prefetch(S, p, g, r_first))
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;
         const bool want_y = r >= g.r0 && r < g.r1;
         if (!has_band && 16 * r - 1 >= p.h) break;          // nothing left below the image
         if (has_band) {
-            V5_FOR_THREADS(stage_load(tid, S, p, g, r))
+            // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
+            // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
+            const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
+            V5_FOR_THREADS({
+                if (bulk && next_band && tid == 0) stage_prefetch(S, p, g, r + 1);
+                stage_load_rest(tid, S, p, g, r, bulk);
+                if (bulk) {
+                    mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[r & 1]), (acc.phase >> (r & 1)) & 1u);
+                    acc.phase ^= 1u << (r & 1);
+                }
+            })
             V5_FOR_THREADS(stage_convert(tid, S, p, g, r))
             const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
             for (int round = 0; round < rounds; round++) {
-                V5_FOR_WARP(blocks_rows_fwd(tid, S, p, g, r, want_y, round))
-                V5_FOR_WARP(blocks_cols(tid, S, p, g, r, want_y, round))
-                V5_FOR_WARP(blocks_rows_inv(tid, S, p, g, r, want_y, round))
+                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_rows_fwd(tid, S, t))
+                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_cols(tid, S, t, acc.col))
+                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_cols_store(tid, S, t, acc.col))
+                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_rows_inv(tid, S, t))
             }
             V5_FOR_THREADS((void)0)
         }

@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libv5ela.so")
+# V5ELA_LIB: development knob — load another build of the SAME library (kernel-tuning variants under profiles/variants/).
+LIB_PATH = os.environ.get("V5ELA_LIB") or os.path.join(_HERE, "libv5ela.so")
 
 # Every symbol include/v5ela.h declares; tests assert the built library exports exactly these.
 EXPORTS = (

@@ -215,7 +215,9 @@ def run_native_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     n_gpus = world
     K, Wm = args.steps, args.warmup
     n_local, total = FRAMES_PER_GPU, FRAMES_PER_GPU * world
@@ -253,11 +255,12 @@ def run_native_arm(args):
     launches = handle.launch_count - launches0
     fused_ms, fused_n = handle.profile_read(reset=True)
     handle.profile_enable(False)
-    # keep the GPU busy a little longer so that slow nvidia-smi polling still sees the load
+    # keep the GPU busy a little longer so that slow nvidia-smi polling still sees the load (local work only: the number
+    # of iterations depends on the wall clock, so no collective may be issued here)
     t_end = time.perf_counter() + 0.6
     while time.perf_counter() < t_end:
-        step()
-    torch.cuda.synchronize()
+        analyze_batch(frames, quality=QUALITY, records_out=records, handle=handle)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

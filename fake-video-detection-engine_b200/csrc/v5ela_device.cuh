@@ -181,16 +181,17 @@ V5_DEV uint32_t pack4(int a, int b, int c, int d)
 // ------------------------------------------------------------------------------------------------- shared memory
 struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
 
-constexpr int RING = 24;                // luma ring lines: 16 of the current band + the 2 (yorig) / 1 (ydec) carried ones
+constexpr int RING = 24;                // yorig ring lines: 16 of the current band + the 2 carried ones, rounded up to 8
+constexpr int RINGD = 20;               // ydec ring lines: 16 + 1 carried, rounded up to 4
+constexpr int BSTRIDE = 72;             // block stage scratch: words per 8x8 block (64 + 8: conflict-free 64-bit stores)
 
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
     uint8_t rgb[2][16][RGB_PITCH];      // band r in rgb[r & 1]; the other buffer receives band r+1 (bulk async copy)
     uint8_t rgb_carry[2][RGB_PITCH];    // line 15 of band r in rgb_carry[r & 1] (finished one iteration later)
-    uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad): both transpositions;
-                                        // 36-word block stride = conflict-free scattered stores and 128-bit loads
+    uint32_t tscratch[NT / 32][8 * BSTRIDE];   // block stage: per warp, 8 blocks x 64 int32 (+pad): both transpositions
     uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
-    uint8_t ydec[RING][Y_PITCH];        // luma after the JPEG round trip, same ring
+    uint8_t ydec[RINGD][Y_PITCH];       // luma after the JPEG round trip; band r line l at [(16r + l) mod RINGD]
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
     uint8_t cdec[2][16][C_PITCH];       // decoded Cb/Cr; band r chroma line j at [8*(r&1) + j]
     uint32_t hist[3][256];
@@ -224,6 +225,12 @@ V5_DEV int ring16(int r, int l)                                         // l in 
     i = i >= RING ? i - RING : i;
     i = i >= RING ? i - RING : i;
     return i < 0 ? i + RING : i;
+}
+V5_DEV int ringd(int r, int l)                                          // l in [-1, 15]
+{
+    int i = 16 * (r % 5) + l;                                           // 16r mod 20 cycles 0,16,12,8,4
+    i = i >= 3 * RINGD ? i - 3 * RINGD : (i >= 2 * RINGD ? i - 2 * RINGD : (i >= RINGD ? i - RINGD : i));
+    return i < 0 ? i + RINGD : i;
 }
 V5_DEV int ring8(int r, int j) { return (8 * (r & 1) + j) & 15; }     // j in [-1, 7]
 
@@ -450,16 +457,17 @@ V5_DEV void idct8(int *v)
 }
 
 // The block stage. Four threads share one 8x8 block; thread j owns rows 2j,2j+1 in the row passes and columns 2j,2j+1
-// in the column passes. The two transpositions go through a per-warp shared-memory scratch as int16 pairs (ranges:
-// |fDCT row output| <= 4096, |IDCT column output| <= 21047 by Parseval + quantisation error), laid out so
-// that both the scattered 32-bit stores and the 128-bit loads are bank-conflict free. Only __syncwarp() is needed between
-// the three sub-stages, and the code is ~600 instructions instead of ~1900 for a block-per-thread unrolling (the
-// instruction cache, not the ALUs, was the first version's limit).
+// in the column passes. The two transpositions go through a per-warp shared-memory scratch of int32 (64-bit scattered
+// stores, conflict-free with the 72-word block stride; 128-bit loads). Only __syncwarp() is needed between the
+// sub-stages, and the code is ~600 instructions instead of ~1900 for a block-per-thread unrolling (the instruction
+// cache, not the ALUs, was the first version's limit).
 struct BlockTask {
     const QEntry *q;
-    const uint8_t *in;
-    uint8_t *out;
+    const uint8_t *in;          // first row of the source block
+    uint8_t *out;               // column of the destination block in line 0 of its buffer
     int pitch;
+    int out_row;                // destination line of block row 0 ...
+    int out_wrap;               // ... in a ring of this many lines (rows wrap; an even row pair never straddles the end)
     bool active;
 };
 
@@ -471,15 +479,19 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     t.in = nullptr;
     t.out = nullptr;
     t.pitch = 0;
+    t.out_row = 0;
+    t.out_wrap = 1 << 20;
     const int tw = g.m1 - g.m0;
     const int nl = want_y ? 4 * tw : 0;
     if (blk < nl) {
         const int br = blk >= 2 * tw ? 1 : 0, bc = blk - br * 2 * tw;
         // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
         if (16 * r + 8 * br >= p.h || 16 * g.m0 + 8 * bc >= p.w) return t;
-        const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
-        t.in = &S.yorig[row][col];
-        t.out = &S.ydec[row][col];
+        const int col = 16 + 8 * bc;
+        t.in = &S.yorig[ring16(r, 8 * br)][col];
+        t.out = &S.ydec[0][col];
+        t.out_row = ringd(r, 8 * br);
+        t.out_wrap = RINGD;
         t.pitch = Y_PITCH;
         t.active = true;
     } else {
@@ -490,7 +502,8 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
         if (mcu < 0 || mcu >= p.mw) return t;
         t.q = S.qtab[1];
         t.in = &S.cenc[comp][0][8 * cbk];
-        t.out = &S.cdec[comp][ring8(r, 0)][8 * cbk];
+        t.out = &S.cdec[comp][0][8 * cbk];
+        t.out_row = ring8(r, 0);
         t.pitch = C_PITCH;
         t.active = true;
     }
@@ -504,11 +517,7 @@ V5_DEV BlockTask block_task_of(int tid, Smem &S, const KParams &p, const Geo &g,
 
 V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
 
-V5_DEV uint32_t pack_s16(int lo, int hi) { return prmt((uint32_t)lo, (uint32_t)hi, 0x5410u); }
-V5_DEV int s16_lo(uint32_t w) { return (int)prmt(w, 0u, 0x9910u); }         // sign-extend the low half: one PRMT
-V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
-
-// sub-stage 1: forward row pass of rows 2j, 2j+1 -> tscratch (column-major pairs)
+// sub-stage 1: forward row pass of rows 2j, 2j+1 -> scratch, column-major: word 8c + r holds element (r, c)
 V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
@@ -523,9 +532,20 @@ V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
     }
     fdct8<1, true>(a);
     fdct8<1, true>(b);
-    uint32_t *ts = &S.tscratch[warp][36 * bw];
+    uint32_t *ts = &S.tscratch[warp][BSTRIDE * bw + 2 * j];
 #pragma unroll
-    for (int c = 0; c < 8; c++) ts[4 * c + j] = pack_s16(a[c], b[c]);
+    for (int c = 0; c < 8; c++) *reinterpret_cast<U2 *>(ts + 8 * c) = U2{(uint32_t)a[c], (uint32_t)b[c]};
+}
+
+// two lines (rows or columns) 2j, 2j+1 of the transposed block: four 128-bit loads
+V5_DEV void load_pair(const uint32_t *ts, int j, int *a, int *b)
+{
+    const U4 a0 = *reinterpret_cast<const U4 *>(ts + 16 * j), a1 = *reinterpret_cast<const U4 *>(ts + 16 * j + 4);
+    const U4 b0 = *reinterpret_cast<const U4 *>(ts + 16 * j + 8), b1 = *reinterpret_cast<const U4 *>(ts + 16 * j + 12);
+    a[0] = (int)a0.x; a[1] = (int)a0.y; a[2] = (int)a0.z; a[3] = (int)a0.w;
+    a[4] = (int)a1.x; a[5] = (int)a1.y; a[6] = (int)a1.z; a[7] = (int)a1.w;
+    b[0] = (int)b0.x; b[1] = (int)b0.y; b[2] = (int)b0.z; b[3] = (int)b0.w;
+    b[4] = (int)b1.x; b[5] = (int)b1.y; b[6] = (int)b1.z; b[7] = (int)b1.w;
 }
 
 // sub-stage 2a: columns 2j, 2j+1: forward column pass, quantise + dequantise (A.5), inverse column pass -> registers
@@ -533,15 +553,14 @@ V5_DEV void blocks_cols(int tid, Smem &S, const BlockTask &t, int *col)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    const uint32_t *ts = &S.tscratch[warp][36 * bw];
-    const U4 w0 = *reinterpret_cast<const U4 *>(ts + 8 * j), w1 = *reinterpret_cast<const U4 *>(ts + 8 * j + 4);
-    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
-    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
+    int a[8], b[8];
+    load_pair(&S.tscratch[warp][BSTRIDE * bw], j, a, b);
     fdct8<1, false>(a);
     fdct8<1, false>(b);
+    const QEntry *qj = t.q + 2 * j;                             // row k of the table is a fixed offset from here
 #pragma unroll
     for (int k = 0; k < 8; k++) {                               // coefficient (row k, column 2j / 2j+1)
-        const QEntry ea = t.q[8 * k + 2 * j], eb = t.q[8 * k + 2 * j + 1];
+        const QEntry ea = qj[8 * k], eb = qj[8 * k + 1];
         const uint32_t xa = (uint32_t)(a[k] + (a[k] >> 31) + ea.bias), xb = (uint32_t)(b[k] + (b[k] >> 31) + eb.bias);
         a[k] = (int)umulhi32(xa, ea.recip) * ea.t - ea.unbias;
         b[k] = (int)umulhi32(xb, eb.recip) * eb.t - eb.unbias;
@@ -560,9 +579,9 @@ V5_DEV void blocks_cols_store(int tid, Smem &S, const BlockTask &t, const int *c
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    uint32_t *rs = &S.tscratch[warp][36 * bw];
+    uint32_t *rs = &S.tscratch[warp][BSTRIDE * bw + 2 * j];
 #pragma unroll
-    for (int k = 0; k < 8; k++) rs[4 * k + j] = pack_s16(col[k], col[8 + k]);
+    for (int k = 0; k < 8; k++) *reinterpret_cast<U2 *>(rs + 8 * k) = U2{(uint32_t)col[k], (uint32_t)col[8 + k]};
 }
 
 // sub-stage 3: final inverse row pass of rows 2j, 2j+1, +128, clamp, store bytes
@@ -570,14 +589,15 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    const uint32_t *rs = &S.tscratch[warp][36 * bw];
-    const U4 w0 = *reinterpret_cast<const U4 *>(rs + 8 * j), w1 = *reinterpret_cast<const U4 *>(rs + 8 * j + 4);
-    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
-    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
+    int a[8], b[8];
+    load_pair(&S.tscratch[warp][BSTRIDE * bw], j, a, b);
     idct8<1, true>(a);
     idct8<1, true>(b);
-    *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
-    *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
+    int row = t.out_row + 2 * j;
+    row = row >= t.out_wrap ? row - t.out_wrap : row;
+    uint8_t *o = t.out + row * t.pitch;
+    *reinterpret_cast<U2 *>(o) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
+    *reinterpret_cast<U2 *>(o + t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
 }
 
 // ------------------------------------------------------------------- stage: upsample, reconstruct, residual, Laplacian
@@ -585,6 +605,7 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
 // lc / ln: decoded chroma lines (current row, neighbour row), pointing at this unit's first chroma column (4-aligned);
 // columns -1 and 4 are the horizontal neighbours. gcx0 = global chroma column of lc[0]; wc1 = Wc - 1.
 // Outputs are the upsampled samples MINUS 128 (what the colour conversion wants).
+template <bool EDGE>
 V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, bool fancy, int out[8])
 {
     const uint32_t c0 = *reinterpret_cast<const uint32_t *>(lc - 4), n0 = *reinterpret_cast<const uint32_t *>(ln - 4);
@@ -600,20 +621,23 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
 #pragma unroll
     for (int j = 0; j < 4; j++) cs[1 + j] = 3 * (int)byte_of(c1, j) + (int)byte_of(n1, j);
     cs[5] = 3 * (int)byte_of(c2, 0) + (int)byte_of(n2, 0);
-    if (gcx0 == 0) cs[0] = cs[1];                               // left image edge: neighbour clamps to column 0
-    if (gcx0 + 4 > wc1) {                                       // right image edge inside / just after this unit
+    if (EDGE && gcx0 == 0) cs[0] = cs[1];                       // left image edge: neighbour clamps to column 0
+    if (EDGE && gcx0 + 4 > wc1) {                               // right image edge inside / just after this unit
 #pragma unroll
         for (int j = 1; j < 6; j++)
             if (gcx0 + j - 1 > wc1) cs[j] = cs[j - 1];
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        out[2 * j] = (3 * cs[j + 1] + cs[j] + (8 - 2048)) >> 4;           // "- 128" folded in: 2048 = 128 << 4
-        out[2 * j + 1] = (3 * cs[j + 1] + cs[j + 2] + (7 - 2048)) >> 4;
+        const int t3 = 3 * cs[j + 1] + (8 - 2048);                          // "- 128" folded in: 2048 = 128 << 4
+        out[2 * j] = (t3 + cs[j]) >> 4;
+        out[2 * j + 1] = (t3 + cs[j + 2] - 1) >> 4;                         // bias 7
     }
 }
 
 // 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
+// EDGE = false: the unit lies strictly inside the image horizontally (no masks, no reflection); true: general case.
+template <bool EDGE>
 V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
 {
     const int y = 16 * r + l;                                   // global pixel row
@@ -630,13 +654,13 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const int ccol = col >> 1, gcx0 = gx0 >> 1;
     const bool fancy = wc1 > 1;
     int cb[8], cr[8];
-    upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
-    upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    upsample8<EDGE>(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
+    upsample8<EDGE>(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
 
     // ---- reconstruct (A.8), residual (A.9), histogram
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
     // (Y << 16) + 32768 straight from the packed luma word, the multiply-adds do the rest.
-    const U2 yd = *reinterpret_cast<const U2 *>(&S.ydec[ring16(r, l)][col]);
+    const U2 yd = *reinterpret_cast<const U2 *>(&S.ydec[ringd(r, l)][col]);
     const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[r & 1][l][3 * col];
     const uint32_t ydw[2] = {yd.x, yd.y};
     uint32_t ow[6], dw[6];
@@ -659,10 +683,10 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
         dw[i] = absdiff4(ow[i], pack4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
 #pragma unroll
     for (int b = 0; b < 24; b++)
-        if (b < 3 * nvalid) smem_inc(&S.hist[b % 3][byte_of(dw[b >> 2], b & 3)]);
+        if (!EDGE || b < 3 * nvalid) smem_inc(&S.hist[b % 3][byte_of(dw[b >> 2], b & 3)]);
     if (g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
-        if (nvalid >= 8 && p.resid_vec_ok) {
+        if ((!EDGE || nvalid >= 8) && p.resid_vec_ok) {
 #pragma unroll
             for (int i = 0; i < 3; i++) reinterpret_cast<U2 *>(dst)[i] = U2{dw[2 * i], dw[2 * i + 1]};
         } else {
@@ -684,10 +708,10 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     // Reflection at the left/right image edge: the left neighbour of column 0 comes from a selected address; the single
     // pixel in column W-1 is left out of the vector loop (nacc) and done on its own below.
     const int wide = p.w > 1;
-    const int edge = nvalid <= 8 ? nvalid - 1 : -1;             // index of the pixel in image column W-1, if in this unit
+    const int edge = EDGE && nvalid <= 8 ? nvalid - 1 : -1;     // index of the pixel in image column W-1, if in this unit
     const int nacc = edge >= 0 ? edge : 8;
     int c[10];                                                  // c[k+1] = luma at column k, k = -1..8
-    c[0] = gx0 == 0 ? yc[wide] : yc[-1];
+    c[0] = EDGE && gx0 == 0 ? yc[wide] : yc[-1];
     c[9] = yc[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) c[k + 1] = (int)byte_of(cww[k >> 2], k & 3);
@@ -696,13 +720,13 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     for (int k = 0; k < 8; k++) {
         int lap = c[k] + c[k + 2] + (int)byte_of(uww[k >> 2], k & 3) + (int)byte_of(lww[k >> 2], k & 3) - 4 * c[k + 1];
         lap = lap < 0 ? -lap : lap;
-        if (k < nacc) {
+        if (!EDGE || k < nacc) {
             sabs += (uint32_t)lap;
             ssq += (uint32_t)(lap * lap);
             mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
         }
     }
-    if (edge >= 0) {
+    if (EDGE && edge >= 0) {
         const int ctr = yc[edge];
         const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;   // W-2 mirrors onto W
         int lap = 2 * side + (int)S.yorig[ring16(r, lu)][col + edge] + (int)S.yorig[ring16(r, ld)][col + edge] - 4 * ctr;
@@ -725,8 +749,12 @@ V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, Thr
     for (int u = tid; u < 16 * n8; u += NT) {
         const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
-        if (y < ylo || y >= yhi || 16 * g.m0 + 8 * ox >= p.w) continue;
-        residual_unit(S, p, g, acc, r, l, ox);
+        const int gx0 = 16 * g.m0 + 8 * ox;
+        if (y < ylo || y >= yhi || gx0 >= p.w) continue;
+        if (gx0 > 0 && gx0 + 8 < p.w)
+            residual_unit<false>(S, p, g, acc, r, l, ox);
+        else
+            residual_unit<true>(S, p, g, acc, r, l, ox);
     }
 }
 

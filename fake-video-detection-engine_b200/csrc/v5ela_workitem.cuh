@@ -10,7 +10,11 @@
 namespace v5 {
 
 // V5_FOR_WARP(body): same, but the ordering point is only warp-wide (device: __syncwarp()).
+// V5_BLOCK_TASK / V5_GET_TASK: the block-stage task of a thread is computed once per round on the device and once per
+// sub-stage loop in the emulator.
 #ifdef __CUDA_ARCH__
+#define V5_BLOCK_TASK(t) const BlockTask t = block_task_of((int)threadIdx.x, S, p, g, r, want_y, round);
+#define V5_GET_TASK(t) (void)0
 #define V5_FOR_WARP(...)                     \
     {                                        \
         const int tid = (int)threadIdx.x;    \
@@ -28,6 +32,8 @@ namespace v5 {
     }                                        \
     __syncthreads();
 #else
+#define V5_BLOCK_TASK(t)
+#define V5_GET_TASK(t) const BlockTask t = block_task_of(tid, S, p, g, r, want_y, round)
 #define V5_FOR_WARP(...)                     \
     for (int tid = 0; tid < NT; tid++) {     \
         ThreadAcc &acc = acc_store[tid];     \
@@ -139,10 +145,11 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             V5_FOR_THREADS(stage_convert(tid, S, p, g, r))
             const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
             for (int round = 0; round < rounds; round++) {
-                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_rows_fwd(tid, S, t))
-                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_cols(tid, S, t, acc.col))
-                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_cols_store(tid, S, t, acc.col))
-                V5_FOR_WARP(BlockTask t = block_task_of(tid, S, p, g, r, want_y, round); blocks_rows_inv(tid, S, t))
+                V5_BLOCK_TASK(t)
+                V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_fwd(tid, S, t))
+                V5_FOR_WARP(V5_GET_TASK(t); blocks_cols(tid, S, t, acc.col))
+                V5_FOR_WARP(V5_GET_TASK(t); blocks_cols_store(tid, S, t, acc.col))
+                V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_inv(tid, S, t))
             }
             V5_FOR_THREADS((void)0)
         }

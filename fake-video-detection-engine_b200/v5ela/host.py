@@ -1,0 +1,46 @@
+"""NumPy-level entry point over ``v5ela_analyze_host`` (include/v5ela.h): host arrays in, host arrays out.
+
+This is what the drop-in node uses (it needs no torch): frames are copied to the GPU, analysed by the fused kernel and
+the records / residual / enhanced maps copied back. No CPU implementation exists behind it.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import _abi
+from .records import RECORD_DTYPE
+
+_tls = threading.local()
+
+
+def _handle(device: int) -> "_abi.Handle":
+    cache = getattr(_tls, "handles", None)
+    if cache is None:
+        cache = _tls.handles = {}
+    h = cache.get(device)
+    if h is None:
+        h = cache[device] = _abi.Handle(device)
+    return h
+
+
+def analyze_frames_host(frames: np.ndarray, quality: int = 90, want_residual: bool = False, want_enhanced: bool = False,
+                        device: int = 0):
+    """frames: (N, H, W, 3) uint8 host array -> (records[N] structured, residual | None, enhanced | None)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    if frames.ndim != 4 or frames.shape[-1] != 3:
+        raise ValueError("frames must have shape (N, H, W, 3)")
+    n, h, w, _ = frames.shape
+    recs = np.zeros(n, dtype=RECORD_DTYPE)
+    residual = np.empty_like(frames) if want_residual else None
+    enhanced = np.empty_like(frames) if want_enhanced else None
+    if n == 0 or h == 0 or w == 0:
+        return recs, residual, enhanced
+    hd = _handle(device)
+    if hd.quality != quality:
+        hd.set_quality(quality)
+    hd.analyze_host(frames.ctypes.data, n, h, w, recs.ctypes.data,
+                    residual.ctypes.data if residual is not None else None,
+                    enhanced.ctypes.data if enhanced is not None else None, None)
+    return recs, residual, enhanced

@@ -130,6 +130,64 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 #endif
 
+// Integer dot products on packed bytes (IDP on the FMA pipe): they replace byte extraction (PRMT on the ALU pipe).
+//   dp4a_us(a, b, c) = c + sum_i u8(a.byte[i]) * s8(b.byte[i])
+//   dp2a_lo/hi_su(a, b, c) = c + s16(a.lo) * u8(b.byte[0|2]) + s16(a.hi) * u8(b.byte[1|3]);  _uu: a halves unsigned
+#ifdef __CUDA_ARCH__
+V5_DEV int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+V5_DEV int dp2a_lo_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+V5_DEV int dp2a_hi_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+V5_DEV int dp2a_lo_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+V5_DEV int dp2a_hi_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// histogram update: bin = byte k of word; the bin's shared address comes out of one dp4a (base + 4 * byte)
+V5_DEV void hist_add(uint32_t *hist_c, uint32_t word, int k)
+{
+    const uint32_t addr = (uint32_t)dp4a_us(word, 4u << (8 * k), (int)(uint32_t)__cvta_generic_to_shared(hist_c));
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+}
+#else
+inline int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)((b >> (8 * i)) & 0xff);
+    return c;
+}
+inline int dp2a_su_(uint32_t a, uint32_t b, int c, int hi, bool sgn)
+{
+    const int a0 = sgn ? (int)(int16_t)(a & 0xffff) : (int)(a & 0xffff), a1 = sgn ? (int)(int16_t)(a >> 16) : (int)(a >> 16);
+    return c + a0 * (int)((b >> (16 * hi)) & 0xff) + a1 * (int)((b >> (16 * hi + 8)) & 0xff);
+}
+inline int dp2a_lo_su(uint32_t a, uint32_t b, int c) { return dp2a_su_(a, b, c, 0, true); }
+inline int dp2a_hi_su(uint32_t a, uint32_t b, int c) { return dp2a_su_(a, b, c, 1, true); }
+inline int dp2a_lo_uu(uint32_t a, uint32_t b, int c) { return dp2a_su_(a, b, c, 0, false); }
+inline int dp2a_hi_uu(uint32_t a, uint32_t b, int c) { return dp2a_su_(a, b, c, 1, false); }
+inline void hist_add(uint32_t *hist_c, uint32_t word, int k) { hist_c[(word >> (8 * k)) & 0xff] += 1u; }
+#endif
+
 // Bulk asynchronous copy (TMA, non-tensor form) global -> shared, completion counted in bytes on an mbarrier.
 #ifdef __CUDA_ARCH__
 V5_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -181,15 +239,15 @@ V5_DEV uint32_t pack4(int a, int b, int c, int d)
 // ------------------------------------------------------------------------------------------------- shared memory
 struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
 
-constexpr int RING = 24;                // yorig ring lines: 16 of the current band + the 2 carried ones, rounded up to 8
-constexpr int RINGD = 20;               // ydec ring lines: 16 + 1 carried, rounded up to 4
-constexpr int BSTRIDE = 72;             // block stage scratch: words per 8x8 block (64 + 8: conflict-free 64-bit stores)
+constexpr int RING = 32;                // yorig ring lines (16 of the current band + 2 carried; power of two: cheap index)
+constexpr int RINGD = 24;               // ydec ring lines (16 + 1 carried)
 
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
     uint8_t rgb[2][16][RGB_PITCH];      // band r in rgb[r & 1]; the other buffer receives band r+1 (bulk async copy)
     uint8_t rgb_carry[2][RGB_PITCH];    // line 15 of band r in rgb_carry[r & 1] (finished one iteration later)
-    uint32_t tscratch[NT / 32][8 * BSTRIDE];   // block stage: per warp, 8 blocks x 64 int32 (+pad): both transpositions
+    uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad): both transpositions;
+                                        // 36-word block stride = conflict-free scattered stores and 128-bit loads
     uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
     uint8_t ydec[RINGD][Y_PITCH];       // luma after the JPEG round trip; band r line l at [(16r + l) mod RINGD]
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
@@ -219,17 +277,12 @@ struct ThreadAcc {              // per-thread state that lives across barriers (
     int col[16];                // block stage: two columns between the two halves of the column sub-stage
 };
 
-V5_DEV int ring16(int r, int l)                                         // l in [-2, 15]
+V5_DEV int ring16(int r, int l) { return (16 * (r & 1) + l) & (RING - 1); }   // yorig line; l in [-2, 15]
+V5_DEV int ringd(int r, int l)                                         // ydec line; l in [-1, 15]
 {
     int i = 16 * (r % 3) + l;                                           // 16r mod 24 cycles 0,16,8
-    i = i >= RING ? i - RING : i;
-    i = i >= RING ? i - RING : i;
-    return i < 0 ? i + RING : i;
-}
-V5_DEV int ringd(int r, int l)                                          // l in [-1, 15]
-{
-    int i = 16 * (r % 5) + l;                                           // 16r mod 20 cycles 0,16,12,8,4
-    i = i >= 3 * RINGD ? i - 3 * RINGD : (i >= 2 * RINGD ? i - 2 * RINGD : (i >= RINGD ? i - RINGD : i));
+    i = i >= RINGD ? i - RINGD : i;
+    i = i >= RINGD ? i - RINGD : i;
     return i < 0 ? i + RINGD : i;
 }
 V5_DEV int ring8(int r, int j) { return (8 * (r & 1) + j) & 15; }     // j in [-1, 7]
@@ -265,6 +318,7 @@ V5_DEV void stage_prefetch(Smem &S, const KParams &p, const Geo &g, int r)
     unsigned long long *bar = &S.full_bar[r & 1];
     async_proxy_fence();                                        // earlier generic accesses to this buffer are done
     mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
+#pragma unroll 1
     for (int l = 0; l < 16; l++) {
         int y = 16 * r + l;
         if (y > p.h - 1) y = p.h - 1;
@@ -292,9 +346,41 @@ V5_DEV void stage_load_rest(int tid, Smem &S, const KParams &p, const Geo &g, in
 }
 
 // ------------------------------------------------------------------------------------- stage: colour convert (A.2/A.3)
-V5_DEV int rgb_to_y(int r, int g, int b) { return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16; }
-V5_DEV int rgb_to_cb(int r, int g, int b) { return (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16; }
-V5_DEV int rgb_to_cr(int r, int g, int b) { return (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16; }
+// Colour conversion straight from the packed RGBRGB... words with dp2a (16-bit coefficient pairs x 2 pixel bytes):
+// pixel k starts at byte 3k; depending on 3k mod 4 its (R,G)(B) or (R)(G,B) byte pairs sit in the low/high half of one or two
+// words. pair() = coefficient pair {first byte, second byte}.
+V5_DEV constexpr uint32_t pair(int first, int second) { return ((uint32_t)first & 0xffffu) | ((uint32_t)second << 16); }
+
+// c + cR*R + cG*G + cB*B for pixel k (compile time) of the packed words w[]; UNS: coefficients are unsigned 16-bit
+template <bool UNS, int CR, int CG, int CB>
+V5_DEV int rgb_dot(const uint32_t *w, int k, int c)
+{
+    const int o = 3 * k, wi = o >> 2, bp = o & 3;
+    const uint32_t rg = pair(CR, CG), b0 = pair(CB, 0), r1 = pair(0, CR), gb = pair(CG, CB);
+    if (UNS) {
+        if (bp == 0) return dp2a_hi_uu(b0, w[wi], dp2a_lo_uu(rg, w[wi], c));
+        if (bp == 3) return dp2a_lo_uu(gb, w[wi + 1], dp2a_hi_uu(r1, w[wi], c));
+        if (bp == 2) return dp2a_lo_uu(b0, w[wi + 1], dp2a_hi_uu(rg, w[wi], c));
+        return dp2a_hi_uu(gb, w[wi], dp2a_lo_uu(r1, w[wi], c));
+    } else {
+        if (bp == 0) return dp2a_hi_su(b0, w[wi], dp2a_lo_su(rg, w[wi], c));
+        if (bp == 3) return dp2a_lo_su(gb, w[wi + 1], dp2a_hi_su(r1, w[wi], c));
+        if (bp == 2) return dp2a_lo_su(b0, w[wi + 1], dp2a_hi_su(rg, w[wi], c));
+        return dp2a_hi_su(gb, w[wi], dp2a_lo_su(r1, w[wi], c));
+    }
+}
+
+// A.2. Cb and Cr have one coefficient equal to 32768, which does not fit a signed 16-bit half, so they are evaluated
+// negated: -Cb = (N - K + 65535) >> 16 with N = 11059 R + 21709 G - 32768 B, K = (128 << 16) + 32767 (floor(-x) = -ceil(x)).
+V5_DEV int y_of(const uint32_t *w, int k) { return rgb_dot<true, 19595, 38470, 7471>(w, k, 32768) >> 16; }
+V5_DEV int neg_cb_of(const uint32_t *w, int k)
+{
+    return rgb_dot<false, 11059, 21709, -32768>(w, k, 65535 - ((128 << 16) + 32767)) >> 16;
+}
+V5_DEV int neg_cr_of(const uint32_t *w, int k)
+{
+    return rgb_dot<false, -32768, 27439, 5329>(w, k, 65535 - ((128 << 16) + 32767)) >> 16;
+}
 
 // 8 pixels of two band lines: optional luma (8 bytes per line) and the 4 downsampled Cb/Cr samples.
 template <bool WANT_Y, bool WANT_C>
@@ -307,36 +393,23 @@ V5_DEV void convert8x2(const uint8_t *la, const uint8_t *lb, U2 &y0, U2 &y1, uin
         a[2 * i] = ta.x; a[2 * i + 1] = ta.y;
         b[2 * i] = tb.x; b[2 * i + 1] = tb.y;
     }
-    int yy[2][8], cb[2][8], cr[2][8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int o = 3 * k;
-        const int ra = byte_of(a[o >> 2], o & 3), ga = byte_of(a[(o + 1) >> 2], (o + 1) & 3),
-                  ba = byte_of(a[(o + 2) >> 2], (o + 2) & 3);
-        const int rb = byte_of(b[o >> 2], o & 3), gb = byte_of(b[(o + 1) >> 2], (o + 1) & 3),
-                  bb = byte_of(b[(o + 2) >> 2], (o + 2) & 3);
-        if (WANT_Y) {
-            yy[0][k] = rgb_to_y(ra, ga, ba);
-            yy[1][k] = rgb_to_y(rb, gb, bb);
-        }
-        if (WANT_C) {
-            cb[0][k] = rgb_to_cb(ra, ga, ba);
-            cb[1][k] = rgb_to_cb(rb, gb, bb);
-            cr[0][k] = rgb_to_cr(ra, ga, ba);
-            cr[1][k] = rgb_to_cr(rb, gb, bb);
-        }
-    }
     if (WANT_Y) {
-        y0 = U2{pack4(yy[0][0], yy[0][1], yy[0][2], yy[0][3]), pack4(yy[0][4], yy[0][5], yy[0][6], yy[0][7])};
-        y1 = U2{pack4(yy[1][0], yy[1][1], yy[1][2], yy[1][3]), pack4(yy[1][4], yy[1][5], yy[1][6], yy[1][7])};
+        int ya[8], yb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            ya[k] = y_of(a, k);
+            yb[k] = y_of(b, k);
+        }
+        y0 = U2{pack4(ya[0], ya[1], ya[2], ya[3]), pack4(ya[4], ya[5], ya[6], ya[7])};
+        y1 = U2{pack4(yb[0], yb[1], yb[2], yb[3]), pack4(yb[4], yb[5], yb[6], yb[7])};
     }
     if (WANT_C) {                                               // h2v2 box filter, bias 1,2,1,2 along x
         int c[4], d[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int bias = 1 + (j & 1);
-            c[j] = (cb[0][2 * j] + cb[0][2 * j + 1] + cb[1][2 * j] + cb[1][2 * j + 1] + bias) >> 2;
-            d[j] = (cr[0][2 * j] + cr[0][2 * j + 1] + cr[1][2 * j] + cr[1][2 * j + 1] + bias) >> 2;
+            c[j] = (bias - (neg_cb_of(a, 2 * j) + neg_cb_of(a, 2 * j + 1) + neg_cb_of(b, 2 * j) + neg_cb_of(b, 2 * j + 1))) >> 2;
+            d[j] = (bias - (neg_cr_of(a, 2 * j) + neg_cr_of(a, 2 * j + 1) + neg_cr_of(b, 2 * j) + neg_cr_of(b, 2 * j + 1))) >> 2;
         }
         cbo = pack4(c[0], c[1], c[2], c[3]);
         cro = pack4(d[0], d[1], d[2], d[3]);
@@ -457,17 +530,16 @@ V5_DEV void idct8(int *v)
 }
 
 // The block stage. Four threads share one 8x8 block; thread j owns rows 2j,2j+1 in the row passes and columns 2j,2j+1
-// in the column passes. The two transpositions go through a per-warp shared-memory scratch of int32 (64-bit scattered
-// stores, conflict-free with the 72-word block stride; 128-bit loads). Only __syncwarp() is needed between the
-// sub-stages, and the code is ~600 instructions instead of ~1900 for a block-per-thread unrolling (the instruction
-// cache, not the ALUs, was the first version's limit).
+// in the column passes. The two transpositions go through a per-warp shared-memory scratch as int16 pairs (ranges:
+// |fDCT row output| <= 4096, |IDCT column output| <= 21047 by Parseval + quantisation error), laid out so
+// that both the scattered 32-bit stores and the 128-bit loads are bank-conflict free. Only __syncwarp() is needed between
+// the three sub-stages, and the code is ~600 instructions instead of ~1900 for a block-per-thread unrolling (the
+// instruction cache, not the ALUs, was the first version's limit).
 struct BlockTask {
     const QEntry *q;
-    const uint8_t *in;          // first row of the source block
-    uint8_t *out;               // column of the destination block in line 0 of its buffer
+    const uint8_t *in;
+    uint8_t *out;
     int pitch;
-    int out_row;                // destination line of block row 0 ...
-    int out_wrap;               // ... in a ring of this many lines (rows wrap; an even row pair never straddles the end)
     bool active;
 };
 
@@ -479,19 +551,15 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     t.in = nullptr;
     t.out = nullptr;
     t.pitch = 0;
-    t.out_row = 0;
-    t.out_wrap = 1 << 20;
     const int tw = g.m1 - g.m0;
     const int nl = want_y ? 4 * tw : 0;
     if (blk < nl) {
         const int br = blk >= 2 * tw ? 1 : 0, bc = blk - br * 2 * tw;
         // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
         if (16 * r + 8 * br >= p.h || 16 * g.m0 + 8 * bc >= p.w) return t;
-        const int col = 16 + 8 * bc;
-        t.in = &S.yorig[ring16(r, 8 * br)][col];
-        t.out = &S.ydec[0][col];
-        t.out_row = ringd(r, 8 * br);
-        t.out_wrap = RINGD;
+        const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
+        t.in = &S.yorig[row][col];
+        t.out = &S.ydec[ringd(r, 8 * br)][col];
         t.pitch = Y_PITCH;
         t.active = true;
     } else {
@@ -502,8 +570,7 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
         if (mcu < 0 || mcu >= p.mw) return t;
         t.q = S.qtab[1];
         t.in = &S.cenc[comp][0][8 * cbk];
-        t.out = &S.cdec[comp][0][8 * cbk];
-        t.out_row = ring8(r, 0);
+        t.out = &S.cdec[comp][ring8(r, 0)][8 * cbk];
         t.pitch = C_PITCH;
         t.active = true;
     }
@@ -517,7 +584,11 @@ V5_DEV BlockTask block_task_of(int tid, Smem &S, const KParams &p, const Geo &g,
 
 V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
 
-// sub-stage 1: forward row pass of rows 2j, 2j+1 -> scratch, column-major: word 8c + r holds element (r, c)
+V5_DEV uint32_t pack_s16(int lo, int hi) { return prmt((uint32_t)lo, (uint32_t)hi, 0x5410u); }
+V5_DEV int s16_lo(uint32_t w) { return (int)prmt(w, 0u, 0x9910u); }         // sign-extend the low half: one PRMT
+V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
+
+// sub-stage 1: forward row pass of rows 2j, 2j+1 -> tscratch (column-major pairs)
 V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
@@ -532,20 +603,9 @@ V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
     }
     fdct8<1, true>(a);
     fdct8<1, true>(b);
-    uint32_t *ts = &S.tscratch[warp][BSTRIDE * bw + 2 * j];
+    uint32_t *ts = &S.tscratch[warp][36 * bw];
 #pragma unroll
-    for (int c = 0; c < 8; c++) *reinterpret_cast<U2 *>(ts + 8 * c) = U2{(uint32_t)a[c], (uint32_t)b[c]};
-}
-
-// two lines (rows or columns) 2j, 2j+1 of the transposed block: four 128-bit loads
-V5_DEV void load_pair(const uint32_t *ts, int j, int *a, int *b)
-{
-    const U4 a0 = *reinterpret_cast<const U4 *>(ts + 16 * j), a1 = *reinterpret_cast<const U4 *>(ts + 16 * j + 4);
-    const U4 b0 = *reinterpret_cast<const U4 *>(ts + 16 * j + 8), b1 = *reinterpret_cast<const U4 *>(ts + 16 * j + 12);
-    a[0] = (int)a0.x; a[1] = (int)a0.y; a[2] = (int)a0.z; a[3] = (int)a0.w;
-    a[4] = (int)a1.x; a[5] = (int)a1.y; a[6] = (int)a1.z; a[7] = (int)a1.w;
-    b[0] = (int)b0.x; b[1] = (int)b0.y; b[2] = (int)b0.z; b[3] = (int)b0.w;
-    b[4] = (int)b1.x; b[5] = (int)b1.y; b[6] = (int)b1.z; b[7] = (int)b1.w;
+    for (int c = 0; c < 8; c++) ts[4 * c + j] = pack_s16(a[c], b[c]);
 }
 
 // sub-stage 2a: columns 2j, 2j+1: forward column pass, quantise + dequantise (A.5), inverse column pass -> registers
@@ -553,13 +613,15 @@ V5_DEV void blocks_cols(int tid, Smem &S, const BlockTask &t, int *col)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    int a[8], b[8];
-    load_pair(&S.tscratch[warp][BSTRIDE * bw], j, a, b);
+    const uint32_t *ts = &S.tscratch[warp][36 * bw];
+    const U4 w0 = *reinterpret_cast<const U4 *>(ts + 8 * j), w1 = *reinterpret_cast<const U4 *>(ts + 8 * j + 4);
+    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
+    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
     fdct8<1, false>(a);
     fdct8<1, false>(b);
-    const QEntry *qj = t.q + 2 * j;                             // row k of the table is a fixed offset from here
+    const QEntry *qj = t.q + 2 * j;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {                               // coefficient (row k, column 2j / 2j+1)
+    for (int k = 0; k < 8; k++) {
         const QEntry ea = qj[8 * k], eb = qj[8 * k + 1];
         const uint32_t xa = (uint32_t)(a[k] + (a[k] >> 31) + ea.bias), xb = (uint32_t)(b[k] + (b[k] >> 31) + eb.bias);
         a[k] = (int)umulhi32(xa, ea.recip) * ea.t - ea.unbias;
@@ -579,9 +641,9 @@ V5_DEV void blocks_cols_store(int tid, Smem &S, const BlockTask &t, const int *c
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    uint32_t *rs = &S.tscratch[warp][BSTRIDE * bw + 2 * j];
+    uint32_t *rs = &S.tscratch[warp][36 * bw];
 #pragma unroll
-    for (int k = 0; k < 8; k++) *reinterpret_cast<U2 *>(rs + 8 * k) = U2{(uint32_t)col[k], (uint32_t)col[8 + k]};
+    for (int k = 0; k < 8; k++) rs[4 * k + j] = pack_s16(col[k], col[8 + k]);
 }
 
 // sub-stage 3: final inverse row pass of rows 2j, 2j+1, +128, clamp, store bytes
@@ -589,15 +651,14 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
 {
     const int warp = tid >> 5, lane = tid & 31, j = lane & 3, bw = lane >> 2;
     if (!t.active) return;
-    int a[8], b[8];
-    load_pair(&S.tscratch[warp][BSTRIDE * bw], j, a, b);
+    const uint32_t *rs = &S.tscratch[warp][36 * bw];
+    const U4 w0 = *reinterpret_cast<const U4 *>(rs + 8 * j), w1 = *reinterpret_cast<const U4 *>(rs + 8 * j + 4);
+    int a[8] = {s16_lo(w0.x), s16_hi(w0.x), s16_lo(w0.y), s16_hi(w0.y), s16_lo(w0.z), s16_hi(w0.z), s16_lo(w0.w), s16_hi(w0.w)};
+    int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
     idct8<1, true>(a);
     idct8<1, true>(b);
-    int row = t.out_row + 2 * j;
-    row = row >= t.out_wrap ? row - t.out_wrap : row;
-    uint8_t *o = t.out + row * t.pitch;
-    *reinterpret_cast<U2 *>(o) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
-    *reinterpret_cast<U2 *>(o + t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
+    *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
+    *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
 }
 
 // ------------------------------------------------------------------- stage: upsample, reconstruct, residual, Laplacian
@@ -605,7 +666,6 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
 // lc / ln: decoded chroma lines (current row, neighbour row), pointing at this unit's first chroma column (4-aligned);
 // columns -1 and 4 are the horizontal neighbours. gcx0 = global chroma column of lc[0]; wc1 = Wc - 1.
 // Outputs are the upsampled samples MINUS 128 (what the colour conversion wants).
-template <bool EDGE>
 V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, bool fancy, int out[8])
 {
     const uint32_t c0 = *reinterpret_cast<const uint32_t *>(lc - 4), n0 = *reinterpret_cast<const uint32_t *>(ln - 4);
@@ -617,27 +677,25 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
         return;
     }
     int cs[6];                                                  // cs[j+1] = 3*c[r][j] + c[nb][j], j = -1..4
-    cs[0] = 3 * (int)byte_of(c0, 3) + (int)byte_of(n0, 3);
+    cs[0] = dp4a_us(c0, 3u << 24, dp4a_us(n0, 1u << 24, 0));
 #pragma unroll
-    for (int j = 0; j < 4; j++) cs[1 + j] = 3 * (int)byte_of(c1, j) + (int)byte_of(n1, j);
-    cs[5] = 3 * (int)byte_of(c2, 0) + (int)byte_of(n2, 0);
-    if (EDGE && gcx0 == 0) cs[0] = cs[1];                       // left image edge: neighbour clamps to column 0
-    if (EDGE && gcx0 + 4 > wc1) {                               // right image edge inside / just after this unit
+    for (int j = 0; j < 4; j++) cs[1 + j] = dp4a_us(c1, 3u << (8 * j), dp4a_us(n1, 1u << (8 * j), 0));
+    cs[5] = dp4a_us(c2, 3u, dp4a_us(n2, 1u, 0));
+    if (gcx0 == 0) cs[0] = cs[1];                               // left image edge: neighbour clamps to column 0
+    if (gcx0 + 4 > wc1) {                                       // right image edge inside / just after this unit
 #pragma unroll
         for (int j = 1; j < 6; j++)
             if (gcx0 + j - 1 > wc1) cs[j] = cs[j - 1];
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int t3 = 3 * cs[j + 1] + (8 - 2048);                          // "- 128" folded in: 2048 = 128 << 4
+        const int t3 = 3 * cs[j + 1] + (8 - 2048);
         out[2 * j] = (t3 + cs[j]) >> 4;
-        out[2 * j + 1] = (t3 + cs[j + 2] - 1) >> 4;                         // bias 7
+        out[2 * j + 1] = (t3 + cs[j + 2] - 1) >> 4;
     }
 }
 
 // 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
-// EDGE = false: the unit lies strictly inside the image horizontally (no masks, no reflection); true: general case.
-template <bool EDGE>
 V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
 {
     const int y = 16 * r + l;                                   // global pixel row
@@ -654,8 +712,8 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const int ccol = col >> 1, gcx0 = gx0 >> 1;
     const bool fancy = wc1 > 1;
     int cb[8], cr[8];
-    upsample8<EDGE>(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
-    upsample8<EDGE>(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
+    upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
 
     // ---- reconstruct (A.8), residual (A.9), histogram
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
@@ -683,10 +741,10 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
         dw[i] = absdiff4(ow[i], pack4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
 #pragma unroll
     for (int b = 0; b < 24; b++)
-        if (!EDGE || b < 3 * nvalid) smem_inc(&S.hist[b % 3][byte_of(dw[b >> 2], b & 3)]);
+        if (b < 3 * nvalid) hist_add(S.hist[b % 3], dw[b >> 2], b & 3);
     if (g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
-        if ((!EDGE || nvalid >= 8) && p.resid_vec_ok) {
+        if (nvalid >= 8 && p.resid_vec_ok) {
 #pragma unroll
             for (int i = 0; i < 3; i++) reinterpret_cast<U2 *>(dst)[i] = U2{dw[2 * i], dw[2 * i + 1]};
         } else {
@@ -704,29 +762,35 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const U2 cw = *reinterpret_cast<const U2 *>(yc);
     const U2 uw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, lu)][col]);
     const U2 lw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, ld)][col]);
-    const uint32_t cww[2] = {cw.x, cw.y}, uww[2] = {uw.x, uw.y}, lww[2] = {lw.x, lw.y};
     // Reflection at the left/right image edge: the left neighbour of column 0 comes from a selected address; the single
     // pixel in column W-1 is left out of the vector loop (nacc) and done on its own below.
     const int wide = p.w > 1;
-    const int edge = EDGE && nvalid <= 8 ? nvalid - 1 : -1;     // index of the pixel in image column W-1, if in this unit
+    const int edge = nvalid <= 8 ? nvalid - 1 : -1;             // index of the pixel in image column W-1, if in this unit
     const int nacc = edge >= 0 ? edge : 8;
-    int c[10];                                                  // c[k+1] = luma at column k, k = -1..8
-    c[0] = EDGE && gx0 == 0 ? yc[wide] : yc[-1];
-    c[9] = yc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) c[k + 1] = (int)byte_of(cww[k >> 2], k & 3);
+    // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per pixel
+    const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = yc[8];
+    const uint32_t x[3] = {prmt(hl, cw.x, 0x6540u), prmt(cw.x, cw.y, 0x6543u), prmt(cw.y, hr, 0x7743u)};
+    const uint32_t ud[2][2] = {{uw.x, lw.x}, {uw.y, lw.y}};
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        int lap = c[k] + c[k + 2] + (int)byte_of(uww[k >> 2], k & 3) + (int)byte_of(lww[k >> 2], k & 3) - 4 * c[k + 1];
+        const int w0 = k >> 2, s0 = k & 3;                      // window e[k..k+2] starts at byte s0 of x[w0]
+        int lap = dp4a_us(ud[w0][0], 1u << (8 * s0), dp4a_us(ud[w0][1], 1u << (8 * s0), 0));      // up + down
+        if (s0 <= 1) {
+            lap = dp4a_us(x[w0], 0x01fc01u << (8 * s0), lap);
+        } else if (s0 == 2) {
+            lap = dp4a_us(x[w0 + 1], 0x00000001u, dp4a_us(x[w0], 0xfc010000u, lap));
+        } else {
+            lap = dp4a_us(x[w0 + 1], 0x000001fcu, dp4a_us(x[w0], 0x01000000u, lap));
+        }
         lap = lap < 0 ? -lap : lap;
-        if (!EDGE || k < nacc) {
+        if (k < nacc) {
             sabs += (uint32_t)lap;
             ssq += (uint32_t)(lap * lap);
             mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
         }
     }
-    if (EDGE && edge >= 0) {
+    if (edge >= 0) {
         const int ctr = yc[edge];
         const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;   // W-2 mirrors onto W
         int lap = 2 * side + (int)S.yorig[ring16(r, lu)][col + edge] + (int)S.yorig[ring16(r, ld)][col + edge] - 4 * ctr;
@@ -749,12 +813,8 @@ V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, Thr
     for (int u = tid; u < 16 * n8; u += NT) {
         const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
-        const int gx0 = 16 * g.m0 + 8 * ox;
-        if (y < ylo || y >= yhi || gx0 >= p.w) continue;
-        if (gx0 > 0 && gx0 + 8 < p.w)
-            residual_unit<false>(S, p, g, acc, r, l, ox);
-        else
-            residual_unit<true>(S, p, g, acc, r, l, ox);
+        if (y < ylo || y >= yhi || 16 * g.m0 + 8 * ox >= p.w) continue;
+        residual_unit(S, p, g, acc, r, l, ox);
     }
 }
 

@@ -281,7 +281,8 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
     if (n == 0) return V5ELA_OK;
     v5::KParams p;
     if (v5::fill_params(p, d_rgb, n, height, width, frame_stride_bytes, row_stride_bytes,
-                        static_cast<v5ela_record *>(d_records), d_residual, h->quality, h->seg_rows) != 0)
+                        static_cast<v5ela_record *>(d_records), d_residual, h->quality, h->seg_rows,
+                        2 * h->sm_count * h->ctas_per_sm) != 0)
         return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: bad pointer, size or stride%s");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

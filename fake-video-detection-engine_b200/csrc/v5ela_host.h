@@ -28,9 +28,11 @@ inline void quant_tables(int quality, uint16_t luma[64], uint16_t chroma[64])
 }
 
 // Work decomposition: frames x strips (<= TW_MAX MCUs wide, balanced) x vertical segments of about `seg_rows` MCU rows.
-// seg_rows <= 0 picks the default. Returns 0 or -1 on invalid arguments.
+// seg_rows <= 0 picks the default: 17 rows (two chroma-only halo bands per segment = ~4 % extra work), shortened down to
+// 4 rows when the batch would otherwise give fewer than `target_items` work items (small batches, single crops), so
+// that the whole GPU is used. Returns 0 or -1 on invalid arguments.
 inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int64_t frame_stride, int64_t row_stride,
-                       v5ela_record *records, uint8_t *residual, int quality, int seg_rows)
+                       v5ela_record *records, uint8_t *residual, int quality, int seg_rows, int target_items = 0)
 {
     if (!rgb || !records || n <= 0 || h <= 0 || w <= 0) return -1;
     if (row_stride < (int64_t)3 * w || (n > 1 && frame_stride < row_stride * (int64_t)h)) return -1;
@@ -48,7 +50,15 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
     p.mw = (w + 15) / 16;
     p.mh = (h + 15) / 16;
     p.n_strips = (p.mw + TW_MAX - 1) / TW_MAX;
-    if (seg_rows <= 0) seg_rows = 17;
+    if (seg_rows <= 0) {
+        seg_rows = 17;
+        const int64_t columns = (int64_t)n * p.n_strips;        // work items per unit of n_segs
+        if (target_items > 0 && columns * ((p.mh + seg_rows - 1) / seg_rows) < target_items) {
+            const int64_t want_segs = (target_items + columns - 1) / columns;
+            seg_rows = (int)((p.mh + want_segs - 1) / want_segs);
+            if (seg_rows < 4) seg_rows = 4;
+        }
+    }
     p.n_segs = (p.mh + seg_rows - 1) / seg_rows;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(rgb) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15) == 0;
     p.resid_vec_ok = residual && ((reinterpret_cast<uintptr_t>(residual) | (uintptr_t)(3 * w)) & 15) == 0;

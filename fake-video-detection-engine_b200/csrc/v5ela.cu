@@ -15,6 +15,7 @@
 #include "v5ela.h"
 #include "v5ela_host.h"
 #include "v5ela_workitem.cuh"
+#include "v5ela_fft.cuh"
 
 static_assert(sizeof(v5ela_record) == 3144, "V5F v1 record layout");
 static_assert(sizeof(v5::KParams) <= 4096, "kernel parameters must fit the 4 KB parameter bank");
@@ -152,6 +153,14 @@ struct v5ela_handle {
     uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
     void *d_rec = nullptr;
     size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
+    // spectrum path (v5ela_fft.cuh): twiddle tables for the last (width, height), DFT workspace
+    double2 *tw_w = nullptr, *tw_h = nullptr;
+    int tw_w_n = 0, tw_h_n = 0;
+    size_t tw_w_cap = 0, tw_h_cap = 0;
+    void *d_g = nullptr, *d_ms = nullptr, *d_minmax = nullptr;
+    size_t d_g_cap = 0, d_ms_cap = 0, d_minmax_cap = 0;
+    uint8_t *d_gray = nullptr, *d_spec = nullptr;
+    size_t d_gray_cap = 0, d_spec_cap = 0;
     uint16_t luma[64], chroma[64];
     char err[512] = {0};
 };
@@ -249,6 +258,13 @@ int v5ela_destroy(v5ela_handle *h)
     cudaFree(h->d_res);
     cudaFree(h->d_enh);
     cudaFree(h->d_rec);
+    cudaFree(h->tw_w);
+    cudaFree(h->tw_h);
+    cudaFree(h->d_g);
+    cudaFree(h->d_ms);
+    cudaFree(h->d_minmax);
+    cudaFree(h->d_gray);
+    cudaFree(h->d_spec);
     delete h;
     return V5ELA_OK;
 }
@@ -348,7 +364,7 @@ int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int heig
         return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_host: bad pointer or size%s");
     DeviceGuard guard(h->device);
     if (!h->copy_stream) {
-        V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         V5_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         V5_CUDA(h, cudaStreamCreateWithFlags(&h->work_stream, cudaStreamNonBlocking));
         V5_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -402,6 +418,84 @@ int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int heig
     V5_CUDA(h, cudaStreamWaitEvent(user, h->ev_join_copy, 0));
     V5_CUDA(h, cudaStreamWaitEvent(user, h->ev_join_work, 0));
     if (!cuda_stream) V5_CUDA(h, cudaStreamSynchronize(user));
+    return V5ELA_OK;
+}
+
+int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, int width, int64_t frame_stride_bytes,
+                   int64_t row_stride_bytes, uint8_t *d_out, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!d_gray || !d_out || n < 0 || height <= 0 || width <= 0 || height > 65536 || width > 65536 ||
+        row_stride_bytes < width || (n > 1 && frame_stride_bytes < row_stride_bytes * (int64_t)height))
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_spectrum: bad pointer, size or stride%s");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int wh = width / 2 + 1;
+    int rc;
+    if (h->tw_w_n != width) {
+        if ((rc = ensure(h, (void **)&h->tw_w, &h->tw_w_cap, sizeof(double2) * (size_t)width))) return rc;
+        v5fft::twiddle_kernel<<<(width + 255) / 256, 256, 0, st>>>(h->tw_w, width);
+        h->tw_w_n = width;
+        h->launches++;
+    }
+    if (h->tw_h_n != height) {
+        if ((rc = ensure(h, (void **)&h->tw_h, &h->tw_h_cap, sizeof(double2) * (size_t)height))) return rc;
+        v5fft::twiddle_kernel<<<(height + 255) / 256, 256, 0, st>>>(h->tw_h, height);
+        h->tw_h_n = height;
+        h->launches++;
+    }
+    // frames per pass: keep the float64 workspace (24 bytes per half-spectrum sample) under ~1 GiB
+    const size_t per_frame = (size_t)height * wh;
+    int chunk = (int)((size_t)(1u << 30) / (per_frame * 24));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    if (chunk > 65535) chunk = 65535;
+    if ((rc = ensure(h, &h->d_g, &h->d_g_cap, per_frame * 16 * chunk))) return rc;
+    if ((rc = ensure(h, &h->d_ms, &h->d_ms_cap, per_frame * 8 * chunk))) return rc;
+    if ((rc = ensure(h, &h->d_minmax, &h->d_minmax_cap, sizeof(unsigned long long) * 2 * (size_t)chunk))) return rc;
+    const dim3 grid((wh + v5fft::TILE - 1) / v5fft::TILE, (height + v5fft::TILE - 1) / v5fft::TILE, 1);
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int fn = f0 + chunk <= n ? chunk : n - f0;
+        // min/max slots: {~0, 0} per frame
+        V5_CUDA(h, cudaMemsetAsync(h->d_minmax, 0, sizeof(unsigned long long) * 2 * (size_t)fn, st));
+        V5_CUDA(h, cudaMemset2DAsync(h->d_minmax, 16, 0xff, 8, (size_t)fn, st));
+        dim3 gr = grid;
+        gr.z = (unsigned)fn;
+        v5fft::dft_rows_kernel<<<gr, 256, 0, st>>>(d_gray + (int64_t)f0 * frame_stride_bytes, frame_stride_bytes, row_stride_bytes,
+                                                   height, width, wh, h->tw_w, static_cast<double2 *>(h->d_g));
+        V5_CUDA(h, cudaGetLastError());
+        v5fft::dft_cols_kernel<<<gr, 256, 0, st>>>(static_cast<const double2 *>(h->d_g), height, wh, h->tw_h,
+                                                   static_cast<double *>(h->d_ms), static_cast<unsigned long long *>(h->d_minmax));
+        V5_CUDA(h, cudaGetLastError());
+        long long bx = ((long long)height * width + 255) / 256;
+        if (bx > 8LL * h->sm_count) bx = 8LL * h->sm_count;
+        v5fft::spectrum_image_kernel<<<dim3((unsigned)bx, 1, (unsigned)fn), 256, 0, st>>>(
+            static_cast<const double *>(h->d_ms), static_cast<const unsigned long long *>(h->d_minmax), height, width, wh,
+            d_out + (int64_t)f0 * height * width);
+        V5_CUDA(h, cudaGetLastError());
+        h->launches += 3;
+    }
+    return V5ELA_OK;
+}
+
+int v5ela_spectrum_host(v5ela_handle *h, const uint8_t *gray_host, int n, int height, int width, uint8_t *out_host)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!gray_host || !out_host || n < 0 || height <= 0 || width <= 0)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_spectrum_host: bad pointer or size%s");
+    DeviceGuard guard(h->device);
+    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    const size_t bytes = (size_t)n * height * width;
+    int rc;
+    if ((rc = ensure(h, (void **)&h->d_gray, &h->d_gray_cap, bytes))) return rc;
+    if ((rc = ensure(h, (void **)&h->d_spec, &h->d_spec_cap, bytes))) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(h->d_gray, gray_host, bytes, cudaMemcpyHostToDevice, h->own_stream));
+    rc = v5ela_spectrum(h, h->d_gray, n, height, width, (int64_t)height * width, width, h->d_spec, h->own_stream);
+    if (rc) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(out_host, h->d_spec, bytes, cudaMemcpyDeviceToHost, h->own_stream));
+    V5_CUDA(h, cudaStreamSynchronize(h->own_stream));
     return V5ELA_OK;
 }
 

@@ -1,0 +1,156 @@
+// v5ela_fft.cuh — the reference's "texture" artefact (v5_texture_ela.py:83-91) on the GPU:
+//     f = np.fft.fft2(gray); fshift = np.fft.fftshift(f); ms = 20*np.log(np.abs(fshift) + 1)
+//     out = cv2.normalize(ms, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+// Face crops have arbitrary sizes (prime widths included), so the 2-D DFT is evaluated as two exact-size float64
+// matrix products with twiddle factors from an N-entry table (index (j*k) mod N kept by integer addition — no argument
+// reduction error): rows real -> half spectrum (Hermitian symmetry), then columns complex -> complex fused with
+// |F|, 20*ln(|F|+1) and the per-frame min/max; a last kernel normalises, shifts (fftshift) and mirrors the half
+// spectrum into the uint8 image. float64 throughout like NumPy; parity target is +-1 LSB of the uint8 image (the
+// reference's pocketfft sums in a different order), SURVEY.md §8f-1.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace v5fft {
+
+// tw[m] = exp(-2*pi*i*m/n)
+__global__ void twiddle_kernel(double2 *tw, int n)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    double s, c;
+    sincospi(2.0 * (double)m / (double)n, &s, &c);
+    tw[m] = make_double2(c, -s);
+}
+
+constexpr int TILE = 32;     // output tile edge per CTA (16x16 threads, 2x2 outputs each)
+constexpr int KC = 32;       // reduction chunk staged in shared memory
+
+// G[y][v] = sum_x gray[y][x] * twW[(x*v) mod W],  v in [0, W/2]
+__global__ void __launch_bounds__(256) dft_rows_kernel(const uint8_t *__restrict__ gray, int64_t frame_stride, int64_t row_stride,
+                                                       int h, int w, int wh, const double2 *__restrict__ tw, double2 *__restrict__ g)
+{
+    __shared__ double xs[TILE][KC + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int y0 = blockIdx.y * TILE, v0 = blockIdx.x * TILE;
+    const uint8_t *src = gray + (int64_t)blockIdx.z * frame_stride;
+    const int va = v0 + tx, vb = v0 + tx + 16;
+    int ia = 0, ib = 0;                                         // (x * v) mod w for the two columns of this thread
+    const int sa = va % w, sb = vb % w;
+    double2 acc[2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    for (int x0 = 0; x0 < w; x0 += KC) {
+        for (int i = threadIdx.x; i < TILE * KC; i += 256) {
+            const int r = i / KC, c = i - r * KC;
+            const int y = y0 + r, x = x0 + c;
+            xs[r][c] = (y < h && x < w) ? (double)src[(int64_t)y * row_stride + x] : 0.0;
+        }
+        __syncthreads();
+        const int kn = min(KC, w - x0);
+        for (int k = 0; k < kn; k++) {
+            const double2 ta = tw[ia], tb = tw[ib];
+            const double xa = xs[ty][k], xb = xs[ty + 16][k];
+            acc[0][0].x = fma(xa, ta.x, acc[0][0].x); acc[0][0].y = fma(xa, ta.y, acc[0][0].y);
+            acc[0][1].x = fma(xa, tb.x, acc[0][1].x); acc[0][1].y = fma(xa, tb.y, acc[0][1].y);
+            acc[1][0].x = fma(xb, ta.x, acc[1][0].x); acc[1][0].y = fma(xb, ta.y, acc[1][0].y);
+            acc[1][1].x = fma(xb, tb.x, acc[1][1].x); acc[1][1].y = fma(xb, tb.y, acc[1][1].y);
+            ia += sa; ia = ia >= w ? ia - w : ia;
+            ib += sb; ib = ib >= w ? ib - w : ib;
+        }
+        __syncthreads();
+    }
+    double2 *dst = g + (int64_t)blockIdx.z * h * wh;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int y = y0 + ty + 16 * i;
+        if (y >= h) continue;
+        if (va < wh) dst[(int64_t)y * wh + va] = acc[i][0];
+        if (vb < wh) dst[(int64_t)y * wh + vb] = acc[i][1];
+    }
+}
+
+// ms[u][v] = 20*ln(|sum_y G[y][v] * twH[(u*y) mod H]| + 1); per-frame min/max as ordered uint64 (ms >= 0)
+__global__ void __launch_bounds__(256) dft_cols_kernel(const double2 *__restrict__ g, int h, int wh, const double2 *__restrict__ tw,
+                                                       double *__restrict__ ms, unsigned long long *__restrict__ minmax)
+{
+    __shared__ double2 gs[KC][TILE + 1];
+    __shared__ unsigned long long smin, smax;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int u0 = blockIdx.y * TILE, v0 = blockIdx.x * TILE;
+    const double2 *src = g + (int64_t)blockIdx.z * h * wh;
+    if (threadIdx.x == 0) { smin = ~0ull; smax = 0ull; }
+    const int ua = u0 + ty, ub = u0 + ty + 16;
+    int ia = 0, ib = 0;
+    const int sa = ua % h, sb = ub % h;
+    double2 acc[2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    for (int y0 = 0; y0 < h; y0 += KC) {
+        for (int i = threadIdx.x; i < KC * TILE; i += 256) {
+            const int r = i / TILE, c = i - r * TILE;
+            const int y = y0 + r, v = v0 + c;
+            gs[r][c] = (y < h && v < wh) ? src[(int64_t)y * wh + v] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        const int kn = min(KC, h - y0);
+        for (int k = 0; k < kn; k++) {
+            const double2 ta = tw[ia], tb = tw[ib];
+            const double2 ga = gs[k][tx], gb = gs[k][tx + 16];
+            // (a + ib)(c + id) = (ac - bd) + i(ad + bc)
+            acc[0][0].x = fma(ga.x, ta.x, fma(-ga.y, ta.y, acc[0][0].x)); acc[0][0].y = fma(ga.x, ta.y, fma(ga.y, ta.x, acc[0][0].y));
+            acc[0][1].x = fma(gb.x, ta.x, fma(-gb.y, ta.y, acc[0][1].x)); acc[0][1].y = fma(gb.x, ta.y, fma(gb.y, ta.x, acc[0][1].y));
+            acc[1][0].x = fma(ga.x, tb.x, fma(-ga.y, tb.y, acc[1][0].x)); acc[1][0].y = fma(ga.x, tb.y, fma(ga.y, tb.x, acc[1][0].y));
+            acc[1][1].x = fma(gb.x, tb.x, fma(-gb.y, tb.y, acc[1][1].x)); acc[1][1].y = fma(gb.x, tb.y, fma(gb.y, tb.x, acc[1][1].y));
+            ia += sa; ia = ia >= h ? ia - h : ia;
+            ib += sb; ib = ib >= h ? ib - h : ib;
+        }
+        __syncthreads();
+    }
+    double *dst = ms + (int64_t)blockIdx.z * h * wh;
+    unsigned long long lo = ~0ull, hi = 0ull;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int u = u0 + ty + 16 * i, v = v0 + tx + 16 * j;
+            if (u >= h || v >= wh) continue;
+            const double m = 20.0 * log(hypot(acc[i][j].x, acc[i][j].y) + 1.0);
+            dst[(int64_t)u * wh + v] = m;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+            lo = bits < lo ? bits : lo;
+            hi = bits > hi ? bits : hi;
+        }
+    }
+    atomicMin(&smin, lo);
+    atomicMax(&smax, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMin(&minmax[2 * blockIdx.z], smin);
+        atomicMax(&minmax[2 * blockIdx.z + 1], smax);
+    }
+}
+
+// out[i][j] = u8(rint(ms_shifted[i][j] * scale + shift)), cv2.normalize(NORM_MINMAX, 0..255) + np.fft.fftshift
+__global__ void __launch_bounds__(256) spectrum_image_kernel(const double *__restrict__ ms, const unsigned long long *__restrict__ minmax,
+                                                             int h, int w, int wh, uint8_t *__restrict__ out)
+{
+    const int frame = blockIdx.z;
+    const double mn = __longlong_as_double((long long)minmax[2 * frame]), mx = __longlong_as_double((long long)minmax[2 * frame + 1]);
+    const double scale = (mx - mn) > 2.220446049250313e-16 ? 255.0 / (mx - mn) : 0.0;   // cv::normalize: DBL_EPSILON guard
+    const double shift = 0.0 - mn * scale;
+    const double *src = ms + (int64_t)frame * h * wh;
+    uint8_t *dst = out + (int64_t)frame * h * w;
+    const int64_t total = (int64_t)h * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / w), j = (int)(idx - (int64_t)i * w);
+        int u = i - h / 2, v = j - w / 2;                        // fftshift: y[i] = x[(i - n//2) mod n]
+        u = u < 0 ? u + h : u;
+        v = v < 0 ? v + w : v;
+        if (v >= wh) {                                           // Hermitian mirror: |F[u][v]| = |F[-u][-v]|
+            v = w - v;
+            u = u == 0 ? 0 : h - u;
+        }
+        double r = rint(__dadd_rn(__dmul_rn(src[(int64_t)u * wh + v], scale), shift));   // cvRound: ties to even
+        r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
+        dst[idx] = (uint8_t)r;
+    }
+}
+
+}  // namespace v5fft

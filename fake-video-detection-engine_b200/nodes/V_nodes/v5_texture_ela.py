@@ -10,12 +10,15 @@ What is replaced: the error-level analysis itself (:66-78: save q=90 -> reopen -
   Brightness.enhance) runs on the GPU through libv5ela.so (include/v5ela.h: v5ela_analyze_host) and is bit-exact, so
   ``ela_{i}.jpg`` is byte-identical to the reference's. There is no CPU fallback: if the library or a B200 is missing the
   per-face ``try`` reports the error exactly like any other analysis failure.
+  The FFT log-magnitude spectrum image (:84-88) also runs on the GPU (v5ela_spectrum_host: float64 DFT + log + min/max
+  normalisation); it is within one grey level of NumPy/OpenCV and bit-identical on every crop of the golden set, so
+  ``fft_{i}.jpg`` matches the reference's file there too. ``state["v5_gpu_fft"] = False`` selects the reference's host code.
 What is added (optional, defaults reproduce the reference): state keys ``v5_quality`` (90), ``v5_max_faces`` (3),
-  ``v5_device`` (0), ``v5_keep_temp_jpeg`` (False: the reference's ``temp_ela_{i}.jpg`` scratch file is only written on
-  request since nothing reads it); the per-face integer/float statistics of the V5F v1 record are attached as
+  ``v5_device`` (0), ``v5_gpu_fft`` (True), ``v5_keep_temp_jpeg`` (False: the reference's ``temp_ela_{i}.jpg`` scratch file
+  is only written on request since nothing reads it); the per-face integer/float statistics of the V5F v1 record are attached as
   ``ela_features`` inside ``texture_ela_details`` entries and ``V5_debug.json`` (lr_node reads only ``avg_score``).
-Still on the host, as in the reference: decoding the crop (:64, :83), the float64 FFT spectrum image (:84-91, a "next"
-  row in DESIGN.md), JPEG-encoding the two artefacts, and the OpenAI call.
+Still on the host, as in the reference: decoding the crop (:64, :83), JPEG-encoding the two artefacts (:81, :91), and
+  the OpenAI call.
 """
 import base64
 import json
@@ -104,10 +107,15 @@ def run(state: dict) -> dict:
             Image.fromarray(enhanced, "RGB").save(ela_output_path)
 
             gray_image = cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
-            f = np.fft.fft2(gray_image)
-            fshift = np.fft.fftshift(f)
-            magnitude_spectrum = 20 * np.log(np.abs(fshift) + 1)
-            magnitude_spectrum = cv2.normalize(magnitude_spectrum, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+            if state.get("v5_gpu_fft", True):
+                from v5ela import host as v5host
+
+                magnitude_spectrum = v5host.spectrum_host(gray_image, device=device)
+            else:                                   # the reference's host path, verbatim (v5_texture_ela.py:84-88)
+                f = np.fft.fft2(gray_image)
+                fshift = np.fft.fftshift(f)
+                magnitude_spectrum = 20 * np.log(np.abs(fshift) + 1)
+                magnitude_spectrum = cv2.normalize(magnitude_spectrum, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
             fft_output_path = os.path.join(ela_dir, f"fft_{i}.jpg")
             cv2.imwrite(fft_output_path, magnitude_spectrum)
 

@@ -13,7 +13,7 @@ from .synth import gen_batch, gen_batch_torch, gen_frame  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must not require the CUDA library (CPU-only tooling, tests)
-    if name in ("analyze_batch", "reduce_records", "get_handle"):
+    if name in ("analyze_batch", "reduce_records", "get_handle", "spectrum_batch"):
         from . import batch
 
         return getattr(batch, name)

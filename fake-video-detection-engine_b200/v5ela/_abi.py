@@ -13,7 +13,7 @@ EXPORTS = (
     "v5ela_abi_version", "v5ela_record_bytes", "v5ela_status_string", "v5ela_create", "v5ela_destroy",
     "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze",
     "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
-    "v5ela_profile_read",
+    "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host",
 )
 
 
@@ -56,6 +56,8 @@ def load() -> ctypes.CDLL:
     lib.v5ela_enhance.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.v5ela_reduce_records.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.v5ela_spectrum.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp]
+    lib.v5ela_spectrum_host.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.v5ela_profile_enable.argtypes = [vp, i32]
     lib.v5ela_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     lib.v5ela_launch_count.restype = i64
@@ -121,6 +123,13 @@ class Handle:
         """Host-buffer entry point; synchronous when `stream` is None, else asynchronous on that stream."""
         self._check(self._lib.v5ela_analyze_host(self._h, rgb_host, n, h, w, records_host, residual_host or None,
                                                  enhanced_host or None, stream or None))
+
+    def spectrum(self, d_gray: int, n: int, h: int, w: int, frame_stride: int, row_stride: int, d_out: int,
+                 stream: int | None):
+        self._check(self._lib.v5ela_spectrum(self._h, d_gray, n, h, w, frame_stride, row_stride, d_out, stream or None))
+
+    def spectrum_host(self, gray_host: int, n: int, h: int, w: int, out_host: int):
+        self._check(self._lib.v5ela_spectrum_host(self._h, gray_host, n, h, w, out_host))
 
     def profile_enable(self, enable: bool = True):
         self._check(self._lib.v5ela_profile_enable(self._h, 1 if enable else 0))

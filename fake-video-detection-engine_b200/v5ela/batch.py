@@ -83,3 +83,21 @@ def reduce_records(records, group: int, handle=None):
     if n:
         hd.reduce_records(records.data_ptr(), n, group, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     return out
+
+
+def spectrum_batch(gray, handle=None):
+    """FFT log-magnitude spectrum images of a torch.uint8 CUDA tensor (N, H, W) -> uint8 (N, H, W); see include/v5ela.h."""
+    import torch
+
+    if not isinstance(gray, torch.Tensor) or gray.dtype != torch.uint8 or gray.dim() != 3 or not gray.is_cuda:
+        raise ValueError("gray must be a torch.uint8 CUDA tensor of shape (N, H, W)")
+    if gray.stride(2) != 1:
+        gray = gray.contiguous()
+    n, h, w = gray.shape
+    dev = gray.device
+    hd = handle or get_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    if n and h and w:
+        hd.spectrum(gray.data_ptr(), n, h, w, gray.stride(0), gray.stride(1), out.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+    return out

@@ -44,3 +44,18 @@ def analyze_frames_host(frames: np.ndarray, quality: int = 90, want_residual: bo
                     residual.ctypes.data if residual is not None else None,
                     enhanced.ctypes.data if enhanced is not None else None, None)
     return recs, residual, enhanced
+
+
+def spectrum_host(gray: np.ndarray, device: int = 0) -> np.ndarray:
+    """FFT log-magnitude spectrum image(s) (v5_texture_ela.py:84-88) of (H, W) or (N, H, W) uint8 host arrays."""
+    g = np.ascontiguousarray(gray, dtype=np.uint8)
+    single = g.ndim == 2
+    if single:
+        g = g[None]
+    if g.ndim != 3:
+        raise ValueError("gray must have shape (H, W) or (N, H, W)")
+    out = np.empty_like(g)
+    n, h, w = g.shape
+    if n and h and w:
+        _handle(device).spectrum_host(g.ctypes.data, n, h, w, out.ctypes.data)
+    return out[0] if single else out

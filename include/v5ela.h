@@ -126,6 +126,19 @@ V5ELA_API int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n
                        void *cuda_stream);
 
 /*
+ * The reference's "texture" artefact, SURVEY.md §8f-1 (v5_texture_ela.py:84-88):
+ *   f = np.fft.fft2(gray); fshift = np.fft.fftshift(f); ms = 20*np.log(np.abs(fshift)+1);
+ *   cv2.normalize(ms, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+ * for `n` single-channel uint8 images of any size (float64 DFT, exact sizes, no padding). d_out: n x h x w uint8,
+ * tightly packed. Parity: within 1 grey level of NumPy/OpenCV (summation order differs from pocketfft).
+ */
+V5ELA_API int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, int width,
+                   int64_t frame_stride_bytes, int64_t row_stride_bytes, uint8_t *d_out, void *cuda_stream);
+/* Same with HOST buffers (what the drop-in node calls); synchronises before returning. */
+V5ELA_API int v5ela_spectrum_host(v5ela_handle *h, const uint8_t *gray_host, int n, int height, int width,
+                        uint8_t *out_host);
+
+/*
  * Measurement hook: while enabled, every v5ela_analyze records a CUDA event pair around the fused kernel on the launch
  * stream. v5ela_profile_read waits for the recorded events, returns the summed kernel time and launch count since the
  * last reset, and optionally resets. Used by bench.py for the roofline line; off by default.

@@ -1,28 +1,26 @@
 """Drop-in replacement for the reference node ``nodes/V_nodes/v5_texture_ela.py`` (same module path, same ``run``).
 
-What is unchanged (reference line numbers refer to /root/reference/nodes/V_nodes/v5_texture_ela.py):
-  * signature ``run(state: dict) -> dict``; reads ``face_detections``, ``debug``, ``data_dir`` (:16-18) and
-    ``OPENAI_API_KEY`` (:49); writes ``texture_ela_score`` / ``texture_ela_details`` (:22-23, :29-30, :163-164, :176-177)
-    with the same reason strings; top-3 selection by confidence*w*h of faces[0] (:33-42); artefacts
-    ``ela_analysis/ela_{i}.jpg`` and ``fft_{i}.jpg`` named by selection rank (:80, :90); the GPT-4o request (:93-138);
-    the score aggregation and ``V5_debug.json`` payload keys (:147-173); per-face errors are printed and swallowed (:140-144).
-What is replaced: the error-level analysis itself (:66-78: save q=90 -> reopen -> ImageChops.difference -> getextrema ->
-  Brightness.enhance) runs on the GPU through libv5ela.so (include/v5ela.h: v5ela_analyze_host) and is bit-exact, so
-  ``ela_{i}.jpg`` is byte-identical to the reference's. There is no CPU fallback: if the library or a B200 is missing the
-  per-face ``try`` reports the error exactly like any other analysis failure.
-  The FFT log-magnitude spectrum image (:84-88) also runs on the GPU (v5ela_spectrum_host: float64 DFT + log + min/max
-  normalisation); it is within one grey level of NumPy/OpenCV and bit-identical on every crop of the golden set, so
-  ``fft_{i}.jpg`` matches the reference's file there too. ``state["v5_gpu_fft"] = False`` selects the reference's host code.
-What is added (optional, defaults reproduce the reference): state keys ``v5_quality`` (90), ``v5_max_faces`` (3),
-  ``v5_device`` (0), ``v5_gpu_fft`` (True), ``v5_keep_temp_jpeg`` (False: the reference's ``temp_ela_{i}.jpg`` scratch file
-  is only written on request since nothing reads it); the per-face integer/float statistics of the V5F v1 record are attached as
-  ``ela_features`` inside ``texture_ela_details`` entries and ``V5_debug.json`` (lr_node reads only ``avg_score``).
-Still on the host, as in the reference: decoding the crop (:64, :83), JPEG-encoding the two artefacts (:81, :91), and
-  the OpenAI call.
+Behaviour contract kept from the reference (line numbers: /root/reference/nodes/V_nodes/v5_texture_ela.py):
+  * ``run(state) -> state``; inputs ``face_detections``, ``debug``, ``data_dir`` (:16-18), env ``OPENAI_API_KEY`` (:49);
+    outputs ``texture_ela_score`` / ``texture_ela_details`` with the three reason strings (:22-23, :29-30, :176-177);
+  * at most three faces, ranked by confidence * w * h of ``faces[0]`` (:33-42); artefacts ``ela_analysis/ela_{i}.jpg`` and
+    ``fft_{i}.jpg`` numbered by rank (:80, :90); the GPT-4o request — model, prompts, three base64 JPEGs, JSON response
+    format, 30 s timeout (:102-125); mean of ``fake_probability`` (:147-165); ``V5_debug.json`` keys (:166-173);
+    any per-face failure is printed and skipped, never raised (:140-144).
+What runs on the B200 instead of Pillow/NumPy: the error-level analysis (:66-78) through ``v5ela_analyze_host`` —
+  bit-exact, so ``ela_{i}.jpg`` equals the reference's file byte for byte — and the FFT log-magnitude image (:84-88)
+  through ``v5ela_spectrum_host`` (within one grey level of NumPy; identical on every golden crop). There is no CPU
+  fallback: a missing library or GPU surfaces as that face's error, like any other analysis failure.
+Optional state keys (defaults = the reference's literals): ``v5_quality`` 90, ``v5_max_faces`` 3, ``v5_device`` 0,
+  ``v5_gpu_fft`` True (False: the reference's NumPy spectrum), ``v5_keep_temp_jpeg`` False (the reference's scratch file
+  ``temp_ela_{i}.jpg``, which nothing reads, is written only on request). The V5F v1 statistics of every analysed face are
+  attached as ``ela_features`` to ``texture_ela_details`` entries and ``V5_debug.json`` (lr_node reads only ``avg_score``).
+Host side, unchanged: decoding the crop, JPEG-encoding the two artefacts, the OpenAI call.
 """
 import base64
 import json
 import os
+import traceback
 
 import cv2
 import numpy as np
@@ -34,181 +32,147 @@ from nodes import dump_node_debug
 
 load_dotenv()
 
+_SYSTEM_PROMPT = (
+    "You are a forensic image analyst specializing in deepfake detection. "
+    "You MUST return a JSON object (nothing else) with keys 'fake_probability' "
+    "and 'reasoning'."
+)
+_USER_PROMPT = "Analyze this face for manipulation. Return JSON."
 
-def _analyze_crop(rgb: np.ndarray, quality: int, device: int):
-    """GPU error-level analysis of one RGB crop -> (features dict, enhanced residual image HxWx3 uint8)."""
+
+def _finish(state, score, details):
+    state["texture_ela_score"] = score
+    state["texture_ela_details"] = details
+    return state
+
+
+def _rank_faces(detections, limit):
+    """Detections that carry a crop, best first by confidence x bbox area of their first face."""
+    with_crops = [d for d in detections if d.get("faces")]
+
+    def weight(det):
+        face = det["faces"][0]
+        return face["confidence"] * face["bbox"]["w"] * face["bbox"]["h"]
+
+    return with_crops, sorted(with_crops, key=weight, reverse=True)[:limit]
+
+
+def _gpu_artefacts(crop_path, rank, ela_dir, state):
+    """ELA + spectrum artefacts of one crop; returns (feature dict, ela path, fft path)."""
     from v5ela import host as v5host
     from v5ela.records import features
 
-    recs, _, enhanced = v5host.analyze_frames_host(rgb[None], quality=quality, want_enhanced=True, device=device)
-    return features(recs[0], rgb.shape[0] * rgb.shape[1]), enhanced[0]
+    quality = int(state.get("v5_quality", 90))
+    device = int(state.get("v5_device", 0))
+    rgb = np.asarray(Image.open(crop_path).convert("RGB"))
+    if state.get("v5_keep_temp_jpeg", False):
+        Image.fromarray(rgb, "RGB").save(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), "JPEG", quality=quality)
+
+    records, _, enhanced = v5host.analyze_frames_host(rgb[None], quality=quality, want_enhanced=True, device=device)
+    feats = features(records[0], rgb.shape[0] * rgb.shape[1])
+    feats["rank"] = rank
+    ela_path = os.path.join(ela_dir, f"ela_{rank}.jpg")
+    Image.fromarray(enhanced[0], "RGB").save(ela_path)
+
+    gray = cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
+    if state.get("v5_gpu_fft", True):
+        spectrum = v5host.spectrum_host(gray, device=device)
+    else:
+        log_mag = 20 * np.log(np.abs(np.fft.fftshift(np.fft.fft2(gray))) + 1)
+        spectrum = cv2.normalize(log_mag, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+    fft_path = os.path.join(ela_dir, f"fft_{rank}.jpg")
+    cv2.imwrite(fft_path, spectrum)
+    return feats, ela_path, fft_path
+
+
+def _ask_model(client, image_paths):
+    """One chat completion over (crop, ELA image, spectrum image); returns the raw message content."""
+    parts = [{"type": "text", "text": _USER_PROMPT}]
+    for path in image_paths:
+        with open(path, "rb") as fh:
+            b64 = base64.b64encode(fh.read()).decode("utf-8")
+        parts.append({"type": "image_url", "image_url": {"url": f"data:image/jpeg;base64,{b64}"}})
+    response = client.chat.completions.create(
+        model="gpt-4o",
+        messages=[{"role": "system", "content": _SYSTEM_PROMPT}, {"role": "user", "content": parts}],
+        response_format={"type": "json_object"},
+        timeout=30.0,
+    )
+    return response.choices[0].message.content
+
+
+def _probabilities(results):
+    out = []
+    for item in results:
+        value = item.get("fake_probability") if isinstance(item, dict) else item
+        try:
+            out.append(float(value))
+        except Exception:
+            pass
+    return out
 
 
 def run(state: dict) -> dict:
     print("Node V5: Running Texture & ELA Analysis...")
-
-    face_detections = state.get("face_detections", [])
+    detections = state.get("face_detections", [])
     debug = state.get("debug", False)
-    output_dir = state.get("data_dir")
-    quality = int(state.get("v5_quality", 90))
-    max_faces = int(state.get("v5_max_faces", 3))
-    device = int(state.get("v5_device", 0))
 
-    if not face_detections:
+    if not detections:
         print("Node V5: No faces detected to analyze.")
-        state["texture_ela_score"] = 0.0
-        state["texture_ela_details"] = {"reason": "No faces found"}
-        return state
-
-    valid_faces = [f for f in face_detections if f.get("faces")]
-    if not valid_faces:
+        return _finish(state, 0.0, {"reason": "No faces found"})
+    with_crops, chosen = _rank_faces(detections, int(state.get("v5_max_faces", 3)))
+    if not with_crops:
         print("Node V5: Face detections present but no crops were generated.")
-        state["texture_ela_score"] = 0.0
-        state["texture_ela_details"] = {"reason": "No face crops available"}
-        return state
+        return _finish(state, 0.0, {"reason": "No face crops available"})
 
-    sorted_faces = sorted(
-        valid_faces,
-        key=lambda x: x["faces"][0]["confidence"] * x["faces"][0]["bbox"]["w"] * x["faces"][0]["bbox"]["h"],
-        reverse=True,
-    )
-    selected_faces = sorted_faces[:max_faces]
-
-    ela_dir = os.path.join(output_dir, "ela_analysis")
+    ela_dir = os.path.join(state.get("data_dir"), "ela_analysis")
     os.makedirs(ela_dir, exist_ok=True)
 
-    analysis_results = []
-    ela_features = []
-
     api_key = os.getenv("OPENAI_API_KEY")
-    client = None
-    if api_key:
-        client = OpenAI(api_key=api_key)
-    else:
+    client = OpenAI(api_key=api_key) if api_key else None
+    if client is None:
         print("Node V5: OPENAI_API_KEY not found. Skipping OpenAI analysis.")
 
-    for i, face_data in enumerate(selected_faces):
+    verdicts, per_face = [], []
+    for rank, detection in enumerate(chosen):
         try:
-            face_info = face_data["faces"][0]
-            crop_path = face_info["crop_path"]
-
+            crop_path = detection["faces"][0]["crop_path"]
             if not os.path.exists(crop_path):
                 continue
-
-            original = Image.open(crop_path).convert("RGB")
-            if state.get("v5_keep_temp_jpeg", False):
-                original.save(os.path.join(ela_dir, f"temp_ela_{i}.jpg"), "JPEG", quality=quality)
-
-            feats, enhanced = _analyze_crop(np.asarray(original), quality, device)
-            feats["rank"] = i
-            ela_features.append(feats)
-
-            ela_output_path = os.path.join(ela_dir, f"ela_{i}.jpg")
-            Image.fromarray(enhanced, "RGB").save(ela_output_path)
-
-            gray_image = cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
-            if state.get("v5_gpu_fft", True):
-                from v5ela import host as v5host
-
-                magnitude_spectrum = v5host.spectrum_host(gray_image, device=device)
-            else:                                   # the reference's host path, verbatim (v5_texture_ela.py:84-88)
-                f = np.fft.fft2(gray_image)
-                fshift = np.fft.fftshift(f)
-                magnitude_spectrum = 20 * np.log(np.abs(fshift) + 1)
-                magnitude_spectrum = cv2.normalize(magnitude_spectrum, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
-            fft_output_path = os.path.join(ela_dir, f"fft_{i}.jpg")
-            cv2.imwrite(fft_output_path, magnitude_spectrum)
-
-            if client:
-                def encode_image(image_path):
-                    with open(image_path, "rb") as image_file:
-                        return base64.b64encode(image_file.read()).decode("utf-8")
-
-                base64_original = encode_image(crop_path)
-                base64_ela = encode_image(ela_output_path)
-                base64_fft = encode_image(fft_output_path)
-
-                response = client.chat.completions.create(
-                    model="gpt-4o",
-                    messages=[
-                        {
-                            "role": "system",
-                            "content": (
-                                "You are a forensic image analyst specializing in deepfake detection. "
-                                "You MUST return a JSON object (nothing else) with keys 'fake_probability' "
-                                "and 'reasoning'."
-                            ),
-                        },
-                        {
-                            "role": "user",
-                            "content": [
-                                {"type": "text", "text": "Analyze this face for manipulation. Return JSON."},
-                                {"type": "image_url", "image_url": {"url": f"data:image/jpeg;base64,{base64_original}"}},
-                                {"type": "image_url", "image_url": {"url": f"data:image/jpeg;base64,{base64_ela}"}},
-                                {"type": "image_url", "image_url": {"url": f"data:image/jpeg;base64,{base64_fft}"}},
-                            ],
-                        },
-                    ],
-                    response_format={"type": "json_object"},
-                    timeout=30.0,
-                )
-
-                content = response.choices[0].message.content
-                if not content:
-                    if debug:
-                        print(f"[DEBUG] V5: Empty response content for face {i}, skipping.")
-                    continue
-                try:
-                    result_json = json.loads(content)
-                    if isinstance(result_json, dict):
-                        result_json.setdefault("ela_features", feats)
-                    analysis_results.append(result_json)
-                except Exception as parse_err:
-                    print(f"Error parsing OpenAI response for face {i}: {parse_err}")
-                    if debug:
-                        print(f"[DEBUG] V5: Raw content: {content}")
-
+            feats, ela_path, fft_path = _gpu_artefacts(crop_path, rank, ela_dir, state)
+            per_face.append(feats)
+            if client is None:
+                continue
+            content = _ask_model(client, (crop_path, ela_path, fft_path))
+            if not content:
+                if debug:
+                    print(f"[DEBUG] V5: Empty response content for face {rank}, skipping.")
+                continue
+            try:
+                verdict = json.loads(content)
+            except Exception as parse_err:
+                print(f"Error parsing OpenAI response for face {rank}: {parse_err}")
+                if debug:
+                    print(f"[DEBUG] V5: Raw content: {content}")
+                continue
+            if isinstance(verdict, dict):
+                verdict.setdefault("ela_features", feats)
+            verdicts.append(verdict)
         except Exception as e:
-            print(f"Error analyzing face {i}: {e}")
+            print(f"Error analyzing face {rank}: {e}")
             if debug:
-                import traceback
-
                 traceback.print_exc()
 
-    def _safe_float(val, default=0.0):
-        try:
-            return float(val)
-        except Exception:
-            return default
-
-    scores = []
-    for r in analysis_results:
-        if isinstance(r, dict):
-            scores.append(_safe_float(r.get("fake_probability"), None))
-        else:
-            scores.append(_safe_float(r, None))
-    scores = [s for s in scores if s is not None]
-
-    if scores:
-        avg_score = sum(scores) / len(scores)
-        state["texture_ela_score"] = avg_score
-        state["texture_ela_details"] = analysis_results
-        print(f"Node V5: Analysis complete. Score: {avg_score:.2f}")
-        dump_node_debug(
-            state,
-            "V5",
-            {
-                "faces_analyzed": len(analysis_results),
-                "avg_score": avg_score,
-                "ela_features": ela_features,
-            },
-        )
-    else:
+    scores = _probabilities(verdicts)
+    if not scores:
         print("Node V5: No analysis results generated.")
-        state["texture_ela_score"] = 0.0
         details = {"reason": "Analysis failed or no keys"}
-        if ela_features:
-            details["ela_features"] = ela_features
-        state["texture_ela_details"] = details
+        if per_face:
+            details["ela_features"] = per_face
+        return _finish(state, 0.0, details)
 
+    avg_score = sum(scores) / len(scores)
+    print(f"Node V5: Analysis complete. Score: {avg_score:.2f}")
+    _finish(state, avg_score, verdicts)
+    dump_node_debug(state, "V5", {"faces_analyzed": len(verdicts), "avg_score": avg_score, "ela_features": per_face})
     return state

@@ -228,6 +228,32 @@ inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { m
 inline void mbar_wait(uint64_t *, uint32_t) {}
 #endif
 
+// cvt.pack.sat.u8.s32 (SASS I2IP): d = (c.lo16 << 16) | (sat_u8(a) << 8) | sat_u8(b) — clamp to 0..255 and pack in one go
+#ifdef __CUDA_ARCH__
+V5_DEV uint32_t packsat2(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#else
+inline uint32_t packsat2(int a, int b, uint32_t c)
+{
+    return ((c & 0xffffu) << 16) | ((uint32_t)clamp255(a) << 8) | (uint32_t)clamp255(b);
+}
+#endif
+// four ints -> bytes [v0, v1, v2, v3], each clamped to 0..255: two I2IP
+#ifndef V5_NO_I2IP
+V5_DEV uint32_t pack4sat(int v0, int v1, int v2, int v3) { return packsat2(v1, v0, packsat2(v3, v2, 0u)); }
+#else
+V5_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel);
+V5_DEV uint32_t pack4sat(int v0, int v1, int v2, int v3)
+{
+    const uint32_t a = (uint32_t)clamp255(v0), b = (uint32_t)clamp255(v1), c = (uint32_t)clamp255(v2), d = (uint32_t)clamp255(v3);
+    return prmt(prmt(a, b, 0x0040u), prmt(c, d, 0x0040u), 0x5410u);
+}
+#endif
+
 // byte k (compile-time) of w, zero-extended: one PRMT
 V5_DEV uint32_t byte_of(uint32_t w, int k) { return prmt(w, 0u, 0x4440u + (uint32_t)k); }
 // four values 0..255 held in ints -> one word: three PRMTs
@@ -400,8 +426,8 @@ V5_DEV void convert8x2(const uint8_t *la, const uint8_t *lb, U2 &y0, U2 &y1, uin
             ya[k] = y_of(a, k);
             yb[k] = y_of(b, k);
         }
-        y0 = U2{pack4(ya[0], ya[1], ya[2], ya[3]), pack4(ya[4], ya[5], ya[6], ya[7])};
-        y1 = U2{pack4(yb[0], yb[1], yb[2], yb[3]), pack4(yb[4], yb[5], yb[6], yb[7])};
+        y0 = U2{pack4sat(ya[0], ya[1], ya[2], ya[3]), pack4sat(ya[4], ya[5], ya[6], ya[7])};
+        y1 = U2{pack4sat(yb[0], yb[1], yb[2], yb[3]), pack4sat(yb[4], yb[5], yb[6], yb[7])};
     }
     if (WANT_C) {                                               // h2v2 box filter, bias 1,2,1,2 along x
         int c[4], d[4];
@@ -411,8 +437,8 @@ V5_DEV void convert8x2(const uint8_t *la, const uint8_t *lb, U2 &y0, U2 &y1, uin
             c[j] = (bias - (neg_cb_of(a, 2 * j) + neg_cb_of(a, 2 * j + 1) + neg_cb_of(b, 2 * j) + neg_cb_of(b, 2 * j + 1))) >> 2;
             d[j] = (bias - (neg_cr_of(a, 2 * j) + neg_cr_of(a, 2 * j + 1) + neg_cr_of(b, 2 * j) + neg_cr_of(b, 2 * j + 1))) >> 2;
         }
-        cbo = pack4(c[0], c[1], c[2], c[3]);
-        cro = pack4(d[0], d[1], d[2], d[3]);
+        cbo = pack4sat(c[0], c[1], c[2], c[3]);
+        cro = pack4sat(d[0], d[1], d[2], d[3]);
     }
 }
 
@@ -488,7 +514,8 @@ V5_DEV void fdct8(int *v)
     v[S] = (t7 * V5_C1_501 + z1 + z4b) >> n;
 }
 
-// Inverse 8-point pass. FINAL: row pass, descale 18, +128 and clamp to 0..255; otherwise column pass, descale 11.
+// Inverse 8-point pass. FINAL: row pass, descale 18, +128 (the clamp to 0..255 happens in the saturating pack that
+// follows); otherwise column pass, descale 11.
 template <int S, bool FINAL>
 V5_DEV void idct8(int *v)
 {
@@ -508,16 +535,7 @@ V5_DEV void idct8(int *v)
     u1 = u1 * V5_C2_053 + z2 + z4b;
     u2 = u2 * V5_C3_072 + z2 + z3b;
     u3 = u3 * V5_C1_501 + z1 + z4b;
-    if (FINAL) {
-        v[0] = clamp255((t10 + u3) >> n);
-        v[7 * S] = clamp255((t10 - u3) >> n);
-        v[S] = clamp255((t11 + u2) >> n);
-        v[6 * S] = clamp255((t11 - u2) >> n);
-        v[2 * S] = clamp255((t12 + u1) >> n);
-        v[5 * S] = clamp255((t12 - u1) >> n);
-        v[3 * S] = clamp255((t13 + u0) >> n);
-        v[4 * S] = clamp255((t13 - u0) >> n);
-    } else {
+    {                                                           // FINAL: the caller packs with saturation (0..255)
         v[0] = (t10 + u3) >> n;
         v[7 * S] = (t10 - u3) >> n;
         v[S] = (t11 + u2) >> n;
@@ -657,8 +675,8 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
     int b[8] = {s16_lo(w1.x), s16_hi(w1.x), s16_lo(w1.y), s16_hi(w1.y), s16_lo(w1.z), s16_hi(w1.z), s16_lo(w1.w), s16_hi(w1.w)};
     idct8<1, true>(a);
     idct8<1, true>(b);
-    *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4(a[0], a[1], a[2], a[3]), pack4(a[4], a[5], a[6], a[7])};
-    *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4(b[0], b[1], b[2], b[3]), pack4(b[4], b[5], b[6], b[7])};
+    *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4sat(a[0], a[1], a[2], a[3]), pack4sat(a[4], a[5], a[6], a[7])};
+    *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4sat(b[0], b[1], b[2], b[3]), pack4sat(b[4], b[5], b[6], b[7])};
 }
 
 // ------------------------------------------------------------------- stage: upsample, reconstruct, residual, Laplacian
@@ -732,16 +750,13 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     for (int k = 0; k < 8; k++) {
         const int ykr = (int)prmt(ydw[k >> 2], 0x00008000u, 0x4054u + ((uint32_t)(k & 3) << 8));   // bytes: 00 80 Y 00
         const int cbv = cb[k], crv = cr[k];
-        rec[3 * k] = clamp255((91881 * crv + ykr) >> 16);
-        rec[3 * k + 1] = clamp255((-22554 * cbv + (-46802 * crv + ykr)) >> 16);
-        rec[3 * k + 2] = clamp255((116130 * cbv + ykr) >> 16);
+        rec[3 * k] = (91881 * crv + ykr) >> 16;                // clamped to 0..255 by the saturating pack below
+        rec[3 * k + 1] = (-22554 * cbv + (-46802 * crv + ykr)) >> 16;
+        rec[3 * k + 2] = (116130 * cbv + ykr) >> 16;
     }
 #pragma unroll
     for (int i = 0; i < 6; i++)
-        dw[i] = absdiff4(ow[i], pack4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
-#pragma unroll
-    for (int b = 0; b < 24; b++)
-        if (b < 3 * nvalid) hist_add(S.hist[b % 3], dw[b >> 2], b & 3);
+        dw[i] = absdiff4(ow[i], pack4sat(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
     if (g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
         if (nvalid >= 8 && p.resid_vec_ok) {
@@ -753,51 +768,74 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
                 if (b < 3 * nvalid) dst[b] = (uint8_t)byte_of(dw[b >> 2], b & 3);
         }
     }
+    // Histogram: every unit adds all 24 bytes unconditionally; a unit cut by the right image edge first zeroes the bytes
+    // of its outside pixels and takes them out of bin 0 again (rare, keeps the common path free of per-byte predicates).
+    if (nvalid < 8) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const int vb = 3 * nvalid - 4 * i;                  // valid bytes in word i
+            dw[i] &= vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : (1u << (8 * vb)) - 1u);
+        }
+#ifdef __CUDA_ARCH__
+        atomicSub(&S.hist[0][0], (uint32_t)(8 - nvalid));
+        atomicSub(&S.hist[1][0], (uint32_t)(8 - nvalid));
+        atomicSub(&S.hist[2][0], (uint32_t)(8 - nvalid));
+#else
+        S.hist[0][0] -= (uint32_t)(8 - nvalid);
+        S.hist[1][0] -= (uint32_t)(8 - nvalid);
+        S.hist[2][0] -= (uint32_t)(8 - nvalid);
+#endif
+    }
+#pragma unroll
+    for (int b = 0; b < 24; b++) hist_add(S.hist[b % 3], dw[b >> 2], b & 3);
 
     // ---- texture: Laplacian of the original luma, BORDER_REFLECT_101 (§8a)
     int lu = l - 1, ld = l + 1;
     if (y == 0) lu = p.h > 1 ? l + 1 : l;
     if (y == p.h - 1) ld = p.h > 1 ? l - 1 : l;
     const uint8_t *yc = &S.yorig[ring16(r, l)][col];
-    const U2 cw = *reinterpret_cast<const U2 *>(yc);
-    const U2 uw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, lu)][col]);
-    const U2 lw = *reinterpret_cast<const U2 *>(&S.yorig[ring16(r, ld)][col]);
-    // Reflection at the left/right image edge: the left neighbour of column 0 comes from a selected address; the single
-    // pixel in column W-1 is left out of the vector loop (nacc) and done on its own below.
+    const uint8_t *yu = &S.yorig[ring16(r, lu)][col], *yd2 = &S.yorig[ring16(r, ld)][col];
     const int wide = p.w > 1;
-    const int edge = nvalid <= 8 ? nvalid - 1 : -1;             // index of the pixel in image column W-1, if in this unit
-    const int nacc = edge >= 0 ? edge : 8;
-    // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per pixel
-    const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = yc[8];
-    const uint32_t x[3] = {prmt(hl, cw.x, 0x6540u), prmt(cw.x, cw.y, 0x6543u), prmt(cw.y, hr, 0x7743u)};
-    const uint32_t ud[2][2] = {{uw.x, lw.x}, {uw.y, lw.y}};
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
+    {
+        // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per
+        // pixel, up + down two more. The pixel in image column W-1 (if in this unit) is left out of the vector loop and
+        // done on its own below, mirroring W onto W-2; column -1 mirrors onto column 1 through the selected address.
+        const U2 cw = *reinterpret_cast<const U2 *>(yc);
+        const U2 uw = *reinterpret_cast<const U2 *>(yu);
+        const U2 lw = *reinterpret_cast<const U2 *>(yd2);
+        const int edge = nvalid <= 8 ? nvalid - 1 : -1;
+        const int nacc = edge >= 0 ? edge : 8;
+        const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = yc[8];
+        const uint32_t x[3] = {prmt(hl, cw.x, 0x6540u), prmt(cw.x, cw.y, 0x6543u), prmt(cw.y, hr, 0x7743u)};
+        const uint32_t ud[2][2] = {{uw.x, lw.x}, {uw.y, lw.y}};
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int w0 = k >> 2, s0 = k & 3;                      // window e[k..k+2] starts at byte s0 of x[w0]
-        int lap = dp4a_us(ud[w0][0], 1u << (8 * s0), dp4a_us(ud[w0][1], 1u << (8 * s0), 0));      // up + down
-        if (s0 <= 1) {
-            lap = dp4a_us(x[w0], 0x01fc01u << (8 * s0), lap);
-        } else if (s0 == 2) {
-            lap = dp4a_us(x[w0 + 1], 0x00000001u, dp4a_us(x[w0], 0xfc010000u, lap));
-        } else {
-            lap = dp4a_us(x[w0 + 1], 0x000001fcu, dp4a_us(x[w0], 0x01000000u, lap));
+        for (int k = 0; k < 8; k++) {
+            const int w0 = k >> 2, s0 = k & 3;                  // window e[k..k+2] starts at byte s0 of x[w0]
+            int lap = dp4a_us(ud[w0][0], 1u << (8 * s0), dp4a_us(ud[w0][1], 1u << (8 * s0), 0));      // up + down
+            if (s0 <= 1) {
+                lap = dp4a_us(x[w0], 0x01fc01u << (8 * s0), lap);
+            } else if (s0 == 2) {
+                lap = dp4a_us(x[w0 + 1], 0x00000001u, dp4a_us(x[w0], 0xfc010000u, lap));
+            } else {
+                lap = dp4a_us(x[w0 + 1], 0x000001fcu, dp4a_us(x[w0], 0x01000000u, lap));
+            }
+            lap = lap < 0 ? -lap : lap;
+            if (k < nacc) {
+                sabs += (uint32_t)lap;
+                ssq += (uint32_t)(lap * lap);
+                mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
+            }
         }
-        lap = lap < 0 ? -lap : lap;
-        if (k < nacc) {
+        if (edge >= 0) {
+            const int ctr = yc[edge];
+            const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;
+            int lap = 2 * side + (int)yu[edge] + (int)yd2[edge] - 4 * ctr;
+            lap = lap < 0 ? -lap : lap;
             sabs += (uint32_t)lap;
             ssq += (uint32_t)(lap * lap);
             mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
         }
-    }
-    if (edge >= 0) {
-        const int ctr = yc[edge];
-        const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;   // W-2 mirrors onto W
-        int lap = 2 * side + (int)S.yorig[ring16(r, lu)][col + edge] + (int)S.yorig[ring16(r, ld)][col + edge] - 4 * ctr;
-        lap = lap < 0 ? -lap : lap;
-        sabs += (uint32_t)lap;
-        ssq += (uint32_t)(lap * lap);
-        mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
     }
     acc.tex_sumabs += sabs;
     acc.tex_sumsq += ssq;

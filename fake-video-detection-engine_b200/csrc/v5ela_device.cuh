@@ -337,20 +337,19 @@ V5_DEV LoadGeo load_geo(const KParams &p, const Geo &g)
 
 V5_DEV bool use_bulk(const KParams &p, const Geo &g) { return load_geo(p, g).nbulk > 0; }
 
-// one thread: arm the barrier with the byte count, then one bulk copy per line
-V5_DEV void stage_prefetch(Smem &S, const KParams &p, const Geo &g, int r)
+// Threads 0..15 (one per band line): thread 0 arms the barrier with the byte count, every thread issues the bulk copy of
+// its line. The barrier phase cannot complete before thread 0's arrive, whatever order the copies land in.
+V5_DEV void stage_prefetch(int tid, Smem &S, const KParams &p, const Geo &g, int r)
 {
+    if (tid >= 16) return;
     const LoadGeo L = load_geo(p, g);
     unsigned long long *bar = &S.full_bar[r & 1];
     async_proxy_fence();                                        // earlier generic accesses to this buffer are done
-    mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
-#pragma unroll 1
-    for (int l = 0; l < 16; l++) {
-        int y = 16 * r + l;
-        if (y > p.h - 1) y = p.h - 1;
-        bulk_g2s(&S.rgb[r & 1][l][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
-                 reinterpret_cast<uint64_t *>(bar));
-    }
+    if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
+    int y = 16 * r + tid;
+    if (y > p.h - 1) y = p.h - 1;
+    bulk_g2s(&S.rgb[r & 1][tid][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
+             reinterpret_cast<uint64_t *>(bar));
 }
 
 // all threads: whatever the bulk copy does not cover (everything when bulk == false)

@@ -125,7 +125,7 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     // Bands r0-1 and r1 only contribute decoded chroma / original luma to the rows next to them.
     const int r_first = g.r0 > 0 ? g.r0 - 1 : 0;
     const bool bulk = use_bulk(p, g);
-    V5_FOR_THREADS(if (bulk && tid == 0) stage_prefetch(S, p, g, r_first))
+    V5_FOR_THREADS(if (bulk) stage_prefetch(tid, S, p, g, r_first))
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;
         const bool want_y = r >= g.r0 && r < g.r1;
@@ -135,7 +135,7 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
             const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
             V5_FOR_THREADS({
-                if (bulk && next_band && tid == 0) stage_prefetch(S, p, g, r + 1);
+                if (bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
                 stage_load_rest(tid, S, p, g, r, bulk);
                 if (bulk) {
                     mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[r & 1]), (acc.phase >> (r & 1)) & 1u);

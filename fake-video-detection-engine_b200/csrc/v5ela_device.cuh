@@ -352,6 +352,12 @@ V5_DEV void stage_prefetch(int tid, Smem &S, const KParams &p, const Geo &g, int
              reinterpret_cast<uint64_t *>(bar));
 }
 
+V5_DEV bool load_rest_needed(const KParams &p, const Geo &g, bool bulk)
+{
+    const LoadGeo L = load_geo(p, g);
+    return (bulk ? L.nbulk : 0) != L.nbytes || L.npad3 > 0;
+}
+
 // all threads: whatever the bulk copy does not cover (everything when bulk == false)
 V5_DEV void stage_load_rest(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool bulk)
 {

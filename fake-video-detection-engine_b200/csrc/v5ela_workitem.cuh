@@ -125,6 +125,7 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     // Bands r0-1 and r1 only contribute decoded chroma / original luma to the rows next to them.
     const int r_first = g.r0 > 0 ? g.r0 - 1 : 0;
     const bool bulk = use_bulk(p, g);
+    const bool rest = load_rest_needed(p, g, bulk);
     V5_FOR_THREADS(if (bulk) stage_prefetch(tid, S, p, g, r_first))
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;
@@ -134,15 +135,18 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
             // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
             const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
+            if (rest) {                                     // ragged right edge / unaligned frames only
+                V5_FOR_THREADS(stage_load_rest(tid, S, p, g, r, bulk))
+            }
+            // every thread waits for the bulk copy itself, so no CTA barrier is needed before the conversion
             V5_FOR_THREADS({
                 if (bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
-                stage_load_rest(tid, S, p, g, r, bulk);
                 if (bulk) {
                     mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[r & 1]), (acc.phase >> (r & 1)) & 1u);
                     acc.phase ^= 1u << (r & 1);
                 }
+                stage_convert(tid, S, p, g, r);
             })
-            V5_FOR_THREADS(stage_convert(tid, S, p, g, r))
             const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
             for (int round = 0; round < rounds; round++) {
                 V5_BLOCK_TASK(t)

@@ -530,7 +530,6 @@ V5_DEV void idct8(int *v)
     const int t2 = i2 * V5_C0_541 + i6 * (V5_C0_541 - V5_C1_847);
     const int t3 = i6 * V5_C0_541 + i2 * (V5_C0_541 + V5_C0_765);
     const int t0 = (v[0] + v[4 * S]) * 8192 + rnd, t1 = (v[0] - v[4 * S]) * 8192 + rnd;
-    const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
     int u0 = v[7 * S], u1 = v[5 * S], u2 = v[3 * S], u3 = v[S];
     const int z1 = (u0 + u3) * -V5_C0_899, z2 = (u1 + u2) * -V5_C2_562;
     const int z3 = u0 + u2, z4 = u1 + u3;
@@ -540,16 +539,15 @@ V5_DEV void idct8(int *v)
     u1 = u1 * V5_C2_053 + z2 + z4b;
     u2 = u2 * V5_C3_072 + z2 + z3b;
     u3 = u3 * V5_C1_501 + z1 + z4b;
-    {                                                           // FINAL: the caller packs with saturation (0..255)
-        v[0] = (t10 + u3) >> n;
-        v[7 * S] = (t10 - u3) >> n;
-        v[S] = (t11 + u2) >> n;
-        v[6 * S] = (t11 - u2) >> n;
-        v[2 * S] = (t12 + u1) >> n;
-        v[5 * S] = (t12 - u1) >> n;
-        v[3 * S] = (t13 + u0) >> n;
-        v[4 * S] = (t13 - u0) >> n;
-    }
+    // three-input sums (t0 +- t3 +- u): one IADD3 each instead of forming t10..t13 first
+    v[0] = (t0 + t3 + u3) >> n;
+    v[7 * S] = (t0 + t3 - u3) >> n;
+    v[S] = (t1 + t2 + u2) >> n;
+    v[6 * S] = (t1 + t2 - u2) >> n;
+    v[2 * S] = (t1 - t2 + u1) >> n;
+    v[5 * S] = (t1 - t2 - u1) >> n;
+    v[3 * S] = (t0 - t3 + u0) >> n;
+    v[4 * S] = (t0 - t3 - u0) >> n;
 }
 
 // The block stage. Four threads share one 8x8 block; thread j owns rows 2j,2j+1 in the row passes and columns 2j,2j+1

@@ -35,8 +35,14 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_co
         mbar_init_fence();
     }
     __syncthreads();
-    // Work items are equal-sized (same strip/segment shapes in every frame): a static stride is balanced.
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) process_work_item(S, p, work, acc_store);
+    // Work items are drawn from a global ticket counter: no tail of idle CTAs whatever the batch size / CTA count ratio.
+    for (;;) {
+        if (threadIdx.x == 0) S.next_work = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int work = (int)S.next_work;
+        if (work >= total_work) break;
+        process_work_item(S, p, work, acc_store);                // ends with a CTA barrier: next_work may be rewritten
+    }
 }
 
 // One warp per (frame, channel): ela_sum = sum b*hist[b], ela_sumsq = sum b^2*hist[b], ela_max = highest non-empty bin.
@@ -152,6 +158,7 @@ struct v5ela_handle {
     int host_chunk_frames = 0;             // 0 = auto
     uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
     void *d_rec = nullptr;
+    unsigned int *d_ticket = nullptr;
     size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
     // spectrum path (v5ela_fft.cuh): twiddle tables for the last (width, height), DFT workspace
     double2 *tw_w = nullptr, *tw_h = nullptr;
@@ -237,6 +244,8 @@ int v5ela_create(int device, v5ela_handle **out)
     }
     const char *env = getenv("V5ELA_SEG_ROWS");
     if (env) h->seg_rows = atoi(env);
+    env = getenv("V5ELA_CTAS_PER_SM");                        // tuning knob: launch fewer persistent CTAs than fit
+    if (env && atoi(env) >= 1 && atoi(env) <= v5::MIN_CTAS) h->ctas_per_sm = atoi(env);
     env = getenv("V5ELA_HOST_CHUNK");
     if (env) h->host_chunk_frames = atoi(env);
     *out = h;
@@ -258,6 +267,7 @@ int v5ela_destroy(v5ela_handle *h)
     cudaFree(h->d_res);
     cudaFree(h->d_enh);
     cudaFree(h->d_rec);
+    cudaFree(h->d_ticket);
     cudaFree(h->tw_w);
     cudaFree(h->tw_h);
     cudaFree(h->d_g);
@@ -304,6 +314,9 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const long long total = (long long)n * p.n_strips * p.n_segs;
     if (total > 0x7fffffffLL) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: batch too large%s");
+    if (!h->d_ticket) V5_CUDA(h, cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    p.ticket = h->d_ticket;
+    V5_CUDA(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), st));
     V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
     const int max_ctas = h->sm_count * h->ctas_per_sm;
     const int grid = total < max_ctas ? (int)total : max_ctas;

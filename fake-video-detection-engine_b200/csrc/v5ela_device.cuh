@@ -69,6 +69,7 @@ struct KParams {
     int n, h, w;
     int mw, mh;                 // MCU columns / rows of the padded frame
     int n_strips, n_segs;       // work decomposition: strips x vertical segments per frame
+    unsigned int *ticket;       // work-item counter (zeroed before every launch): CTAs draw items dynamically
     int vec_ok;                 // 1: every band line start is 16-byte aligned in global memory (128-bit loads)
     int resid_vec_ok;           // 1: residual rows are 16-byte aligned (3*W % 16 == 0 and base aligned): 128-bit stores
     QuantTab q[2];              // [0] luma, [1] chroma — lives in the kernel parameter constant bank
@@ -265,13 +266,20 @@ V5_DEV uint32_t pack4(int a, int b, int c, int d)
 // ------------------------------------------------------------------------------------------------- shared memory
 struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
 
-constexpr int RING = 32;                // yorig ring lines (16 of the current band + 2 carried; power of two: cheap index)
+// Two shared-memory layouts, chosen by the number of resident CTAs the kernel is built for:
+//   RGB_BUFS == 2 (2 CTAs/SM): double-buffered RGB band (TMA runs a whole iteration ahead), original pixels for the
+//                  residual stage come from shared memory, 32-line luma ring.
+//   RGB_BUFS == 1 (3 CTAs/SM): one RGB staging buffer (the TMA copy of band r+1 is issued as soon as band r has been
+//                  converted and lands during the block and residual stages), the residual stage re-reads the original
+//                  pixels from global memory (L2 hits: the band went through L2 moments ago), 24-line luma ring.
+constexpr int RGB_BUFS = MIN_CTAS >= 3 ? 1 : 2;
+constexpr int RING = RGB_BUFS == 2 ? 32 : 24;   // yorig ring lines: 16 of the current band + 2 carried
 constexpr int RINGD = 24;               // ydec ring lines (16 + 1 carried)
 
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
-    uint8_t rgb[2][16][RGB_PITCH];      // band r in rgb[r & 1]; the other buffer receives band r+1 (bulk async copy)
-    uint8_t rgb_carry[2][RGB_PITCH];    // line 15 of band r in rgb_carry[r & 1] (finished one iteration later)
+    uint8_t rgb[RGB_BUFS][16][RGB_PITCH];   // band r in rgb[rb(r)]; with two buffers the other one receives band r+1
+    uint8_t rgb_carry[RGB_BUFS == 2 ? 2 : 1][RGB_BUFS == 2 ? RGB_PITCH : 16];   // line 15 of band r (two-buffer layout only)
     uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad): both transpositions;
                                         // 36-word block stride = conflict-free scattered stores and 128-bit loads
     uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
@@ -282,7 +290,8 @@ struct alignas(16) Smem {
     unsigned long long tex_sumabs, tex_sumsq;
     unsigned long long full_bar[2];     // mbarriers: "band has landed in rgb[b]"
     uint32_t tex_maxabs;
-    uint32_t pad_[3];
+    uint32_t next_work;                 // ticket drawn by thread 0 for the CTA's next work item
+    uint32_t pad_[2];
 };
 
 // Per work item geometry (uniform across the CTA).
@@ -303,7 +312,15 @@ struct ThreadAcc {              // per-thread state that lives across barriers (
     int col[16];                // block stage: two columns between the two halves of the column sub-stage
 };
 
-V5_DEV int ring16(int r, int l) { return (16 * (r & 1) + l) & (RING - 1); }   // yorig line; l in [-2, 15]
+V5_DEV int rb(int r) { return RGB_BUFS == 2 ? (r & 1) : 0; }           // RGB buffer / mbarrier of band r
+V5_DEV int ring16(int r, int l)                                        // yorig line; l in [-2, 15]
+{
+    if (RING == 32) return (16 * (r & 1) + l) & 31;
+    int i = 16 * (r % 3) + l;                                           // 16r mod 24 cycles 0,16,8
+    i = i >= RING ? i - RING : i;
+    i = i >= RING ? i - RING : i;
+    return i < 0 ? i + RING : i;
+}
 V5_DEV int ringd(int r, int l)                                         // ydec line; l in [-1, 15]
 {
     int i = 16 * (r % 3) + l;                                           // 16r mod 24 cycles 0,16,8
@@ -343,12 +360,12 @@ V5_DEV void stage_prefetch(int tid, Smem &S, const KParams &p, const Geo &g, int
 {
     if (tid >= 16) return;
     const LoadGeo L = load_geo(p, g);
-    unsigned long long *bar = &S.full_bar[r & 1];
+    unsigned long long *bar = &S.full_bar[rb(r)];
     async_proxy_fence();                                        // earlier generic accesses to this buffer are done
     if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
     int y = 16 * r + tid;
     if (y > p.h - 1) y = p.h - 1;
-    bulk_g2s(&S.rgb[r & 1][tid][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
+    bulk_g2s(&S.rgb[rb(r)][tid][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
              reinterpret_cast<uint64_t *>(bar));
 }
 
@@ -362,7 +379,7 @@ V5_DEV bool load_rest_needed(const KParams &p, const Geo &g, bool bulk)
 V5_DEV void stage_load_rest(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool bulk)
 {
     const LoadGeo L = load_geo(p, g);
-    uint8_t(*dst)[RGB_PITCH] = S.rgb[r & 1];
+    uint8_t(*dst)[RGB_PITCH] = S.rgb[rb(r)];
     const int warp = tid >> 5, lane = tid & 31;
     int done = bulk ? L.nbulk : 0;
     if (done == L.nbytes && L.npad3 <= 0) return;
@@ -453,9 +470,10 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
     const int last_cline = ((p.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
     const int last_line = p.h - 1 - 16 * r;                     // local index of the last real pixel line
-    const uint8_t(*src)[RGB_PITCH] = S.rgb[r & 1];
-    for (int i = tid; i < RGB_PITCH / 16; i += NT)              // keep line 15 for the next iteration's residual stage
-        reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
+    const uint8_t(*src)[RGB_PITCH] = S.rgb[rb(r)];
+    if (RGB_BUFS == 2)
+        for (int i = tid; i < RGB_PITCH / 16; i += NT)          // keep line 15 for the next iteration's residual stage
+            reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
     for (int u = tid; u < 8 * 2 * BAND_MCUS; u += NT) {          // unit = 2 lines x 8 px
         const int li = u / (2 * BAND_MCUS), ox = u - li * (2 * BAND_MCUS);
         const int mcu = g.m0 - 1 + (ox >> 1);
@@ -740,13 +758,36 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
     // (Y << 16) + 32768 straight from the packed luma word, the multiply-adds do the rest.
     const U2 yd = *reinterpret_cast<const U2 *>(&S.ydec[ringd(r, l)][col]);
-    const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[r & 1][l][3 * col];
     const uint32_t ydw[2] = {yd.x, yd.y};
     uint32_t ow[6], dw[6];
+    if (RGB_BUFS == 2) {
+        const uint8_t *orig = l < 0 ? &S.rgb_carry[(r - 1) & 1][3 * col] : &S.rgb[r & 1][l][3 * col];
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const U2 t = reinterpret_cast<const U2 *>(orig)[i];
-        ow[2 * i] = t.x; ow[2 * i + 1] = t.y;
+        for (int i = 0; i < 3; i++) {
+            const U2 t = reinterpret_cast<const U2 *>(orig)[i];
+            ow[2 * i] = t.x; ow[2 * i + 1] = t.y;
+        }
+    } else {
+        // single-buffer layout: the band's RGB is gone from shared memory by now; these 24 bytes were fetched through L2
+        // one iteration ago. A unit cut by the image edge (or an unaligned frame) must not read past its row.
+        const uint8_t *orig = g.frame + (int64_t)y * p.row_stride + 3 * gx0;
+        if (p.vec_ok && nvalid >= 8) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const U2 t = reinterpret_cast<const U2 *>(orig)[i];
+                ow[2 * i] = t.x; ow[2 * i + 1] = t.y;
+            }
+        } else {
+            const int nb = nvalid >= 8 ? 24 : 3 * nvalid;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * i + b < nb) w |= (uint32_t)orig[4 * i + b] << (8 * b);
+                ow[i] = w;
+            }
+        }
     }
     int rec[24];
 #pragma unroll

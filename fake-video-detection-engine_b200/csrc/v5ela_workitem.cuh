@@ -140,13 +140,17 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             }
             // every thread waits for the bulk copy itself, so no CTA barrier is needed before the conversion
             V5_FOR_THREADS({
-                if (bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
+                if (RGB_BUFS == 2 && bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
                 if (bulk) {
-                    mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[r & 1]), (acc.phase >> (r & 1)) & 1u);
-                    acc.phase ^= 1u << (r & 1);
+                    mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[rb(r)]), (acc.phase >> rb(r)) & 1u);
+                    acc.phase ^= 1u << rb(r);
                 }
                 stage_convert(tid, S, p, g, r);
             })
+            // single staging buffer: band r has been consumed by every warp (barrier above), fetch band r+1 over it now
+            if (RGB_BUFS == 1 && bulk && next_band) {
+                V5_FOR_WARP(stage_prefetch(tid, S, p, g, r + 1))
+            }
             const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
             for (int round = 0; round < rounds; round++) {
                 V5_BLOCK_TASK(t)

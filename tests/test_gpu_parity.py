@@ -220,3 +220,38 @@ def test_error_codes_do_not_raise_cuda_faults():
     h.analyze(t.data_ptr(), 1, 16, 16, 768, 48, r.data_ptr(), None, None)
     torch.cuda.synchronize()
     h.close()
+
+
+def test_8k_frame_and_empty_batch():
+    """Maximum-size style input (7680x4320, 99.5 MB) and the empty batch."""
+    import torch
+    import v5ela
+
+    frame = gen_frame(2, 4320, 7680, 1)
+    out = run_gpu(frame[None], 90)
+    o = c_oracle.analyze_frame(frame, 90)
+    assert np.array_equal(out["residual"][0], o["residual"])
+    assert out["records"][0].tobytes() == o["record"].tobytes()
+    empty = v5ela.analyze_batch(torch.empty((0, 64, 64, 3), dtype=torch.uint8, device="cuda"), want_residual=True)
+    assert empty["records"].shape == (0, 3144) and empty["residual"].shape == (0, 64, 64, 3)
+
+
+def test_many_small_frames_dynamic_tickets():
+    """More work items than resident CTAs, of unequal size (ragged strips and segments): every item is done exactly once."""
+    frames = gen_batch(0, 700, 40, 1000, seed=2)                 # 700 frames x 3 strips (21+21+21 MCUs, ragged edge)
+    out = run_gpu(frames, 90)
+    recs, resid = c_oracle.analyze(frames, 90, want_residual=True)
+    assert np.array_equal(out["residual"], resid)
+    assert out["records"].tobytes() == recs.tobytes()
+
+
+def test_repeated_calls_are_deterministic():
+    import torch
+    import v5ela
+
+    t = gen_batch_torch(0, 8, 360, 640, seed=9)
+    a = v5ela.analyze_batch(t)["records"].clone()
+    for _ in range(5):
+        b = v5ela.analyze_batch(t)["records"]
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)

@@ -16,15 +16,17 @@ from v5ela.synth import gen_frame
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module")
-def emu():
-    so = os.path.join(HERE, "emu", "libv5ela_emu.so")
+@pytest.fixture(scope="module", params=["2cta", "3cta"])
+def emu(request):
+    """The default layout (2 CTAs/SM, double-buffered RGB) and the -DV5_MIN_CTAS=3 single-buffer layout."""
+    variant = request.param
+    so = os.path.join(HERE, "emu", f"libv5ela_emu_{variant}.so")
     src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
     csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "include"),
-                               "-I", csrc, src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}",
+                               "-I", os.path.join(ROOT, "include"), "-I", csrc, src, "-o", so])
     lib = ctypes.CDLL(so)
     u8p = ctypes.POINTER(ctypes.c_uint8)
     lib.v5emu_analyze.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,

@@ -25,6 +25,10 @@ import subprocess
 import sys
 import time
 
+# stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "fake-video-detection-engine_b200")
 for _p in (ROOT, PKG):

@@ -163,6 +163,7 @@ struct v5ela_handle {
     // spectrum path (v5ela_fft.cuh): twiddle tables for the last (width, height), DFT workspace
     double2 *tw_w = nullptr, *tw_h = nullptr;
     int tw_w_n = 0, tw_h_n = 0;
+    bool fft_attr_set = false;
     size_t tw_w_cap = 0, tw_h_cap = 0;
     void *d_g = nullptr, *d_ms = nullptr, *d_minmax = nullptr;
     size_t d_g_cap = 0, d_ms_cap = 0, d_minmax_cap = 0;
@@ -468,19 +469,45 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
     if ((rc = ensure(h, &h->d_ms, &h->d_ms_cap, per_frame * 8 * chunk))) return rc;
     if ((rc = ensure(h, &h->d_minmax, &h->d_minmax_cap, sizeof(unsigned long long) * 2 * (size_t)chunk))) return rc;
     const dim3 grid((wh + v5fft::TILE - 1) / v5fft::TILE, (height + v5fft::TILE - 1) / v5fft::TILE, 1);
+    // Sizes with only 2/3/5 as prime factors take the shared-memory FFT; anything else (crops are arbitrary) the exact-size
+    // DFT products. V5ELA_FFT=0 forces the latter (tests compare the two).
+    v5fft::FftPlan plan_w, plan_h;
+    const char *fft_env = getenv("V5ELA_FFT");
+    const size_t rows_smem = sizeof(double2) * 2 * (size_t)width;
+    int cc = (int)((size_t)(96u << 10) / (sizeof(double2) * 2 * (size_t)height));
+    cc = cc > 4 ? 4 : cc;
+    const size_t cols_smem = sizeof(double2) * 2 * (size_t)(cc > 0 ? cc : 1) * (size_t)height;
+    const bool fast = !(fft_env && atoi(fft_env) == 0) && v5fft::make_plan(width, plan_w) && v5fft::make_plan(height, plan_h) &&
+                      cc >= 1 && rows_smem <= (200u << 10) && cols_smem <= (200u << 10) && n <= 65535;
+    if (fast && !h->fft_attr_set) {
+        V5_CUDA(h, cudaFuncSetAttribute(v5fft::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        V5_CUDA(h, cudaFuncSetAttribute(v5fft::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        h->fft_attr_set = true;
+    }
     for (int f0 = 0; f0 < n; f0 += chunk) {
         const int fn = f0 + chunk <= n ? chunk : n - f0;
         // min/max slots: {~0, 0} per frame
         V5_CUDA(h, cudaMemsetAsync(h->d_minmax, 0, sizeof(unsigned long long) * 2 * (size_t)fn, st));
         V5_CUDA(h, cudaMemset2DAsync(h->d_minmax, 16, 0xff, 8, (size_t)fn, st));
-        dim3 gr = grid;
-        gr.z = (unsigned)fn;
-        v5fft::dft_rows_kernel<<<gr, 256, 0, st>>>(d_gray + (int64_t)f0 * frame_stride_bytes, frame_stride_bytes, row_stride_bytes,
-                                                   height, width, wh, h->tw_w, static_cast<double2 *>(h->d_g));
-        V5_CUDA(h, cudaGetLastError());
-        v5fft::dft_cols_kernel<<<gr, 256, 0, st>>>(static_cast<const double2 *>(h->d_g), height, wh, h->tw_h,
-                                                   static_cast<double *>(h->d_ms), static_cast<unsigned long long *>(h->d_minmax));
-        V5_CUDA(h, cudaGetLastError());
+        if (fast) {
+            v5fft::fft_rows_kernel<<<dim3((unsigned)((height + 1) / 2), (unsigned)fn), 256, rows_smem, st>>>(
+                d_gray + (int64_t)f0 * frame_stride_bytes, frame_stride_bytes, row_stride_bytes, height, width, wh, plan_w, h->tw_w,
+                static_cast<double2 *>(h->d_g));
+            V5_CUDA(h, cudaGetLastError());
+            v5fft::fft_cols_kernel<<<dim3((unsigned)((wh + cc - 1) / cc), (unsigned)fn), 256, cols_smem, st>>>(
+                static_cast<const double2 *>(h->d_g), height, wh, cc, plan_h, h->tw_h, static_cast<double *>(h->d_ms),
+                static_cast<unsigned long long *>(h->d_minmax));
+            V5_CUDA(h, cudaGetLastError());
+        } else {
+            dim3 gr = grid;
+            gr.z = (unsigned)fn;
+            v5fft::dft_rows_kernel<<<gr, 256, 0, st>>>(d_gray + (int64_t)f0 * frame_stride_bytes, frame_stride_bytes, row_stride_bytes,
+                                                       height, width, wh, h->tw_w, static_cast<double2 *>(h->d_g));
+            V5_CUDA(h, cudaGetLastError());
+            v5fft::dft_cols_kernel<<<gr, 256, 0, st>>>(static_cast<const double2 *>(h->d_g), height, wh, h->tw_h,
+                                                       static_cast<double *>(h->d_ms), static_cast<unsigned long long *>(h->d_minmax));
+            V5_CUDA(h, cudaGetLastError());
+        }
         long long bx = ((long long)height * width + 255) / 256;
         if (bx > 8LL * h->sm_count) bx = 8LL * h->sm_count;
         v5fft::spectrum_image_kernel<<<dim3((unsigned)bx, 1, (unsigned)fn), 256, 0, st>>>(

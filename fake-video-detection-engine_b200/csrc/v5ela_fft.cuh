@@ -127,6 +127,151 @@ __global__ void __launch_bounds__(256) dft_cols_kernel(const double2 *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for sizes whose prime factors are all in {2, 3, 5} (every common video size): mixed-radix Stockham
+// autosort FFT in shared memory, float64. One stage of radix r over a sequence of current length n and stride s
+// (n * s == N): for p in [0, n/r), q in [0, s):
+//     a_t = x[q + s*(p + t*n/r)],  b_u = (sum_t a_t w_r^{t u}) * exp(-2 pi i p u s / N),  y[q + s*(r*p + u)] = b_u
+// then n /= r, s *= r and the buffers swap. p*u*s < N, so the twiddle is a direct index into the N-entry table.
+struct FftPlan {
+    int n;
+    int nst;
+    int radix[24];
+};
+
+// Host: factor n into 5s, 3s and 2s; returns false when another prime factor remains.
+inline bool make_plan(int n, FftPlan &plan)
+{
+    plan.n = n;
+    plan.nst = 0;
+    const int rs[3] = {5, 3, 2};
+    for (int r : rs)
+        while (n % r == 0 && plan.nst < 24) {
+            plan.radix[plan.nst++] = r;
+            n /= r;
+        }
+    return n == 1;
+}
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 mul_neg_i(double2 a) { return make_double2(a.y, -a.x); }   // -i * a
+
+// All stages of `nseq` sequences of length plan.n stored one after the other in x (work buffer y). Returns the buffer
+// that holds the result. Must be called by every thread of the CTA.
+__device__ double2 *stockham(double2 *x, double2 *y, int nseq, const FftPlan &plan, const double2 *__restrict__ tw)
+{
+    const int N = plan.n;
+    int n = N, s = 1;
+    for (int st = 0; st < plan.nst; st++) {
+        const int r = plan.radix[st], m = n / r, per_seq = N / r;
+        for (int wi = threadIdx.x; wi < nseq * per_seq; wi += blockDim.x) {
+            const int seq = wi / per_seq, idx = wi - seq * per_seq;
+            const int p = idx / s, q = idx - p * s;
+            const double2 *xi = x + seq * N + q + s * p;
+            double2 *yo = y + seq * N + q + s * r * p;
+            const int ms_ = s * m;                              // input stride between the r operands
+            if (r == 2) {
+                const double2 a0 = xi[0], a1 = xi[ms_];
+                yo[0] = cadd(a0, a1);
+                yo[s] = cmul(csub(a0, a1), tw[p * s]);
+            } else if (r == 3) {
+                const double2 a0 = xi[0], a1 = xi[ms_], a2 = xi[2 * ms_];
+                const double2 t1 = cadd(a1, a2);
+                const double2 t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
+                const double2 d = csub(a1, a2);
+                const double2 e = mul_neg_i(make_double2(0.86602540378443864676 * d.x, 0.86602540378443864676 * d.y));
+                yo[0] = cadd(a0, t1);
+                yo[s] = cmul(cadd(t2, e), tw[p * s]);
+                yo[2 * s] = cmul(csub(t2, e), tw[2 * p * s]);
+            } else {                                            // r == 5
+                const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+                const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+                const double2 a0 = xi[0], a1 = xi[ms_], a2 = xi[2 * ms_], a3 = xi[3 * ms_], a4 = xi[4 * ms_];
+                const double2 t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+                const double2 m1 = make_double2(a0.x + c1 * t1.x + c2 * t2.x, a0.y + c1 * t1.y + c2 * t2.y);
+                const double2 m2 = make_double2(a0.x + c2 * t1.x + c1 * t2.x, a0.y + c2 * t1.y + c1 * t2.y);
+                const double2 n1 = mul_neg_i(make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+                const double2 n2 = mul_neg_i(make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+                yo[0] = make_double2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
+                yo[s] = cmul(cadd(m1, n1), tw[p * s]);
+                yo[2 * s] = cmul(cadd(m2, n2), tw[2 * p * s]);
+                yo[3 * s] = cmul(csub(m2, n2), tw[3 * p * s]);
+                yo[4 * s] = cmul(csub(m1, n1), tw[4 * p * s]);
+            }
+        }
+        __syncthreads();
+        double2 *t = x;
+        x = y;
+        y = t;
+        n = m;
+        s *= r;
+    }
+    return x;
+}
+
+// Rows: two real rows ride in one complex transform (z = a + i b); the half spectra of both are separated with
+// A_k = (Z_k + conj(Z_{N-k}))/2, B_k = (Z_k - conj(Z_{N-k}))/(2i).
+__global__ void __launch_bounds__(256) fft_rows_kernel(const uint8_t *__restrict__ gray, int64_t frame_stride, int64_t row_stride,
+                                                       int h, int w, int wh, const __grid_constant__ FftPlan plan,
+                                                       const double2 *__restrict__ tw, double2 *__restrict__ g)
+{
+    extern __shared__ double2 fbuf[];
+    const int y0 = 2 * blockIdx.x, y1 = y0 + 1;
+    const uint8_t *src = gray + (int64_t)blockIdx.y * frame_stride;
+    for (int x = threadIdx.x; x < w; x += blockDim.x)
+        fbuf[x] = make_double2((double)src[(int64_t)y0 * row_stride + x], y1 < h ? (double)src[(int64_t)y1 * row_stride + x] : 0.0);
+    __syncthreads();
+    const double2 *res = stockham(fbuf, fbuf + w, 1, plan, tw);
+    double2 *ga = g + ((int64_t)blockIdx.y * h + y0) * wh;
+    for (int k = threadIdx.x; k < wh; k += blockDim.x) {
+        const double2 zk = res[k], zn = res[k == 0 ? 0 : w - k];
+        ga[k] = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+        if (y1 < h) ga[wh + k] = make_double2(0.5 * (zk.y + zn.y), 0.5 * (zn.x - zk.x));
+    }
+}
+
+// Columns: `cc` adjacent columns per CTA (cc * 16 contiguous bytes per row), transform, then |F|, 20 ln(|F|+1), min/max.
+__global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict__ g, int h, int wh, int cc,
+                                                       const __grid_constant__ FftPlan plan, const double2 *__restrict__ tw,
+                                                       double *__restrict__ ms, unsigned long long *__restrict__ minmax)
+{
+    extern __shared__ double2 fbuf[];
+    __shared__ unsigned long long smin, smax;
+    if (threadIdx.x == 0) { smin = ~0ull; smax = 0ull; }
+    const int v0 = blockIdx.x * cc;
+    const double2 *src = g + (int64_t)blockIdx.y * h * wh;
+    for (int i = threadIdx.x; i < h * cc; i += blockDim.x) {
+        const int y = i / cc, c = i - y * cc;
+        fbuf[c * h + y] = v0 + c < wh ? src[(int64_t)y * wh + v0 + c] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const double2 *res = stockham(fbuf, fbuf + cc * h, cc, plan, tw);
+    double *dst = ms + (int64_t)blockIdx.y * h * wh;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int i = threadIdx.x; i < h * cc; i += blockDim.x) {
+        const int u = i / cc, c = i - u * cc;
+        if (v0 + c >= wh) continue;
+        const double2 f = res[c * h + u];
+        const double m = 20.0 * log(hypot(f.x, f.y) + 1.0);
+        dst[(int64_t)u * wh + v0 + c] = m;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+        lo = bits < lo ? bits : lo;
+        hi = bits > hi ? bits : hi;
+    }
+    atomicMin(&smin, lo);
+    atomicMax(&smax, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMin(&minmax[2 * blockIdx.y], smin);
+        atomicMax(&minmax[2 * blockIdx.y + 1], smax);
+    }
+}
+
 // out[i][j] = u8(rint(ms_shifted[i][j] * scale + shift)), cv2.normalize(NORM_MINMAX, 0..255) + np.fft.fftshift
 __global__ void __launch_bounds__(256) spectrum_image_kernel(const double *__restrict__ ms, const unsigned long long *__restrict__ minmax,
                                                              int h, int w, int wh, uint8_t *__restrict__ out)

@@ -15,5 +15,6 @@ for (n, h, w) in [(64, 257, 301), (16, 720, 1280), (8, 1080, 1920)]:
     ms = e0.elapsed_time(e1) / 3
     t0 = time.perf_counter(); ref = pil_oracle.fft_spectrum(g[0].cpu().numpy()); cpu = time.perf_counter() - t0
     d = np.abs(out[0].cpu().numpy().astype(np.int16) - ref.astype(np.int16))
-    gflop = n * (2.0 * h * w * (w // 2 + 1) * 2 + 8.0 * h * h * (w // 2 + 1)) / 1e9
-    print(f"{n} x {w}x{h}: {ms:8.3f} ms/batch = {n / ms * 1e3:9,.0f} images/s ({gflop / ms:6.1f} GFLOP/ms f64)  numpy 1 thread {1 / cpu:6.1f} images/s  max diff {d.max()}  exact {float((d == 0).mean()) * 100:.4f}%")
+    wh = w // 2 + 1
+    gbs = n * (h * w * 2 + h * wh * (16 * 2 + 8 * 2)) / ms / 1e6       # gray in, image out, G written+read, ms written+read
+    print(f"{n} x {w}x{h}: {ms:8.3f} ms/batch = {n / ms * 1e3:9,.0f} images/s ({gbs:6.1f} GB/s of intermediate+io traffic)  numpy 1 thread {1 / cpu:6.1f} images/s  max diff {d.max()}  exact {float((d == 0).mean()) * 100:.4f}%")

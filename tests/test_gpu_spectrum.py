@@ -72,3 +72,21 @@ def test_720p_luma_batch():
         ref = pil_oracle.fft_spectrum(frames[i])
         d = np.abs(out[i].astype(np.int16) - ref.astype(np.int16))
         assert int(d.max()) <= 1 and float((d == 0).mean()) > 0.999
+
+
+@pytest.mark.parametrize("hw", [(1080, 1920), (360, 640), (150, 90), (45, 2), (1, 30), (486, 250)])
+def test_fft_path_equals_dft_path_within_one_level(hw):
+    """Sizes made of 2, 3 and 5 take the shared-memory Stockham FFT; V5ELA_FFT=0 forces the exact-size DFT products."""
+    h, w = hw
+    rng = np.random.default_rng(h + w)
+    gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    fast = gpu_spectrum(gray)
+    os.environ["V5ELA_FFT"] = "0"
+    try:
+        slow = gpu_spectrum(gray)
+    finally:
+        del os.environ["V5ELA_FFT"]
+    d = np.abs(fast.astype(np.int16) - slow.astype(np.int16))
+    assert int(d.max()) <= 1 and float((d == 0).mean()) > 0.999
+    if h * w <= 640 * 360:
+        check(gray)

@@ -244,16 +244,7 @@ inline uint32_t packsat2(int a, int b, uint32_t c)
 }
 #endif
 // four ints -> bytes [v0, v1, v2, v3], each clamped to 0..255: two I2IP
-#ifndef V5_NO_I2IP
 V5_DEV uint32_t pack4sat(int v0, int v1, int v2, int v3) { return packsat2(v1, v0, packsat2(v3, v2, 0u)); }
-#else
-V5_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel);
-V5_DEV uint32_t pack4sat(int v0, int v1, int v2, int v3)
-{
-    const uint32_t a = (uint32_t)clamp255(v0), b = (uint32_t)clamp255(v1), c = (uint32_t)clamp255(v2), d = (uint32_t)clamp255(v3);
-    return prmt(prmt(a, b, 0x0040u), prmt(c, d, 0x0040u), 0x5410u);
-}
-#endif
 
 // byte k (compile-time) of w, zero-extended: one PRMT
 V5_DEV uint32_t byte_of(uint32_t w, int k) { return prmt(w, 0u, 0x4440u + (uint32_t)k); }

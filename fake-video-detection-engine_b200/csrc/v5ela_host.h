@@ -38,6 +38,7 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
     if (row_stride < (int64_t)3 * w || (n > 1 && frame_stride < row_stride * (int64_t)h)) return -1;
     if (quality < 1 || quality > 100) return -1;
     if ((int64_t)h > 65536 || (int64_t)w > 65536) return -1;
+    if ((int64_t)h * w > 0x7fffffffLL) return -1;             // per-frame histogram counters are 32-bit
     memset(&p, 0, sizeof(p));
     p.rgb = rgb;
     p.frame_stride = frame_stride;

@@ -183,6 +183,15 @@ def load_ncu_traffic():
         return None
 
 
+def load_issue_stats():
+    """ncu-measured issue-slot figures of the fused kernel (the resource that actually binds it), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_kernel_issue.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def load_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -318,7 +327,9 @@ def run_native_arm(args):
                          "traffic": load_ncu_traffic(), "kernel": "v5::ela_fused_kernel", "kernel_ms": kernel_ms,
                          "kernel_launches_timed": int(fused_n), "bytes_per_launch": n_local * BYTES_PER_FRAME,
                          "peak_source": peak_src,
-                         "note": "integer-issue bound, not HBM bound: ~100 exact int32 instructions per pixel (DESIGN.md)"},
+                         "note": "integer-issue bound, not HBM bound: ~138 exact int32 thread-instructions per pixel "
+                                 "(DESIGN.md 4.4); int_issue = ncu figures of the committed profile",
+                         "int_issue": load_issue_stats()},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

@@ -141,70 +141,8 @@ __global__ void __launch_bounds__(256) ela_reduce_kernel(const v5ela_record *rec
 }  // namespace v5
 
 // ======================================================================================================= C ABI
-struct v5ela_handle {
-    int device = 0;
-    int quality = 90;
-    int sm_count = 0;
-    int seg_rows = 0;                      // 0 = default
-    int ctas_per_sm = v5::MIN_CTAS;
-    int64_t launches = 0;
-    cudaStream_t own_stream = nullptr;     // v5ela_analyze_host with a NULL stream
-    cudaStream_t copy_stream = nullptr, work_stream = nullptr;   // chunk pipeline of v5ela_analyze_host
-    cudaEvent_t ev_fork = nullptr, ev_join_copy = nullptr, ev_join_work = nullptr;
-    std::vector<cudaEvent_t> ev_chunk;     // "chunk c has landed" events
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;  // pairs (start, stop) around the fused kernel
-    size_t prof_used = 0;
-    int host_chunk_frames = 0;             // 0 = auto
-    uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
-    void *d_rec = nullptr;
-    unsigned int *d_ticket = nullptr;
-    size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
-    // spectrum path (v5ela_fft.cuh): twiddle tables for the last (width, height), DFT workspace
-    double2 *tw_w = nullptr, *tw_h = nullptr;
-    int tw_w_n = 0, tw_h_n = 0;
-    bool fft_attr_set = false;
-    size_t tw_w_cap = 0, tw_h_cap = 0;
-    void *d_g = nullptr, *d_ms = nullptr, *d_minmax = nullptr;
-    size_t d_g_cap = 0, d_ms_cap = 0, d_minmax_cap = 0;
-    uint8_t *d_gray = nullptr, *d_spec = nullptr;
-    size_t d_gray_cap = 0, d_spec_cap = 0;
-    uint16_t luma[64], chroma[64];
-    char err[512] = {0};
-};
-
-namespace {
-
-int fail(v5ela_handle *h, int code, const char *fmt, const char *detail = "")
-{
-    if (h) snprintf(h->err, sizeof(h->err), fmt, detail);
-    return code;
-}
-
-#define V5_CUDA(h, call)                                                                    \
-    do {                                                                                    \
-        cudaError_t e_ = (call);                                                            \
-        if (e_ != cudaSuccess) return fail((h), V5ELA_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-int ensure(v5ela_handle *h, void **ptr, size_t *cap, size_t need)
-{
-    if (*cap >= need) return 0;
-    if (*ptr) cudaFree(*ptr);
-    *ptr = nullptr;
-    *cap = 0;
-    V5_CUDA(h, cudaMalloc(ptr, need));
-    *cap = need;
-    return 0;
-}
-
-}  // namespace
+#include "v5ela_handle.h"
+using namespace v5host;
 
 extern "C" {
 
@@ -219,6 +157,7 @@ const char *v5ela_status_string(int status)
         case V5ELA_ERR_CUDA: return "CUDA error";
         case V5ELA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
         case V5ELA_ERR_NOMEM: return "out of memory";
+        case V5ELA_ERR_UNSUPPORTED: return "unsupported JPEG flavour";
         default: return "unknown status";
     }
 }
@@ -276,6 +215,7 @@ int v5ela_destroy(v5ela_handle *h)
     cudaFree(h->d_minmax);
     cudaFree(h->d_gray);
     cudaFree(h->d_spec);
+    v5jpeg_release(h);
     delete h;
     return V5ELA_OK;
 }

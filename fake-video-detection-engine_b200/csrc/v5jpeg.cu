@@ -1,0 +1,458 @@
+// v5jpeg.cu — codec rows of libv5ela.so (SURVEY.md §8f-2 decode, §8f-3 encode): C-ABI entry points v5ela_jpeg_*.
+// Kernels: v5jpeg_enc.cuh, v5jpeg_dec.cuh. Host-side header writing / parsing: v5jpeg_common.h.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "v5ela.h"
+#include "v5ela_handle.h"
+#include "v5ela_host.h"
+#include "v5jpeg_common.h"
+#include "v5jpeg_enc.cuh"
+#include "v5jpeg_dec.cuh"
+
+using namespace v5host;
+
+struct v5jpeg_state {
+    // encoder
+    v5j::EncTables *d_enc_tabs = nullptr;
+    uint8_t *d_header = nullptr;
+    void *d_coef = nullptr, *d_bitoff = nullptr, *d_total = nullptr, *d_raw = nullptr;
+    size_t coef_cap = 0, bitoff_cap = 0, total_cap = 0, raw_cap = 0;
+    // host-buffer entry points
+    uint8_t *d_img = nullptr, *d_out = nullptr;
+    int32_t *d_sizes = nullptr;
+    size_t img_cap = 0, out_cap = 0, sizes_cap = 0;
+    // decoder: one pinned staging buffer (descriptors | table sets | quantisation tables | scan segments) mirrored on the
+    // device, plus the per-batch workspace (unstuffed streams, coefficients, sample planes)
+    uint8_t *stage_host = nullptr, *d_stage = nullptr;
+    size_t stage_host_cap = 0, stage_cap = 0;
+    cudaEvent_t stage_free = nullptr;          // the last upload from stage_host has completed
+    void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr;
+    size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0;
+    uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
+    size_t dec_rgb_cap = 0, dec_gray_cap = 0;
+};
+
+void v5jpeg_release(v5ela_handle *h)
+{
+    v5jpeg_state *s = h->jpeg;
+    if (!s) return;
+    cudaFree(s->d_enc_tabs);
+    cudaFree(s->d_header);
+    cudaFree(s->d_coef);
+    cudaFree(s->d_bitoff);
+    cudaFree(s->d_total);
+    cudaFree(s->d_raw);
+    cudaFree(s->d_img);
+    cudaFree(s->d_out);
+    cudaFree(s->d_sizes);
+    if (s->stage_host) cudaFreeHost(s->stage_host);
+    if (s->stage_free) cudaEventDestroy(s->stage_free);
+    cudaFree(s->d_stage);
+    cudaFree(s->d_streams);
+    cudaFree(s->d_dcoef);
+    cudaFree(s->d_planes);
+    cudaFree(s->d_bits);
+    cudaFree(s->d_status);
+    cudaFree(s->d_dec_rgb);
+    cudaFree(s->d_dec_gray);
+    delete s;
+    h->jpeg = nullptr;
+}
+
+namespace {
+
+int jpeg_state(v5ela_handle *h, v5jpeg_state **out)
+{
+    if (!h->jpeg) {
+        h->jpeg = new (std::nothrow) v5jpeg_state();
+        if (!h->jpeg) return fail(h, V5ELA_ERR_NOMEM, "v5ela_jpeg: out of host memory%s");
+    }
+    *out = h->jpeg;
+    return 0;
+}
+
+constexpr int kHeaderMax = 1024;
+
+}  // namespace
+
+extern "C" {
+
+int64_t v5ela_jpeg_bound(int height, int width, int channels)
+{
+    if (height <= 0 || width <= 0 || (channels != 1 && channels != 3)) return V5ELA_ERR_INVALID;
+    // worst case per block: DC 9 + 11 bits, 63 x (16 + 10) bits, every byte stuffed
+    return (int64_t)v5j::enc_geo(height, width, channels).blocks * 416 + kHeaderMax;
+}
+
+int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, int width, int channels,
+                      int64_t frame_stride_bytes, int64_t row_stride_bytes, int quality, uint8_t *d_out,
+                      int64_t out_stride_bytes, int32_t *d_sizes, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!d_img || !d_out || !d_sizes || n < 0 || height <= 0 || width <= 0 || height > 65535 || width > 65535 ||
+        (channels != 1 && channels != 3) || quality < 1 || quality > 100 || row_stride_bytes < (int64_t)width * channels ||
+        (n > 1 && frame_stride_bytes < row_stride_bytes * (int64_t)height) || out_stride_bytes < kHeaderMax ||
+        out_stride_bytes > (int64_t)1 << 30)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_encode: bad pointer, size, stride, channel count or quality%s");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    v5jpeg_state *s;
+    int rc;
+    if ((rc = jpeg_state(h, &s))) return rc;
+
+    const v5j::EncGeo g = v5j::enc_geo(height, width, channels);
+    uint16_t ql[64], qc[64];
+    v5::quant_tables(quality, ql, qc);
+    const std::vector<uint8_t> header = v5j::file_header(height, width, channels, ql, qc);
+    if (!s->d_enc_tabs) {
+        v5j::EncTables tabs;
+        v5j::standard_enc_tables(tabs);
+        V5_CUDA(h, cudaMalloc(&s->d_enc_tabs, sizeof(tabs)));
+        V5_CUDA(h, cudaMemcpyAsync(s->d_enc_tabs, &tabs, sizeof(tabs), cudaMemcpyHostToDevice, st));
+        V5_CUDA(h, cudaMalloc(&s->d_header, kHeaderMax));
+    }
+    V5_CUDA(h, cudaMemcpyAsync(s->d_header, header.data(), header.size(), cudaMemcpyHostToDevice, st));
+
+    // images per pass: keep the workspace (coefficients 128 B/block, offsets, unstuffed stream) under ~1 GiB
+    const int64_t raw_words = (out_stride_bytes + 3) / 4;
+    const size_t per_image = (size_t)g.blocks * (128 + 4) + (size_t)raw_words * 4 + 16;
+    int chunk = (int)((size_t)(1u << 30) / per_image);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    if (chunk > 65535) chunk = 65535;
+    if ((rc = ensure(h, &s->d_coef, &s->coef_cap, (size_t)chunk * g.blocks * 128))) return rc;
+    if ((rc = ensure(h, &s->d_bitoff, &s->bitoff_cap, (size_t)chunk * g.blocks * 4))) return rc;
+    if ((rc = ensure(h, &s->d_total, &s->total_cap, (size_t)chunk * 4))) return rc;
+    if ((rc = ensure(h, &s->d_raw, &s->raw_cap, (size_t)chunk * raw_words * 4))) return rc;
+
+    v5j::CoefParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.frame_stride = frame_stride_bytes;
+    cp.row_stride = row_stride_bytes;
+    cp.coef = static_cast<int16_t *>(s->d_coef);
+    cp.g = g;
+    v5j::make_enc_quant(ql, cp.q[0]);
+    v5j::make_enc_quant(qc, cp.q[1]);
+    const int per_strip = channels == 3 ? v5j::ENC_TM : v5j::ENC_BLOCKS;
+    const unsigned tiles_x = (unsigned)((g.mcux + per_strip - 1) / per_strip);
+
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int fn = f0 + chunk <= n ? chunk : n - f0;
+        cp.img = d_img + (int64_t)f0 * frame_stride_bytes;
+        v5j::coef_kernel<<<dim3(tiles_x, (unsigned)g.mcuy, (unsigned)fn), v5j::ENC_NT, 0, st>>>(cp);
+        V5_CUDA(h, cudaGetLastError());
+        v5j::EntropyParams ep;
+        ep.coef = cp.coef;
+        ep.bitoff = static_cast<uint32_t *>(s->d_bitoff);
+        ep.total_bits = static_cast<uint32_t *>(s->d_total);
+        ep.raw = static_cast<uint32_t *>(s->d_raw);
+        ep.raw_words = raw_words;
+        ep.blocks = g.blocks;
+        ep.bpm = g.bpm;
+        ep.n = fn;
+        const dim3 eg((unsigned)((g.blocks + 127) / 128), (unsigned)fn);
+        v5j::entropy_kernel<false><<<eg, 128, 0, st>>>(ep, s->d_enc_tabs);
+        V5_CUDA(h, cudaGetLastError());
+        v5j::scan_kernel<<<fn, 1024, 0, st>>>(ep);
+        V5_CUDA(h, cudaGetLastError());
+        V5_CUDA(h, cudaMemsetAsync(s->d_raw, 0, (size_t)fn * raw_words * 4, st));
+        v5j::entropy_kernel<true><<<eg, 128, 0, st>>>(ep, s->d_enc_tabs);
+        V5_CUDA(h, cudaGetLastError());
+        v5j::StuffParams sp;
+        sp.raw = ep.raw;
+        sp.raw_words = raw_words;
+        sp.total_bits = ep.total_bits;
+        sp.header = s->d_header;
+        sp.header_len = (int)header.size();
+        sp.out = d_out + (int64_t)f0 * out_stride_bytes;
+        sp.out_stride = out_stride_bytes;
+        sp.sizes = d_sizes + f0;
+        v5j::stuff_kernel<<<fn, 1024, 0, st>>>(sp);
+        V5_CUDA(h, cudaGetLastError());
+        h->launches += 5;
+    }
+    return V5ELA_OK;
+}
+
+int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, int n, int height, int width, int channels, int quality,
+                           uint8_t *out_host, int64_t out_stride_bytes, int32_t *sizes_host)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!img_host || !out_host || !sizes_host || n < 0 || height <= 0 || width <= 0 || (channels != 1 && channels != 3) ||
+        out_stride_bytes < kHeaderMax)
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_encode_host: bad pointer, size or channel count%s");
+    DeviceGuard guard(h->device);
+    v5jpeg_state *s;
+    int rc;
+    if ((rc = jpeg_state(h, &s))) return rc;
+    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->own_stream;
+    const size_t fbytes = (size_t)height * width * channels;
+    if ((rc = ensure(h, (void **)&s->d_img, &s->img_cap, fbytes * n))) return rc;
+    if ((rc = ensure(h, (void **)&s->d_out, &s->out_cap, (size_t)out_stride_bytes * n))) return rc;
+    if ((rc = ensure(h, (void **)&s->d_sizes, &s->sizes_cap, sizeof(int32_t) * (size_t)n))) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(s->d_img, img_host, fbytes * n, cudaMemcpyHostToDevice, st));
+    rc = v5ela_jpeg_encode(h, s->d_img, n, height, width, channels, (int64_t)fbytes, (int64_t)width * channels, quality,
+                           s->d_out, out_stride_bytes, s->d_sizes, st);
+    if (rc) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(sizes_host, s->d_sizes, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    V5_CUDA(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) {                               // only the bytes that make up each file come back
+        const int64_t sz = sizes_host[i] <= out_stride_bytes ? sizes_host[i] : 0;
+        if (sz) V5_CUDA(h, cudaMemcpyAsync(out_host + (int64_t)i * out_stride_bytes, s->d_out + (int64_t)i * out_stride_bytes,
+                                           (size_t)sz, cudaMemcpyDeviceToHost, st));
+    }
+    V5_CUDA(h, cudaStreamSynchronize(st));
+    return V5ELA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------- decode
+int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *width, int *channels)
+{
+    if (!file_host || len <= 0 || !height || !width || !channels) return V5ELA_ERR_INVALID;
+    v5j::FileInfo *F = new (std::nothrow) v5j::FileInfo();
+    if (!F) return V5ELA_ERR_NOMEM;
+    const int rc = v5j::parse_file(file_host, (size_t)len, *F);
+    if (rc == v5j::JPEG_OK) {
+        *height = F->h;
+        *width = F->w;
+        *channels = F->ncomp;
+    }
+    delete F;
+    return rc == v5j::JPEG_OK ? V5ELA_OK : (rc == v5j::JPEG_UNSUPPORTED ? V5ELA_ERR_UNSUPPORTED : V5ELA_ERR_INVALID);
+}
+
+}  // extern "C"
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DecPlan {                               // host-side description of one chunk of files
+    std::vector<v5j::DecImage> images;
+    std::vector<int> file_index;
+    size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0;
+    int max_blocks = 0;
+    int64_t max_pixels = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *d_rgb,
+                      const int64_t *rgb_offsets, uint8_t *d_gray, const int64_t *gray_offsets, int32_t *d_status,
+                      void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!files_host || !lens || n < 0 || (!d_rgb && !d_gray))
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: bad pointer or count%s");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    v5jpeg_state *s;
+    int rc;
+    if ((rc = jpeg_state(h, &s))) return rc;
+    if (!s->stage_free) V5_CUDA(h, cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+
+    // ---- parse every file; unique Huffman table sets and quantisation table pairs
+    std::vector<v5j::FileInfo> info((size_t)n);
+    std::vector<v5j::DecTabSet> tabsets;
+    std::vector<std::vector<uint16_t>> qsets;
+    std::vector<int> tab_of((size_t)n), q_of((size_t)n);
+    for (int i = 0; i < n; i++) {
+        if (!files_host[i] || lens[i] <= 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: null or empty file%s");
+        const int prc = v5j::parse_file(files_host[i], (size_t)lens[i], info[i]);
+        if (prc != v5j::JPEG_OK) {
+            char which[64];
+            snprintf(which, sizeof(which), " (file %d)", i);
+            return prc == v5j::JPEG_UNSUPPORTED
+                       ? fail(h, V5ELA_ERR_UNSUPPORTED, "v5ela_jpeg_decode: not 8-bit baseline 4:2:0 / one-component JPEG without restarts%s", which)
+                       : fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: corrupt JPEG headers%s", which);
+        }
+        v5j::DecTabSet ts;
+        ts.dc[0] = info[i].dc[0]; ts.dc[1] = info[i].dc[1]; ts.ac[0] = info[i].ac[0]; ts.ac[1] = info[i].ac[1];
+        int found = -1;
+        for (size_t k = 0; k < tabsets.size() && found < 0; k++)
+            if (!memcmp(&tabsets[k], &ts, sizeof(ts))) found = (int)k;
+        if (found < 0) { tabsets.push_back(ts); found = (int)tabsets.size() - 1; }
+        tab_of[i] = found;
+        std::vector<uint16_t> q(128);
+        memcpy(q.data(), info[i].qt[0], 128);
+        memcpy(q.data() + 64, info[i].qt[1], 128);
+        found = -1;
+        for (size_t k = 0; k < qsets.size() && found < 0; k++)
+            if (qsets[k] == q) found = (int)k;
+        if (found < 0) { qsets.push_back(q); found = (int)qsets.size() - 1; }
+        q_of[i] = found;
+    }
+
+    // ---- chunks of files whose workspace stays under ~2 GiB
+    std::vector<DecPlan> plans(1);
+    int64_t rgb_run = 0, gray_run = 0;
+    for (int i = 0; i < n; i++) {
+        const v5j::FileInfo &F = info[i];
+        v5j::DecImage im;
+        memset(&im, 0, sizeof(im));
+        im.h = F.h; im.w = F.w; im.ncomp = F.ncomp;
+        const int m = F.ncomp == 3 ? 16 : 8;
+        im.mcux = (F.w + m - 1) / m; im.mcuy = (F.h + m - 1) / m;
+        im.bpm = F.ncomp == 3 ? 6 : 1;
+        im.blocks = im.mcux * im.mcuy * im.bpm;
+        im.tabset = tab_of[i];
+        im.qt = q_of[i];
+        im.yw = im.mcux * m; im.yh = im.mcuy * m;
+        im.cw = F.ncomp == 3 ? im.yw / 2 : 0; im.ch = F.ncomp == 3 ? im.yh / 2 : 0;
+        const size_t planes = (size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch;
+        const size_t need = F.scan_len * 2 + (size_t)im.blocks * 128 + planes + 256;
+        DecPlan *P = &plans.back();
+        if (!P->images.empty() && (P->scan_bytes * 2 + P->coef_blocks * 128 + P->plane_bytes + need > ((size_t)2 << 30) || P->images.size() >= 65535)) {
+            plans.emplace_back();
+            P = &plans.back();
+        }
+        im.scan_off = (int64_t)P->scan_bytes;          // relative to the scan area of the staging buffer (fixed up below)
+        im.scan_len = (int64_t)F.scan_len;
+        im.stream_off = (int64_t)P->stream_bytes;
+        im.coef_off = (int64_t)P->coef_blocks;
+        im.plane_off = (int64_t)P->plane_bytes;
+        im.rgb_off = d_rgb ? (rgb_offsets ? rgb_offsets[i] : rgb_run) : -1;
+        im.gray_off = d_gray ? (gray_offsets ? gray_offsets[i] : gray_run) : -1;
+        rgb_run += (int64_t)F.h * F.w * 3;
+        gray_run += (int64_t)F.h * F.w;
+        P->scan_bytes += align_up(F.scan_len, 16);
+        P->stream_bytes += align_up(F.scan_len + 32, 16);
+        P->coef_blocks += (size_t)im.blocks;
+        P->plane_bytes += align_up(planes, 16);
+        if (im.blocks > P->max_blocks) P->max_blocks = im.blocks;
+        if ((int64_t)F.h * F.w > P->max_pixels) P->max_pixels = (int64_t)F.h * F.w;
+        P->images.push_back(im);
+        P->file_index.push_back(i);
+    }
+
+    for (DecPlan &P : plans) {
+        const int cn = (int)P.images.size();
+        // staging layout: descriptors | table sets | quantisation tables | scan segments
+        const size_t off_img = 0, off_tab = align_up(sizeof(v5j::DecImage) * (size_t)cn, 16);
+        const size_t off_q = off_tab + align_up(sizeof(v5j::DecTabSet) * tabsets.size(), 16);
+        const size_t off_scan = off_q + align_up(256 * qsets.size(), 16);
+        const size_t stage_bytes = off_scan + P.scan_bytes;
+        if (s->stage_host_cap < stage_bytes) {
+            V5_CUDA(h, cudaEventSynchronize(s->stage_free));
+            if (s->stage_host) cudaFreeHost(s->stage_host);
+            s->stage_host = nullptr;
+            s->stage_host_cap = 0;
+            V5_CUDA(h, cudaHostAlloc((void **)&s->stage_host, stage_bytes + stage_bytes / 4, cudaHostAllocDefault));
+            s->stage_host_cap = stage_bytes + stage_bytes / 4;
+        }
+        if ((rc = ensure(h, (void **)&s->d_stage, &s->stage_cap, stage_bytes))) return rc;
+        if ((rc = ensure(h, &s->d_streams, &s->streams_cap, P.stream_bytes))) return rc;
+        if ((rc = ensure(h, &s->d_dcoef, &s->dcoef_cap, P.coef_blocks * 128))) return rc;
+        if ((rc = ensure(h, &s->d_planes, &s->planes_cap, P.plane_bytes))) return rc;
+        if ((rc = ensure(h, &s->d_bits, &s->bits_cap, sizeof(uint32_t) * (size_t)cn))) return rc;
+        if ((rc = ensure(h, &s->d_status, &s->status_cap, sizeof(int32_t) * (size_t)cn))) return rc;
+        V5_CUDA(h, cudaEventSynchronize(s->stage_free));                 // the previous upload no longer reads stage_host
+        for (int k = 0; k < cn; k++) {
+            v5j::DecImage &im = P.images[(size_t)k];
+            const int fi = P.file_index[(size_t)k];
+            memcpy(s->stage_host + off_scan + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len);
+            im.scan_off += (int64_t)off_scan;
+        }
+        memcpy(s->stage_host + off_img, P.images.data(), sizeof(v5j::DecImage) * (size_t)cn);
+        memcpy(s->stage_host + off_tab, tabsets.data(), sizeof(v5j::DecTabSet) * tabsets.size());
+        for (size_t k = 0; k < qsets.size(); k++) memcpy(s->stage_host + off_q + 256 * k, qsets[k].data(), 256);
+        V5_CUDA(h, cudaMemcpyAsync(s->d_stage, s->stage_host, stage_bytes, cudaMemcpyHostToDevice, st));
+        V5_CUDA(h, cudaEventRecord(s->stage_free, st));
+        V5_CUDA(h, cudaMemsetAsync(s->d_streams, 0, P.stream_bytes, st));
+        V5_CUDA(h, cudaMemsetAsync(s->d_dcoef, 0, P.coef_blocks * 128, st));
+
+        const v5j::DecImage *d_images = reinterpret_cast<const v5j::DecImage *>(s->d_stage + off_img);
+        const v5j::DecTabSet *d_tabs = reinterpret_cast<const v5j::DecTabSet *>(s->d_stage + off_tab);
+        const uint16_t *d_q = reinterpret_cast<const uint16_t *>(s->d_stage + off_q);
+        uint32_t *d_bits = static_cast<uint32_t *>(s->d_bits);
+        int32_t *d_st = static_cast<int32_t *>(s->d_status);
+        v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, s->d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
+        V5_CUDA(h, cudaGetLastError());
+        v5j::huffman_kernel<<<cn, v5j::HUFF_NT, 0, st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
+                                                        static_cast<int16_t *>(s->d_dcoef), d_st);
+        V5_CUDA(h, cudaGetLastError());
+        v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dcoef));
+        V5_CUDA(h, cudaGetLastError());
+        v5j::idct_kernel<<<dim3((unsigned)((P.max_blocks + 63) / 64), (unsigned)cn), 256, 0, st>>>(
+            d_images, d_q, static_cast<const int16_t *>(s->d_dcoef), static_cast<uint8_t *>(s->d_planes));
+        V5_CUDA(h, cudaGetLastError());
+        v5j::colour_kernel<<<dim3((unsigned)((P.max_pixels + 255) / 256), (unsigned)cn), 256, 0, st>>>(
+            d_images, static_cast<const uint8_t *>(s->d_planes), d_rgb, d_gray);
+        V5_CUDA(h, cudaGetLastError());
+        if (d_status)                                                      // chunks keep file order: one contiguous range
+            V5_CUDA(h, cudaMemcpyAsync(d_status + P.file_index[0], d_st, sizeof(int32_t) * (size_t)cn, cudaMemcpyDeviceToDevice, st));
+        h->launches += 5;
+    }
+    return V5ELA_OK;
+}
+
+int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *rgb_host,
+                           const int64_t *rgb_offsets, uint8_t *gray_host, const int64_t *gray_offsets)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!files_host || !lens || n < 0 || (!rgb_host && !gray_host))
+        return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode_host: bad pointer or count%s");
+    DeviceGuard guard(h->device);
+    v5jpeg_state *s;
+    int rc;
+    if ((rc = jpeg_state(h, &s))) return rc;
+    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->own_stream;
+    // output extents: the caller's offsets, or tight packing in file order
+    std::vector<int64_t> px((size_t)n);
+    int64_t rgb_end = 0, gray_end = 0, run = 0;
+    for (int i = 0; i < n; i++) {
+        int hh, ww, cc;
+        if (!files_host[i] || (rc = v5ela_jpeg_info(files_host[i], lens[i], &hh, &ww, &cc)))
+            return fail(h, rc ? rc : V5ELA_ERR_INVALID, "v5ela_jpeg_decode_host: unreadable JPEG headers%s");
+        px[(size_t)i] = (int64_t)hh * ww;
+        const int64_t ro = rgb_offsets ? rgb_offsets[i] : 3 * run, go = gray_offsets ? gray_offsets[i] : run;
+        if (ro < 0 || go < 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode_host: negative output offset%s");
+        if (ro + 3 * px[(size_t)i] > rgb_end) rgb_end = ro + 3 * px[(size_t)i];
+        if (go + px[(size_t)i] > gray_end) gray_end = go + px[(size_t)i];
+        run += px[(size_t)i];
+    }
+    if (rgb_host && (rc = ensure(h, (void **)&s->d_dec_rgb, &s->dec_rgb_cap, (size_t)rgb_end))) return rc;
+    if (gray_host && (rc = ensure(h, (void **)&s->d_dec_gray, &s->dec_gray_cap, (size_t)gray_end))) return rc;
+    std::vector<int32_t> status((size_t)n, 0);
+    int32_t *d_status = nullptr;
+    V5_CUDA(h, cudaMalloc(&d_status, sizeof(int32_t) * (size_t)n));
+    rc = v5ela_jpeg_decode(h, files_host, lens, n, rgb_host ? s->d_dec_rgb : nullptr, rgb_offsets, gray_host ? s->d_dec_gray : nullptr,
+                           gray_offsets, d_status, st);
+    if (rc == V5ELA_OK) {
+        cudaMemcpyAsync(status.data(), d_status, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st);
+        run = 0;
+        for (int i = 0; i < n; i++) {
+            const int64_t ro = rgb_offsets ? rgb_offsets[i] : 3 * run, go = gray_offsets ? gray_offsets[i] : run;
+            if (rgb_host) cudaMemcpyAsync(rgb_host + ro, s->d_dec_rgb + ro, (size_t)(3 * px[(size_t)i]), cudaMemcpyDeviceToHost, st);
+            if (gray_host) cudaMemcpyAsync(gray_host + go, s->d_dec_gray + go, (size_t)px[(size_t)i], cudaMemcpyDeviceToHost, st);
+            run += px[(size_t)i];
+        }
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(h, V5ELA_ERR_CUDA, "v5ela_jpeg_decode_host: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_status);
+    if (rc) return rc;
+    for (int i = 0; i < n; i++)
+        if (status[(size_t)i] != 0) {
+            char which[64];
+            snprintf(which, sizeof(which), " (file %d)", i);
+            return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode_host: entropy-coded data ends early or is corrupt%s", which);
+        }
+    return V5ELA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+// v5jpeg_dec.cuh — baseline JPEG decoder on the GPU: what the reference does with
+// Image.open(crop).convert('RGB') (v5_texture_ela.py:64) and cv2.imread(crop, IMREAD_GRAYSCALE) (:83) on the crop files V1
+// wrote with cv2.imwrite (v1_keyframes_facetrack.py:166) — libjpeg's defaults: ISLOW inverse DCT, fancy h2v2 upsampling.
+// Pixel-identical to both libraries. Per batch of files (any mix of sizes):
+//
+//   unstuff_kernel  one CTA per file: entropy-coded segment with FF 00 -> FF, as a flat bit stream
+//   huffman_kernel  one CTA per file: Huffman decoding in parallel by SELF-SYNCHRONISATION. The stream is cut into
+//                   1024-bit subsequences, one per thread. Only the first thread knows its decoder state (bit position,
+//                   block-in-MCU, zigzag index); the others start blind at their subsequence's first bit, and because
+//                   Huffman codes resynchronise after a few symbols, almost all of them are in the right state when they
+//                   leave their subsequence. Every thread then keeps decoding into the following subsequences until its
+//                   exit state equals the one recorded there, overwriting the record otherwise; when nobody moves, every
+//                   recorded state is the true one. A prefix sum of the blocks completed per subsequence gives every thread
+//                   its output position and a last pass decodes again, this time writing coefficients. Windows of 1024
+//                   subsequences are processed in order by the same CTA, carrying the exact state from one to the next.
+//   dc_kernel       one CTA per file: DC differences -> DC values (prefix sum per component, T.81 F.2.2.1)
+//   idct_kernel     dequantise + ISLOW inverse DCT, 4 threads per block -> sample planes
+//   colour_kernel   fancy upsample (A.7) + YCbCr -> RGB (A.8), and/or the luma plane alone
+//
+// The symbol-level logic is __host__ __device__ so that tests/emu can run it on the CPU (a debugging aid, not a fallback).
+#pragma once
+#include <stdint.h>
+
+#include "v5ela_device.cuh"
+#include "v5jpeg_common.h"
+
+namespace v5j {
+
+#ifndef V5J_HUFF_NT
+#define V5J_HUFF_NT 1024
+#endif
+#ifndef V5J_SUB_BITS
+#define V5J_SUB_BITS 1024
+#endif
+constexpr int HUFF_NT = V5J_HUFF_NT;       // subsequences per window = threads of the decoding CTA
+constexpr uint32_t SUB_BITS = V5J_SUB_BITS;   // bits per subsequence (> 31: a symbol never skips a whole subsequence)
+
+struct DecTabSet {                         // Huffman tables of one file: [0] luma, [1] chroma
+    DecTable dc[2], ac[2];
+};
+
+struct DecImage {
+    int32_t h, w, ncomp;
+    int32_t mcux, mcuy, bpm, blocks;
+    int32_t tabset;                        // index into the table-set array
+    int32_t qt;                            // index into the quantisation-table array (2 x 64 uint16 per entry)
+    int32_t yw, yh, cw, ch;                // padded plane sizes
+    int64_t scan_off, scan_len;            // entropy-coded segment inside the uploaded file bytes
+    int64_t stream_off;                    // unstuffed stream inside the stream buffer (16-byte aligned)
+    int64_t coef_off;                      // first block inside the coefficient buffer
+    int64_t plane_off;                     // Y plane inside the plane buffer; Cb follows, then Cr
+    int64_t rgb_off, gray_off;             // output positions (bytes), -1 = not wanted
+};
+
+struct SubState {                          // decoder state between two symbols
+    uint32_t p;                            // bit position in the unstuffed stream
+    uint16_t c;                            // block inside the MCU (0..bpm-1)
+    uint16_t z;                            // next zigzag index (0 = a DC symbol comes next)
+};
+struct SubInfo {
+    SubState s;                            // state on leaving the subsequence
+    uint32_t n;                            // blocks completed inside it
+    uint32_t pad;
+};
+
+V5_HOSTDEV bool same_state(const SubState &a, const SubState &b) { return a.p == b.p && a.c == b.c && a.z == b.z; }
+
+// 32 stream bits starting at bit position p (most significant first). The stream buffer is padded with zero bytes.
+V5_HOSTDEV uint32_t window32(const uint8_t *stream, uint32_t p)
+{
+#ifdef __CUDA_ARCH__
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(stream) + (p >> 5);
+    const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
+    return __funnelshift_l(lo, hi, p & 31);
+#else
+    const uint8_t *b = stream + (p >> 3);
+    const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | b[4];
+    return (uint32_t)(v >> (8 - (p & 7)));
+#endif
+}
+
+// One Huffman symbol from the window: returns the symbol, adds its code length to `len`. Codes that do not exist decode as
+// symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
+V5_HOSTDEV int huff_symbol(const DecTable &t, uint32_t win, int &len)
+{
+    const uint32_t look = t.look[win >> 23];
+    if (look) {
+        len = (int)(look >> 8);
+        return (int)(look & 0xff);
+    }
+    for (int l = 10; l <= 16; l++) {
+        const int32_t code = (int32_t)(win >> (32 - l));
+        if (code <= t.maxcode[l]) {
+            len = l;
+            return t.vals[(t.valoff[l] + code) & 0xff];
+        }
+    }
+    len = 16;
+    return 0;
+}
+
+// Decodes from state `s` until the bit position reaches `limit`; returns the number of blocks completed. WRITE: stores
+// every non-zero coefficient of block (block0 + completed) at coef[block * 64 + zigzag index] (DC as a difference);
+// blocks >= max_blocks (trailing padding bits decoded as symbols) are dropped.
+template <bool WRITE>
+V5_HOSTDEV uint32_t decode_span(const uint8_t *stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
+                                int64_t block0, int64_t max_blocks)
+{
+    uint32_t p = s.p, done = 0;
+    int c = s.c, z = s.z;
+    while (p < limit) {
+        const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
+        const uint32_t win = window32(stream, p);
+        int len;
+        if (z == 0) {
+            int sz = huff_symbol(T.dc[comp], win, len);
+            if (sz > 15) sz = 15;
+            if (WRITE && sz && block0 + done < max_blocks) {
+                const int v = (int)((win << len) >> (32 - sz));
+                coef[(block0 + done) * 64] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+            }
+            p += (uint32_t)(len + sz);
+            z = 1;
+        } else {
+            const int rs = huff_symbol(T.ac[comp], win, len), r = rs >> 4, sz = rs & 15;
+            if (sz == 0) {
+                z = r == 15 ? z + 16 : 64;                               // ZRL / EOB
+                p += (uint32_t)len;
+            } else {
+                z += r;
+                if (WRITE && z < 64 && block0 + done < max_blocks) {
+                    const int v = (int)((win << len) >> (32 - sz));
+                    coef[(block0 + done) * 64 + z] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+                }
+                z++;
+                p += (uint32_t)(len + sz);
+            }
+        }
+        if (z >= 64) {
+            z = 0;
+            c = c + 1 == bpm ? 0 : c + 1;
+            done++;
+        }
+    }
+    s.p = p;
+    s.c = (uint16_t)c;
+    s.z = (uint16_t)z;
+    return done;
+}
+
+// ------------------------------------------------------------------------------------ window logic of huffman_kernel
+// Shared by the kernel and the CPU emulation: every function is one barrier-delimited phase of thread t.
+struct HuffWindow {
+    SubInfo info[HUFF_NT];                 // info[t]: exit state of subsequence w0 + t, blocks completed inside it
+    SubState cur[HUFF_NT];                 // travelling state of thread t
+    uint8_t done[HUFF_NT];
+    SubState carry;                        // exact state at the start of the window
+    uint32_t base_blocks;                  // blocks completed before the window
+};
+
+struct HuffJob {
+    const uint8_t *stream;
+    uint32_t total_bits, nsub;
+    int bpm;
+    int64_t max_blocks;
+    int16_t *coef;
+};
+
+V5_HOSTDEV uint32_t sub_limit(const HuffJob &J, uint32_t j)
+{
+    const uint64_t e = (uint64_t)(j + 1) * SUB_BITS;
+    return e < J.total_bits ? (uint32_t)e : J.total_bits;
+}
+
+V5_HOSTDEV void huff_phase_first(int t, HuffWindow &W, const HuffJob &J, const DecTabSet &T, uint32_t w0)
+{
+    const uint32_t j = w0 + (uint32_t)t;
+    if (j >= J.nsub) {
+        W.done[t] = 1;
+        return;
+    }
+    SubState st;
+    if (t == 0) st = W.carry;
+    else { st.p = j * SUB_BITS; st.c = 0; st.z = 0; }
+    W.info[t].n = decode_span<false>(J.stream, st, sub_limit(J, j), T, J.bpm, nullptr, 0, 0);
+    W.info[t].s = st;
+    W.cur[t] = st;
+    W.done[t] = 0;
+}
+
+// round r >= 1: thread t decodes subsequence w0 + t + r from where it stands
+V5_HOSTDEV void huff_phase_round(int t, int r, HuffWindow &W, const HuffJob &J, const DecTabSet &T, uint32_t w0)
+{
+    if (W.done[t]) return;
+    const int k = t + r;
+    if (k >= HUFF_NT || w0 + (uint32_t)k >= J.nsub) {
+        W.done[t] = 1;
+        return;
+    }
+    SubState st = W.cur[t];
+    const uint32_t n = decode_span<false>(J.stream, st, sub_limit(J, w0 + (uint32_t)k), T, J.bpm, nullptr, 0, 0);
+    if (same_state(st, W.info[k].s)) W.done[t] = 1;                     // synchronised: the rest of the walk is already recorded
+    W.info[k].s = st;                                                    // this thread entered k in a state at least as good
+    W.info[k].n = n;                                                     // as the recorded one: its block count is the one to keep
+    W.cur[t] = st;
+}
+
+// write pass: block0 = blocks completed before subsequence w0 + t
+V5_HOSTDEV void huff_phase_write(int t, HuffWindow &W, const HuffJob &J, const DecTabSet &T, uint32_t w0, uint32_t block0)
+{
+    const uint32_t j = w0 + (uint32_t)t;
+    if (j >= J.nsub) return;
+    SubState st = t == 0 ? W.carry : W.info[t - 1].s;
+    decode_span<true>(J.stream, st, sub_limit(J, j), T, J.bpm, J.coef, (int64_t)block0, J.max_blocks);
+}
+
+// ------------------------------------------------------------------------------------------------- DC prediction
+// diff -> value for the blocks of one MCU given the running predictors; coefficients in place.
+V5_HOSTDEV void dc_apply_mcu(int16_t *mcu_coef, int bpm, int &py, int &pcb, int &pcr)
+{
+    if (bpm == 1) {
+        py += mcu_coef[0];
+        mcu_coef[0] = (int16_t)py;
+        return;
+    }
+    for (int i = 0; i < 4; i++) {
+        py += mcu_coef[64 * i];
+        mcu_coef[64 * i] = (int16_t)py;
+    }
+    pcb += mcu_coef[64 * 4];
+    mcu_coef[64 * 4] = (int16_t)pcb;
+    pcr += mcu_coef[64 * 5];
+    mcu_coef[64 * 5] = (int16_t)pcr;
+}
+
+// ------------------------------------------------------------------------------------------- inverse DCT of a block
+// thread j of 4: columns 2j, 2j+1 (dequantised) -> ws; then rows 2j, 2j+1 -> 8 clamped samples each
+V5_DEV void idct_cols(const int16_t *coef_zz, const uint16_t *qt, const uint8_t *zz, int j, int16_t *ws)
+{
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+        const int c = 2 * j + cc;
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (int)coef_zz[zz[8 * k + c]] * (int)qt[8 * k + c];
+        v5::idct8<1, false>(v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) ws[8 * k + c] = (int16_t)v[k];
+    }
+}
+
+V5_DEV void idct_rows(const int16_t *ws, int j, uint8_t *dst, int pitch)
+{
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = 2 * j + rr;
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = ws[8 * r + k];
+        v5::idct8<1, true>(v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[r * pitch + k] = (uint8_t)v5::clamp255(v[k]);
+    }
+}
+
+// where block g (scan order) of an image lands: plane pointer offset and pitch
+V5_HOSTDEV int64_t block_dest(const DecImage &im, int g, int &pitch, int &comp)
+{
+    if (im.bpm == 1) {
+        pitch = im.yw;
+        comp = 0;
+        const int my = g / im.mcux, mx = g - my * im.mcux;
+        return (int64_t)(8 * my) * im.yw + 8 * mx;
+    }
+    const int m = g / 6, i = g - 6 * m;
+    const int my = m / im.mcux, mx = m - my * im.mcux;
+    if (i < 4) {
+        pitch = im.yw;
+        comp = 0;
+        return (int64_t)(16 * my + 8 * (i >> 1)) * im.yw + 16 * mx + 8 * (i & 1);
+    }
+    pitch = im.cw;
+    comp = i - 3;
+    return (int64_t)im.yw * im.yh + (int64_t)(i - 4) * im.cw * im.ch + (int64_t)(8 * my) * im.cw + 8 * mx;
+}
+
+// ------------------------------------------------------------------------------------------ upsample + colour (A.7/A.8)
+V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int y, uint8_t out[3])
+{
+    const uint8_t *yp = planes, *cbp = planes + (int64_t)im.yw * im.yh, *crp = cbp + (int64_t)im.cw * im.ch;
+    const int yy = yp[(int64_t)y * im.yw + x];
+    if (im.ncomp == 1) {
+        out[0] = out[1] = out[2] = (uint8_t)yy;
+        return;
+    }
+    const int hc = (im.h + 1) >> 1, wc = (im.w + 1) >> 1, cw = im.cw;
+    const int r = y >> 1, cx = x >> 1;
+    int nb = (y & 1) ? r + 1 : r - 1;
+    nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
+    int cb, cr;
+    if (wc <= 2) {
+        cb = cbp[(int64_t)r * cw + cx];
+        cr = crp[(int64_t)r * cw + cx];
+    } else {
+        int nx = (x & 1) ? cx + 1 : cx - 1;
+        nx = nx < 0 ? 0 : (nx > wc - 1 ? wc - 1 : nx);
+        const int bias = (x & 1) ? 7 : 8;
+        int s0 = 3 * cbp[(int64_t)r * cw + cx] + cbp[(int64_t)nb * cw + cx];
+        int s1 = 3 * cbp[(int64_t)r * cw + nx] + cbp[(int64_t)nb * cw + nx];
+        cb = (3 * s0 + s1 + bias) >> 4;
+        s0 = 3 * crp[(int64_t)r * cw + cx] + crp[(int64_t)nb * cw + cx];
+        s1 = 3 * crp[(int64_t)r * cw + nx] + crp[(int64_t)nb * cw + nx];
+        cr = (3 * s0 + s1 + bias) >> 4;
+    }
+    const int cbd = cb - 128, crd = cr - 128;
+    out[0] = (uint8_t)v5::clamp255(yy + ((91881 * crd + 32768) >> 16));
+    out[1] = (uint8_t)v5::clamp255(yy + ((-22554 * cbd - 46802 * crd + 32768) >> 16));
+    out[2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------------- kernels
+__constant__ uint8_t kNaturalToZigzagDev[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                                41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                                46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+__device__ __forceinline__ uint32_t dec_cta_scan(uint32_t v, uint32_t *warp_sums, uint32_t *sum)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_sums[lane] = wi - w;
+        if (lane == 31) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t excl = incl - v + warp_sums[warp];
+    *sum = warp_sums[32];
+    __syncthreads();
+    return excl;
+}
+
+// FF 00 -> FF. stream_bits[img] = 8 x kept bytes. The stream buffer is zero-initialised and padded by the host side.
+__global__ void __launch_bounds__(1024) unstuff_kernel(const DecImage *images, const uint8_t *files, uint8_t *streams,
+                                                       uint32_t *stream_bits)
+{
+    __shared__ uint32_t warp_sums[33];
+    const DecImage im = images[blockIdx.x];
+    const uint8_t *src = files + im.scan_off;
+    uint8_t *dst = streams + im.stream_off;
+    uint32_t running = 0;
+    for (int64_t base = 0; base < im.scan_len; base += 4 * 1024) {
+        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        uint8_t b[5];
+        uint32_t keep = 0, cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int64_t i = i0 - 1 + k;
+            b[k] = (i >= 0 && i < im.scan_len) ? src[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k < im.scan_len && !(b[k + 1] == 0x00 && b[k] == 0xFF)) {
+                keep |= 1u << k;
+                cnt++;
+            }
+        uint32_t sum;
+        uint32_t o = running + dec_cta_scan(cnt, warp_sums, &sum);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (keep & (1u << k)) dst[o++] = b[k + 1];
+        running += sum;
+    }
+    if (threadIdx.x == 0) stream_bits[blockIdx.x] = running * 8u;
+}
+
+struct HuffSmem {
+    DecTabSet T;
+    HuffWindow W;
+    uint32_t warp_sums[33];
+};
+
+__global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+                                                          const uint32_t *stream_bits, int16_t *coef, int32_t *status)
+{
+    __shared__ HuffSmem S;
+    const int t = (int)threadIdx.x;
+    const DecImage im = images[blockIdx.x];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&tabsets[im.tabset]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
+        for (int i = t; i < (int)(sizeof(DecTabSet) / 4); i += HUFF_NT) dst[i] = src[i];
+    }
+    HuffJob J;
+    J.stream = streams + im.stream_off;
+    J.total_bits = stream_bits[blockIdx.x];
+    J.nsub = (J.total_bits + SUB_BITS - 1) / SUB_BITS;
+    J.bpm = im.bpm;
+    J.max_blocks = im.blocks;
+    J.coef = coef + im.coef_off * 64;
+    if (t == 0) {
+        S.W.carry.p = 0;
+        S.W.carry.c = 0;
+        S.W.carry.z = 0;
+        S.W.base_blocks = 0;
+    }
+    __syncthreads();
+    for (uint32_t w0 = 0; w0 < J.nsub; w0 += HUFF_NT) {
+        huff_phase_first(t, S.W, J, S.T, w0);
+        __syncthreads();
+        for (int r = 1; r < HUFF_NT; r++) {
+            huff_phase_round(t, r, S.W, J, S.T, w0);
+            if (__syncthreads_and(S.W.done[t])) break;
+        }
+        const bool active = w0 + (uint32_t)t < J.nsub;
+        uint32_t sum;
+        const uint32_t ex = dec_cta_scan(active ? S.W.info[t].n : 0u, S.warp_sums, &sum);
+        huff_phase_write(t, S.W, J, S.T, w0, S.W.base_blocks + ex);
+        __syncthreads();
+        if (t == 0) {
+            const uint32_t last = J.nsub - w0 < (uint32_t)HUFF_NT ? J.nsub - w0 - 1 : HUFF_NT - 1;
+            S.W.carry = S.W.info[last].s;
+            S.W.base_blocks += sum;
+        }
+        __syncthreads();
+    }
+    // a well-formed stream holds exactly `blocks` blocks (trailing pad bits may decode into at most a few phantom ones)
+    if (t == 0) status[blockIdx.x] = S.W.base_blocks >= (uint32_t)im.blocks ? 0 : -1;
+}
+
+// DC differences -> values. One CTA per file; thread t owns MCU chunk_base + t, three CTA scans per chunk of 1024 MCUs.
+__global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_t *coef)
+{
+    __shared__ uint32_t warp_sums[33];
+    const DecImage im = images[blockIdx.x];
+    int16_t *base = coef + im.coef_off * 64;
+    const int mcus = im.mcux * im.mcuy;
+    int run[3] = {0, 0, 0};
+    for (int m0 = 0; m0 < mcus; m0 += 1024) {
+        const int m = m0 + (int)threadIdx.x;
+        int16_t *mc = base + (int64_t)m * im.bpm * 64;
+        int d[3] = {0, 0, 0};
+        if (m < mcus) {
+            if (im.bpm == 1) d[0] = mc[0];
+            else {
+                d[0] = mc[0] + mc[64] + mc[128] + mc[192];
+                d[1] = mc[256];
+                d[2] = mc[320];
+            }
+        }
+        int pred[3];
+        for (int c = 0; c < (im.bpm == 1 ? 1 : 3); c++) {
+            uint32_t sum;
+            const uint32_t ex = dec_cta_scan((uint32_t)d[c], warp_sums, &sum);     // two's complement: wraps like int
+            pred[c] = run[c] + (int)ex;
+            run[c] += (int)sum;
+        }
+        if (m < mcus) dc_apply_mcu(mc, im.bpm, pred[0], pred[1], pred[2]);
+    }
+}
+
+// 64 blocks per CTA, 4 threads per block. grid = (ceil(max blocks / 64), files)
+__global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const uint16_t *qtabs, const int16_t *coef, uint8_t *planes)
+{
+    __shared__ int16_t ws[64][64 + 8];
+    __shared__ uint8_t zz[64];
+    const DecImage im = images[blockIdx.y];
+    if (threadIdx.x < 64) zz[threadIdx.x] = kNaturalToZigzagDev[threadIdx.x];
+    __syncthreads();
+    const int lb = (int)threadIdx.x >> 2, j = (int)threadIdx.x & 3;
+    const int g = (int)blockIdx.x * 64 + lb;
+    const bool active = g < im.blocks;
+    int pitch = 0, comp = 0;
+    int64_t off = 0;
+    if (active) {
+        off = block_dest(im, g, pitch, comp);
+        idct_cols(coef + (im.coef_off + g) * 64, qtabs + ((int64_t)im.qt * 2 + (comp ? 1 : 0)) * 64, zz, j, ws[lb]);
+    }
+    __syncwarp();
+    if (active) idct_rows(ws[lb], j, planes + im.plane_off + off, pitch);
+}
+
+// one thread per pixel. grid = (ceil(max pixels / 256), files)
+__global__ void __launch_bounds__(256) colour_kernel(const DecImage *images, const uint8_t *planes, uint8_t *rgb_out, uint8_t *gray_out)
+{
+    const DecImage im = images[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)im.h * im.w) return;
+    const int y = (int)(i / im.w), x = (int)(i - (int64_t)y * im.w);
+    const uint8_t *pl = planes + im.plane_off;
+    if (im.gray_off >= 0) gray_out[im.gray_off + i] = pl[(int64_t)y * im.yw + x];
+    if (im.rgb_off >= 0) {
+        uint8_t o[3];
+        pixel_rgb(im, pl, x, y, o);
+        uint8_t *d = rgb_out + im.rgb_off + 3 * i;
+        d[0] = o[0];
+        d[1] = o[1];
+        d[2] = o[2];
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace v5j

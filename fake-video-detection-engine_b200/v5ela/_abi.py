@@ -13,7 +13,8 @@ EXPORTS = (
     "v5ela_abi_version", "v5ela_record_bytes", "v5ela_status_string", "v5ela_create", "v5ela_destroy",
     "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze",
     "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
-    "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host",
+    "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host", "v5ela_jpeg_bound", "v5ela_jpeg_encode",
+    "v5ela_jpeg_encode_host", "v5ela_jpeg_info", "v5ela_jpeg_decode", "v5ela_jpeg_decode_host",
 )
 
 
@@ -58,13 +59,20 @@ def load() -> ctypes.CDLL:
     lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.v5ela_spectrum.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp]
     lib.v5ela_spectrum_host.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.v5ela_jpeg_bound.restype = i64
+    lib.v5ela_jpeg_bound.argtypes = [i32, i32, i32]
+    lib.v5ela_jpeg_encode.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, i32, vp, i64, vp, vp]
+    lib.v5ela_jpeg_encode_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp]
+    lib.v5ela_jpeg_info.argtypes = [vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    lib.v5ela_jpeg_decode.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.v5ela_jpeg_decode_host.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.v5ela_profile_enable.argtypes = [vp, i32]
     lib.v5ela_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     lib.v5ela_launch_count.restype = i64
     lib.v5ela_launch_count.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name not in ("v5ela_abi_version",):
+        if fn.restype is ctypes.c_int and name not in ("v5ela_abi_version", "v5ela_jpeg_bound"):
             fn.restype = i32
     if lib.v5ela_abi_version() != 1:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.v5ela_abi_version()} != 1")
@@ -130,6 +138,25 @@ class Handle:
 
     def spectrum_host(self, gray_host: int, n: int, h: int, w: int, out_host: int):
         self._check(self._lib.v5ela_spectrum_host(self._h, gray_host, n, h, w, out_host))
+
+    def jpeg_encode(self, d_img: int, n: int, h: int, w: int, channels: int, frame_stride: int, row_stride: int, quality: int,
+                    d_out: int, out_stride: int, d_sizes: int, stream: int | None):
+        self._check(self._lib.v5ela_jpeg_encode(self._h, d_img, n, h, w, channels, frame_stride, row_stride, quality, d_out,
+                                                out_stride, d_sizes, stream or None))
+
+    def jpeg_encode_host(self, img_host: int, n: int, h: int, w: int, channels: int, quality: int, out_host: int,
+                         out_stride: int, sizes_host: int):
+        self._check(self._lib.v5ela_jpeg_encode_host(self._h, img_host, n, h, w, channels, quality, out_host, out_stride,
+                                                     sizes_host))
+
+    def jpeg_decode(self, files, lens, n: int, d_rgb: int | None, rgb_offsets, d_gray: int | None, gray_offsets,
+                    d_status: int | None, stream: int | None):
+        self._check(self._lib.v5ela_jpeg_decode(self._h, files, lens, n, d_rgb or None, rgb_offsets, d_gray or None, gray_offsets,
+                                                d_status or None, stream or None))
+
+    def jpeg_decode_host(self, files, lens, n: int, rgb_host: int | None, rgb_offsets, gray_host: int | None, gray_offsets):
+        self._check(self._lib.v5ela_jpeg_decode_host(self._h, files, lens, n, rgb_host or None, rgb_offsets, gray_host or None,
+                                                     gray_offsets))
 
     def profile_enable(self, enable: bool = True):
         self._check(self._lib.v5ela_profile_enable(self._h, 1 if enable else 0))

@@ -36,7 +36,8 @@ typedef enum {
     V5ELA_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, bad stride, quality outside 1..100) */
     V5ELA_ERR_CUDA = -2,        /* a CUDA runtime call failed; see v5ela_last_error */
     V5ELA_ERR_NO_DEVICE = -3,   /* no CUDA device / device is not compute capability 10.x */
-    V5ELA_ERR_NOMEM = -4
+    V5ELA_ERR_NOMEM = -4,
+    V5ELA_ERR_UNSUPPORTED = -5  /* a JPEG file outside the supported set (see v5ela_jpeg_decode) */
 } v5ela_status;
 
 /*
@@ -137,6 +138,49 @@ V5ELA_API int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int 
 /* Same with HOST buffers (what the drop-in node calls); synchronises before returning. */
 V5ELA_API int v5ela_spectrum_host(v5ela_handle *h, const uint8_t *gray_host, int n, int height, int width,
                         uint8_t *out_host);
+
+/*
+ * ---- Codec rows: the JPEG files on either side of the ELA arithmetic, on the GPU ----------------
+ *
+ * Encoder: what the reference writes with PIL / OpenCV — `original.save(tmp,'JPEG',quality=90)` (v5_texture_ela.py:66-67),
+ * `enhanced_diff.save(ela_i.jpg)` (v5…:80-81, PIL default quality 75) and `cv2.imwrite(fft_i.jpg, spectrum)` (v5…:90-91, OpenCV
+ * default quality 95, one component) — byte-identical to libjpeg's output: baseline sequential, Annex K tables scaled by
+ * `quality`, 4:2:0 for three channels, the standard Huffman tables, JFIF 1.01 header.
+ *   d_img      : n images, uint8, `channels` = 1 (HW) or 3 (HWC, RGB), all height x width.
+ *   d_out      : n x out_stride_bytes; file i starts at d_out + i * out_stride_bytes.
+ *   d_sizes    : n file sizes. A size larger than out_stride_bytes means that file did not fit and its bytes are undefined;
+ *                v5ela_jpeg_bound() is a capacity that always fits (it is ~13 bytes per pixel; real files are far smaller).
+ * Asynchronous on `cuda_stream`; owns a workspace inside the handle.
+ */
+V5ELA_API int64_t v5ela_jpeg_bound(int height, int width, int channels);
+V5ELA_API int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, int width, int channels,
+                      int64_t frame_stride_bytes, int64_t row_stride_bytes, int quality,
+                      uint8_t *d_out, int64_t out_stride_bytes, int32_t *d_sizes, void *cuda_stream);
+/* Same with HOST buffers (what the drop-in node calls); synchronises before returning. */
+V5ELA_API int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, int n, int height, int width, int channels,
+                           int quality, uint8_t *out_host, int64_t out_stride_bytes, int32_t *sizes_host);
+
+/*
+ * Decoder: what the reference reads with `Image.open(crop_path).convert('RGB')` (v5_texture_ela.py:64) and
+ * `cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)` (v5…:83) — the crops V1 wrote with cv2.imwrite (v1_keyframes_facetrack.py:166).
+ * Pixel-identical to libjpeg's defaults (ISLOW inverse DCT, fancy upsampling). Supported: 8-bit baseline Huffman files with
+ * one component or three components sampled 2x2,1x1,1x1 (4:2:0), one scan, any Huffman / quantisation tables, no restart
+ * interval — everything PIL's and OpenCV's writers produce by default; anything else returns V5ELA_ERR_UNSUPPORTED and
+ * v5ela_last_error names the file.
+ *   files_host / lens : n complete JPEG files in HOST memory (they come from disk); sizes may differ from file to file.
+ *   d_rgb   : optional DEVICE buffer; file i is decoded to RGB (HWC; a one-component file is replicated) at byte offset
+ *             rgb_offsets[i], or tightly packed in file order when rgb_offsets is NULL.
+ *   d_gray  : optional DEVICE buffer; the luma plane alone (what IMREAD_GRAYSCALE returns), offsets likewise.
+ *   d_status: optional DEVICE array of n ints: 0, or -1 when the entropy-coded data of that file ended early.
+ * Header parsing and the staging copy happen on the calling thread; the decode itself is asynchronous on `cuda_stream`.
+ */
+V5ELA_API int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *width, int *channels);
+V5ELA_API int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n,
+                      uint8_t *d_rgb, const int64_t *rgb_offsets, uint8_t *d_gray, const int64_t *gray_offsets,
+                      int32_t *d_status, void *cuda_stream);
+/* Same with HOST outputs; synchronises, and reports truncated / corrupt entropy data as V5ELA_ERR_INVALID. */
+V5ELA_API int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n,
+                           uint8_t *rgb_host, const int64_t *rgb_offsets, uint8_t *gray_host, const int64_t *gray_offsets);
 
 /*
  * Measurement hook: while enabled, every v5ela_analyze records a CUDA event pair around the fused kernel on the launch

@@ -1,0 +1,177 @@
+// tests/emu/v5jpeg_emu.cpp — TEST INFRASTRUCTURE: runs the host/device-shared logic of the codec kernels
+// (csrc/v5jpeg_enc.cuh, csrc/v5jpeg_dec.cuh compiled by g++) with the threads of a CTA emulated sequentially between
+// barriers, so strip/edge/dummy-block indexing, the bit writer and the self-synchronising Huffman decoder can be checked
+// against the oracle in a container without a GPU. The prefix sums and the byte (un)stuffing are plain loops here; their
+// CUDA versions are covered by the -m gpu tests. NOT a CPU fallback: nothing under fake-video-detection-engine_b200/ loads it.
+//
+// Build (tests/test_jpeg_emu.py does it): g++ -O2 -shared -fPIC [-DV5J_HUFF_NT=.. -DV5J_SUB_BITS=..] -I include -I <csrc> ...
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "v5ela_host.h"
+#include "v5jpeg_enc.cuh"
+#include "v5jpeg_dec.cuh"
+
+using namespace v5j;
+
+extern "C" int64_t v5jemu_encode(const uint8_t *img, int h, int w, int channels, int64_t row_stride, int quality, uint8_t *out,
+                                 int64_t cap, int16_t *coef_out)
+{
+    const EncGeo g = enc_geo(h, w, channels);
+    uint16_t ql[64], qc[64];
+    v5::quant_tables(quality, ql, qc);
+    std::vector<int16_t> coef((size_t)g.blocks * 64);
+    CoefParams p;
+    memset(&p, 0, sizeof(p));
+    p.img = img;
+    p.row_stride = row_stride;
+    p.coef = coef.data();
+    p.g = g;
+    make_enc_quant(ql, p.q[0]);
+    make_enc_quant(qc, p.q[1]);
+    const int per = channels == 3 ? ENC_TM : ENC_BLOCKS;
+    CoefSmem *S = (CoefSmem *)aligned_alloc(16, (sizeof(CoefSmem) + 15) & ~(size_t)15);
+    for (int my = 0; my < g.mcuy; my++)
+        for (int tile_x = 0; tile_x * per < g.mcux; tile_x++) {
+            memset(S, 0xA5, sizeof(CoefSmem));                              // poison
+            memcpy(S->zz, kZigzag, 64);
+            const int mx0 = tile_x * per, mcus = g.mcux - mx0 < per ? g.mcux - mx0 : per, nblocks = mcus * g.bpm;
+            for (int t = 0; t < ENC_NT; t++) {
+                if (channels == 3) coef_load_colour(t, *S, p, img, tile_x, my);
+                else coef_load_gray(t, *S, p, img, tile_x, my);
+            }
+            for (int t = 0; t < ENC_NT; t++) coef_rows(t, *S, g.ncomp, nblocks);
+            for (int t = 0; t < ENC_NT; t++) coef_cols(t, *S, p, nblocks);
+            int16_t *dst = p.coef + ((int64_t)my * g.mcux + mx0) * g.bpm * 64;
+            for (int t = 0; t < ENC_NT; t++) coef_store(t, *S, p, dst, mx0, my, nblocks);
+        }
+    free(S);
+    if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
+    EncTables T;
+    standard_enc_tables(T);
+    std::vector<uint32_t> off((size_t)g.blocks + 1);
+    uint32_t total = 0;
+    for (int b = 0; b < g.blocks; b++) {
+        const int prev = dc_predecessor(b, g.bpm), pred = prev >= 0 ? coef[(size_t)prev * 64] : 0;
+        const int t = (g.bpm == 6 && (b % 6) >= 4) ? 1 : 0;
+        BitCounter cnt;
+        encode_block(&coef[(size_t)b * 64], pred, T.dc[t], T.ac[t], cnt);
+        off[b] = total;
+        total += cnt.total;
+    }
+    off[g.blocks] = total;
+    std::vector<uint32_t> raw((total + 31) / 32 + 2, 0u);
+    for (int b = g.blocks - 1; b >= 0; b--) {                               // any order must work
+        const int prev = dc_predecessor(b, g.bpm), pred = prev >= 0 ? coef[(size_t)prev * 64] : 0;
+        const int t = (g.bpm == 6 && (b % 6) >= 4) ? 1 : 0;
+        BitSink sink;
+        sink.init(raw.data(), off[b]);
+        encode_block(&coef[(size_t)b * 64], pred, T.dc[t], T.ac[t], sink);
+        sink.finish();
+    }
+    const std::vector<uint8_t> hdr = file_header(h, w, channels, ql, qc);
+    std::vector<uint8_t> file(hdr);
+    const uint32_t nbytes = (total + 7) / 8;
+    for (uint32_t i = 0; i < nbytes; i++) {
+        uint8_t v = (uint8_t)(raw[i >> 2] >> (24 - 8 * (i & 3)));
+        if (i == nbytes - 1 && (total & 7)) v |= (uint8_t)(0xff >> (total & 7));
+        file.push_back(v);
+        if (v == 0xff) file.push_back(0);
+    }
+    file.push_back(0xFF);
+    file.push_back(0xD9);
+    if ((int64_t)file.size() <= cap) memcpy(out, file.data(), file.size());
+    return (int64_t)file.size();
+}
+
+// -> 0, or the parse error; rounds_out (optional): the largest number of synchronisation rounds any window needed
+extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out, uint8_t *gray_out, int16_t *coef_out, int *rounds_out)
+{
+    FileInfo *F = new FileInfo();
+    const int rc = parse_file(data, (size_t)len, *F);
+    if (rc) { delete F; return rc; }
+    DecImage im;
+    memset(&im, 0, sizeof(im));
+    im.h = F->h; im.w = F->w; im.ncomp = F->ncomp;
+    const int m = F->ncomp == 3 ? 16 : 8;
+    im.mcux = (F->w + m - 1) / m; im.mcuy = (F->h + m - 1) / m;
+    im.bpm = F->ncomp == 3 ? 6 : 1;
+    im.blocks = im.mcux * im.mcuy * im.bpm;
+    im.yw = im.mcux * m; im.yh = im.mcuy * m;
+    im.cw = F->ncomp == 3 ? im.yw / 2 : 0; im.ch = F->ncomp == 3 ? im.yh / 2 : 0;
+    std::vector<uint8_t> stream;
+    for (size_t i = 0; i < F->scan_len; i++) {
+        const uint8_t b = data[F->scan_off + i];
+        if (b == 0 && i > 0 && data[F->scan_off + i - 1] == 0xFF) continue;
+        stream.push_back(b);
+    }
+    const uint32_t total_bits = (uint32_t)stream.size() * 8;
+    stream.resize(stream.size() + 32, 0);
+    DecTabSet *T = new DecTabSet();
+    T->dc[0] = F->dc[0]; T->dc[1] = F->dc[1]; T->ac[0] = F->ac[0]; T->ac[1] = F->ac[1];
+    std::vector<int16_t> coef((size_t)im.blocks * 64, 0);
+    HuffJob J;
+    J.stream = stream.data();
+    J.total_bits = total_bits;
+    J.nsub = (total_bits + SUB_BITS - 1) / SUB_BITS;
+    J.bpm = im.bpm;
+    J.max_blocks = im.blocks;
+    J.coef = coef.data();
+    HuffWindow *W = new HuffWindow();
+    memset(W, 0xA5, sizeof(*W));
+    W->carry.p = 0; W->carry.c = 0; W->carry.z = 0;
+    W->base_blocks = 0;
+    int max_rounds = 0;
+    for (uint32_t w0 = 0; w0 < J.nsub; w0 += HUFF_NT) {
+        for (int t = 0; t < HUFF_NT; t++) huff_phase_first(t, *W, J, *T, w0);
+        for (int r = 1; r < HUFF_NT; r++) {
+            for (int t = 0; t < HUFF_NT; t++) huff_phase_round(t, r, *W, J, *T, w0);
+            bool all = true;
+            for (int t = 0; t < HUFF_NT; t++) all = all && W->done[t];
+            if (r > max_rounds) max_rounds = r;
+            if (all) break;
+        }
+        uint32_t run = W->base_blocks;
+        std::vector<uint32_t> b0(HUFF_NT);
+        for (int t = 0; t < HUFF_NT; t++) {
+            b0[t] = run;
+            if (w0 + (uint32_t)t < J.nsub) run += W->info[t].n;
+        }
+        for (int t = HUFF_NT - 1; t >= 0; t--) huff_phase_write(t, *W, J, *T, w0, b0[t]);
+        const uint32_t last = J.nsub - w0 < (uint32_t)HUFF_NT ? J.nsub - w0 - 1 : HUFF_NT - 1;
+        W->carry = W->info[last].s;
+        W->base_blocks = run;
+    }
+    const bool ok = W->base_blocks >= (uint32_t)im.blocks;
+    if (rounds_out) *rounds_out = max_rounds;
+    int py = 0, pcb = 0, pcr = 0;
+    for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&coef[(size_t)mcu * im.bpm * 64], im.bpm, py, pcb, pcr);
+    if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
+    std::vector<uint8_t> planes((size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch);
+    uint8_t n2z[64];
+    for (int i = 0; i < 64; i++) n2z[kZigzag[i]] = (uint8_t)i;
+    for (int g = 0; g < im.blocks; g++) {
+        int pitch, comp;
+        const int64_t off = block_dest(im, g, pitch, comp);
+        int16_t ws[64];
+        for (int j = 0; j < 4; j++) idct_cols(&coef[(size_t)g * 64], F->qt[comp ? 1 : 0], n2z, j, ws);
+        for (int j = 0; j < 4; j++) idct_rows(ws, j, planes.data() + off, pitch);
+    }
+    for (int y = 0; y < im.h; y++)
+        for (int x = 0; x < im.w; x++) {
+            if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
+            if (rgb_out) pixel_rgb(im, planes.data(), x, y, rgb_out + ((size_t)y * im.w + x) * 3);
+        }
+    delete W; delete T; delete F;
+    return ok ? 0 : -3;
+}
+
+extern "C" int v5jemu_info(const uint8_t *data, int64_t len, int *h, int *w, int *ncomp)
+{
+    FileInfo *F = new FileInfo();
+    const int rc = parse_file(data, (size_t)len, *F);
+    if (!rc) { *h = F->h; *w = F->w; *ncomp = F->ncomp; }
+    delete F;
+    return rc;
+}

@@ -1,0 +1,139 @@
+"""CPU: the codec kernels' host/device-shared logic (csrc/v5jpeg_enc.cuh, v5jpeg_dec.cuh), compiled by g++ with the threads of
+a CTA emulated between barriers (tests/emu/v5jpeg_emu.cpp), against the oracle and the goldens. A debugging aid for strip /
+edge / dummy-block indexing, the bit writer and the self-synchronising Huffman decoder in a container without a GPU; the
+-m gpu tests are the real gate."""
+import ctypes
+import hashlib
+import io
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+from PIL import Image
+
+from helpers import HERE, golden_frame, load_json, sha
+from oracle import c_oracle
+
+ROOT = os.path.dirname(HERE)
+JPEG = load_json("jpeg_golden.json")
+SMALL = [c for c in JPEG["cases"] if c["h"] * c["w"] <= 300 * 500]
+_id = lambda c: f"{c['spec'][0]}{c['spec'][1]}_{c['h']}x{c['w']}_q{c['q']}"  # noqa: E731
+
+
+def _build(tag, defs):
+    so = os.path.join(HERE, "emu", f"libv5jpeg_emu_{tag}.so")
+    src = os.path.join(HERE, "emu", "v5jpeg_emu.cpp")
+    csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("v5jpeg_enc.cuh", "v5jpeg_dec.cuh", "v5jpeg_common.h", "v5ela_device.cuh", "v5ela_host.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", *defs, "-I", os.path.join(ROOT, "include"),
+                               "-I", csrc, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    u8p, i16p = ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int16)
+    lib.v5jemu_encode.restype = ctypes.c_int64
+    lib.v5jemu_encode.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, u8p, ctypes.c_int64, i16p]
+    lib.v5jemu_decode.argtypes = [u8p, ctypes.c_int64, u8p, u8p, i16p, ctypes.POINTER(ctypes.c_int)]
+    lib.v5jemu_info.argtypes = [u8p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int)] * 3
+    return lib
+
+
+@pytest.fixture(scope="module", params=["full", "tiny"])
+def emu(request):
+    """'full': the shipped window (1024 subsequences of 1024 bits). 'tiny': 8 subsequences of 64 bits per window, so that
+    even small files cross many windows and need many synchronisation rounds."""
+    defs = [] if request.param == "full" else ["-DV5J_HUFF_NT=8", "-DV5J_SUB_BITS=64"]
+    return _build(request.param, defs)
+
+
+def _u8(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+def emu_encode(lib, img, q, want_coef=False):
+    img = np.ascontiguousarray(img)
+    ch = 1 if img.ndim == 2 else 3
+    h, w = img.shape[:2]
+    cap = 4 * h * w * ch + 4096
+    out = np.zeros(cap, np.uint8)
+    coef = np.zeros((c_oracle.jpeg_blocks(h, w, ch), 64), np.int16)
+    n = lib.v5jemu_encode(_u8(img), h, w, ch, w * ch, q, _u8(out), cap, coef.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    assert 0 < n <= cap
+    return (out[:n].tobytes(), coef) if want_coef else out[:n].tobytes()
+
+
+def emu_decode(lib, data):
+    buf = np.frombuffer(data, np.uint8)
+    h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.v5jemu_info(_u8(buf), len(data), ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
+    if rc:
+        raise ValueError(rc)
+    rgb = np.zeros((h.value, w.value, 3), np.uint8)
+    gray = np.zeros((h.value, w.value), np.uint8)
+    coef = np.zeros((c_oracle.jpeg_blocks(h.value, w.value, c.value), 64), np.int16)
+    rounds = ctypes.c_int()
+    rc = lib.v5jemu_decode(_u8(buf), len(data), _u8(rgb), _u8(gray), coef.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)),
+                           ctypes.byref(rounds))
+    if rc:
+        raise ValueError(rc)
+    return {"rgb": rgb, "gray": gray, "coef": coef, "rounds": rounds.value}
+
+
+@pytest.mark.parametrize("case", SMALL, ids=_id)
+def test_encoder_logic_reproduces_golden_files(emu, case):
+    rgb = golden_frame(case)
+    data, coef = emu_encode(emu, rgb, case["q"], want_coef=True)
+    ref, ref_coef = c_oracle.jpeg_encode(rgb, case["q"], want_coef=True)
+    assert np.array_equal(coef, ref_coef)
+    assert data == ref
+    assert (len(data), hashlib.sha256(data).hexdigest()[:16]) == (case["rgb_file_len"], case["rgb_file_sha"])
+    data = emu_encode(emu, np.ascontiguousarray(rgb[..., 1]), case["q"])
+    assert (len(data), hashlib.sha256(data).hexdigest()[:16]) == (case["gray_file_len"], case["gray_file_sha"])
+
+
+@pytest.mark.parametrize("case", SMALL, ids=_id)
+def test_decoder_logic_reproduces_golden_pixels(emu, case):
+    rgb = golden_frame(case)
+    buf = io.BytesIO()
+    Image.fromarray(rgb, "RGB").save(buf, "JPEG", quality=case["q"])
+    out = emu_decode(emu, buf.getvalue())
+    ref = c_oracle.jpeg_decode(buf.getvalue(), want_coef=True)
+    assert np.array_equal(out["coef"], ref["coef"])
+    assert sha(out["rgb"]) == case["dec_rgb_sha"] and sha(out["gray"]) == case["dec_y_sha"]
+    ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(rgb[..., 1]), [cv2.IMWRITE_JPEG_QUALITY, case["q"]])
+    out = emu_decode(emu, enc.tobytes())
+    assert sha(out["gray"]) == case["dec_gray_file_sha"]
+
+
+def test_wide_images_cross_strip_boundaries(emu):
+    rng = np.random.default_rng(3)
+    for h, w in ((20, 300), (9, 520), (40, 771)):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert emu_encode(emu, rgb, 90) == c_oracle.jpeg_encode(rgb, 90)
+        gray = np.ascontiguousarray(rgb[..., 0])
+        data = emu_encode(emu, gray, 95)
+        assert data == c_oracle.jpeg_encode(gray, 95)
+        assert np.array_equal(emu_decode(emu, data)["gray"], c_oracle.jpeg_decode(data)["gray"])
+
+
+def test_decoder_custom_tables_and_noise(emu):
+    rng = np.random.default_rng(4)
+    rgb = rng.integers(0, 256, (64, 80, 3), dtype=np.uint8)
+    for kw in ({"quality": 100}, {"quality": 60, "optimize": True}, {"quality": 5}):
+        buf = io.BytesIO()
+        Image.fromarray(rgb).save(buf, "JPEG", **kw)
+        out = emu_decode(emu, buf.getvalue())
+        assert np.array_equal(out["rgb"], np.asarray(Image.open(buf).convert("RGB"))), kw
+
+
+def test_unsupported_files_are_refused(emu):
+    rgb = golden_frame({"spec": ["gen", 1, 2], "h": 40, "w": 40})
+    for kw in ({"subsampling": 0}, {"progressive": True}):
+        buf = io.BytesIO()
+        Image.fromarray(rgb).save(buf, "JPEG", quality=80, **kw)
+        with pytest.raises(ValueError):
+            emu_decode(emu, buf.getvalue())
+    ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3])
+    with pytest.raises(ValueError):
+        emu_decode(emu, enc.tobytes())

@@ -7,15 +7,23 @@ Behaviour contract kept from the reference (line numbers: /root/reference/nodes/
     ``fft_{i}.jpg`` numbered by rank (:80, :90); the GPT-4o request — model, prompts, three base64 JPEGs, JSON response
     format, 30 s timeout (:102-125); mean of ``fake_probability`` (:147-165); ``V5_debug.json`` keys (:166-173);
     any per-face failure is printed and skipped, never raised (:140-144).
-What runs on the B200 instead of Pillow/NumPy: the error-level analysis (:66-78) through ``v5ela_analyze_host`` —
-  bit-exact, so ``ela_{i}.jpg`` equals the reference's file byte for byte — and the FFT log-magnitude image (:84-88)
-  through ``v5ela_spectrum_host`` (within one grey level of NumPy; identical on every golden crop). There is no CPU
-  fallback: a missing library or GPU surfaces as that face's error, like any other analysis failure.
+What runs on the B200 instead of Pillow/OpenCV/NumPy:
+  * decoding the crop file, both as RGB (:64) and as its luma plane (:83), through ``v5ela_jpeg_decode_host`` — pixel-identical;
+  * the error-level analysis (:66-78) through ``v5ela_analyze_host`` — bit-exact;
+  * the FFT log-magnitude image (:84-88) through ``v5ela_spectrum_host`` (within one grey level of NumPy; identical on
+    every golden crop);
+  * JPEG-encoding the artefacts ``ela_{i}.jpg`` (:80-81, quality 75), ``fft_{i}.jpg`` (:90-91, quality 95, one component) and,
+    on request, the scratch file ``temp_ela_{i}.jpg`` (:66-67) through ``v5ela_jpeg_encode_host`` — the files equal the
+    reference's byte for byte.
+  There is no CPU fallback for any of it: a missing library or GPU surfaces as that face's error, like any other analysis
+  failure. A crop that is not a JPEG at all, or a JPEG flavour outside the GPU decoder's set (progressive, 4:4:4, restart
+  markers — nothing V1 writes), is read with the reference's own two library calls and says so on stdout.
 Optional state keys (defaults = the reference's literals): ``v5_quality`` 90, ``v5_max_faces`` 3, ``v5_device`` 0,
-  ``v5_gpu_fft`` True (False: the reference's NumPy spectrum), ``v5_keep_temp_jpeg`` False (the reference's scratch file
-  ``temp_ela_{i}.jpg``, which nothing reads, is written only on request). The V5F v1 statistics of every analysed face are
-  attached as ``ela_features`` to ``texture_ela_details`` entries and ``V5_debug.json`` (lr_node reads only ``avg_score``).
-Host side, unchanged: decoding the crop, JPEG-encoding the two artefacts, the OpenAI call.
+  ``v5_gpu_fft`` True (False: the reference's NumPy spectrum), ``v5_gpu_codec`` True (False: Pillow/OpenCV read and write the
+  files), ``v5_keep_temp_jpeg`` False (the reference's scratch file, which nothing reads, is written only on request). The
+  V5F v1 statistics of every analysed face are attached as ``ela_features`` to ``texture_ela_details`` entries and
+  ``V5_debug.json`` (lr_node reads only ``avg_score``).
+Host side, unchanged: the OpenAI call.
 """
 import base64
 import json
@@ -57,6 +65,37 @@ def _rank_faces(detections, limit):
     return with_crops, sorted(with_crops, key=weight, reverse=True)[:limit]
 
 
+def _read_crop(crop_path, device, gpu_codec):
+    """The crop as RGB (reference :64) and as its luma plane (:83)."""
+    if gpu_codec:
+        from v5ela import _abi, jpeg
+
+        with open(crop_path, "rb") as fh:
+            data = fh.read()
+        if data[:2] == b"\xff\xd8":
+            try:
+                planes = jpeg.decode_host([data], want_rgb=True, want_gray=True, device=device)[0]
+                return planes["rgb"], planes["gray"]
+            except _abi.V5ElaError as err:
+                if err.status != jpeg.UNSUPPORTED:
+                    raise
+        print(f"Node V5: {os.path.basename(crop_path)} is outside the GPU decoder's JPEG set; read with Pillow/OpenCV.")
+    return np.asarray(Image.open(crop_path).convert("RGB")), cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
+
+
+def _write_jpeg(path, image, quality, device, gpu_codec):
+    """``Image.save(path, 'JPEG', quality=q)`` / ``cv2.imwrite(path, gray)`` — the same bytes either way."""
+    if gpu_codec:
+        from v5ela import jpeg
+
+        with open(path, "wb") as fh:
+            fh.write(jpeg.encode_host(image[None], quality, device=device)[0])
+    elif image.ndim == 3:
+        Image.fromarray(image, "RGB").save(path, "JPEG", quality=quality)
+    else:
+        cv2.imwrite(path, image, [cv2.IMWRITE_JPEG_QUALITY, quality])
+
+
 def _gpu_artefacts(crop_path, rank, ela_dir, state):
     """ELA + spectrum artefacts of one crop; returns (feature dict, ela path, fft path)."""
     from v5ela import host as v5host
@@ -64,24 +103,24 @@ def _gpu_artefacts(crop_path, rank, ela_dir, state):
 
     quality = int(state.get("v5_quality", 90))
     device = int(state.get("v5_device", 0))
-    rgb = np.asarray(Image.open(crop_path).convert("RGB"))
+    gpu_codec = bool(state.get("v5_gpu_codec", True))
+    rgb, gray = _read_crop(crop_path, device, gpu_codec)
     if state.get("v5_keep_temp_jpeg", False):
-        Image.fromarray(rgb, "RGB").save(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), "JPEG", quality=quality)
+        _write_jpeg(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), rgb, quality, device, gpu_codec)
 
     records, _, enhanced = v5host.analyze_frames_host(rgb[None], quality=quality, want_enhanced=True, device=device)
     feats = features(records[0], rgb.shape[0] * rgb.shape[1])
     feats["rank"] = rank
     ela_path = os.path.join(ela_dir, f"ela_{rank}.jpg")
-    Image.fromarray(enhanced[0], "RGB").save(ela_path)
+    _write_jpeg(ela_path, enhanced[0], 75, device, gpu_codec)          # PIL's default quality (reference :81)
 
-    gray = cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
     if state.get("v5_gpu_fft", True):
         spectrum = v5host.spectrum_host(gray, device=device)
     else:
         log_mag = 20 * np.log(np.abs(np.fft.fftshift(np.fft.fft2(gray))) + 1)
         spectrum = cv2.normalize(log_mag, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
     fft_path = os.path.join(ela_dir, f"fft_{rank}.jpg")
-    cv2.imwrite(fft_path, spectrum)
+    _write_jpeg(fft_path, spectrum, 95, device, gpu_codec)              # OpenCV's default quality (reference :91)
     return feats, ela_path, fft_path
 
 

@@ -261,7 +261,10 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
     v5jpeg_state *s;
     int rc;
     if ((rc = jpeg_state(h, &s))) return rc;
-    if (!s->stage_free) V5_CUDA(h, cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+    if (!s->stage_free) {
+        V5_CUDA(h, cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+        V5_CUDA(h, cudaFuncSetAttribute(v5j::huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v5j::HuffSmem)));
+    }
 
     // ---- parse every file; unique Huffman table sets and quantisation table pairs
     std::vector<v5j::FileInfo> info((size_t)n);
@@ -380,7 +383,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         int32_t *d_st = static_cast<int32_t *>(s->d_status);
         v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, s->d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
         V5_CUDA(h, cudaGetLastError());
-        v5j::huffman_kernel<<<cn, v5j::HUFF_NT, 0, st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
+        v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
                                                         static_cast<int16_t *>(s->d_dcoef), d_st);
         V5_CUDA(h, cudaGetLastError());
         v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dcoef));

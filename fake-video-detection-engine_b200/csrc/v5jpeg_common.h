@@ -281,10 +281,21 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F)
         F.dc[1] = F.dc[0];
         F.ac[1] = F.ac[0];
     }
-    // the entropy-coded segment ends at the first marker that is not a stuffed zero (EOI in a well-formed file)
-    size_t e = F.scan_off;
-    while (e + 1 < len && !(d[e] == 0xFF && d[e + 1] != 0x00)) e++;
-    if (e + 1 >= len) e = len;
+    // The entropy-coded segment ends at the first marker that is not a stuffed zero: EOI in a well-formed file. Writers put
+    // EOI in the last two bytes, which is checked first; otherwise the segment is searched (memchr: FF bytes are rare).
+    size_t e;
+    if (len >= F.scan_off + 2 && d[len - 2] == 0xFF && d[len - 1] == 0xD9 && !(len >= F.scan_off + 3 && d[len - 3] == 0xFF)) {
+        e = len - 2;
+    } else {
+        e = F.scan_off;
+        for (;;) {
+            const void *hit = e + 1 < len ? memchr(d + e, 0xFF, len - 1 - e) : nullptr;
+            if (!hit) { e = len; break; }
+            e = (size_t)(static_cast<const uint8_t *>(hit) - d);
+            if (d[e + 1] != 0x00) break;
+            e += 2;
+        }
+    }
     F.scan_len = e - F.scan_off;
     return JPEG_OK;
 }

@@ -65,18 +65,65 @@ struct SubInfo {
 
 V5_HOSTDEV bool same_state(const SubState &a, const SubState &b) { return a.p == b.p && a.c == b.c && a.z == b.z; }
 
-// 32 stream bits starting at bit position p (most significant first). The stream buffer is padded with zero bytes.
-V5_HOSTDEV uint32_t window32(const uint8_t *stream, uint32_t p)
-{
+// Where the decoder reads the stream from. window(p) = the 32 stream bits that start at bit position p, most significant
+// first. The stream buffer is padded with zero bytes, so reading a little past the end is harmless.
+struct ByteStream {                        // plain bytes in (global) memory
+    const uint8_t *data;
+    V5_HOSTDEV uint32_t window(uint32_t p) const
+    {
 #ifdef __CUDA_ARCH__
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(stream) + (p >> 5);
-    const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
-    return __funnelshift_l(lo, hi, p & 31);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(data) + (p >> 5);
+        const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
+        return __funnelshift_l(lo, hi, p & 31);
 #else
-    const uint8_t *b = stream + (p >> 3);
-    const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | b[4];
-    return (uint32_t)(v >> (8 - (p & 7)));
+        const uint8_t *b = data + (p >> 3);
+        const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | b[4];
+        return (uint32_t)(v >> (8 - (p & 7)));
 #endif
+    }
+};
+
+// One window of the stream staged in shared memory as big-endian 32-bit words. Thread t works on words 32t .. 32t+31 (its
+// subsequence) and the threads of a warp tend to sit at similar offsets inside their subsequences, so word w is stored at
+// row w / 32, column (w + row) mod 32: equal offsets in 32 different subsequences fall into 32 different banks.
+constexpr int SUB_WORDS = (int)(SUB_BITS / 32);
+constexpr int WINDOW_WORDS = HUFF_NT * SUB_WORDS;
+constexpr int STAGE_WORDS = WINDOW_WORDS + SUB_WORDS;                      // + one row: a symbol may end just past the window
+V5_HOSTDEV int stage_slot(uint32_t w)
+{
+    if (SUB_WORDS == 32) return (int)((w & ~31u) | ((w + (w >> 5)) & 31u));
+    return (int)w;                                                         // test builds with tiny subsequences: no swizzle
+}
+struct StagedStream {
+    const uint32_t *words;                 // STAGE_WORDS entries
+    uint32_t base_word;                    // stream word index of words[stage_slot(0)]
+    V5_HOSTDEV uint32_t window(uint32_t p) const
+    {
+        const uint32_t w = (p >> 5) - base_word;
+        const uint32_t hi = words[stage_slot(w)], lo = words[stage_slot(w + 1)];
+#ifdef __CUDA_ARCH__
+        return __funnelshift_l(lo, hi, p & 31);
+#else
+        return (p & 31) ? (hi << (p & 31)) | (lo >> (32 - (p & 31))) : hi;
+#endif
+    }
+};
+// thread t of nt: copies the window that starts at stream word base_word (stream: bytes, padded with zeros up to pad_bytes)
+V5_HOSTDEV void stage_window(int t, int nt, uint32_t *words, const uint8_t *stream, uint32_t base_word, uint32_t stream_words)
+{
+    for (int i = t; i < STAGE_WORDS; i += nt) {
+        const uint32_t gw = base_word + (uint32_t)i;
+        uint32_t v = 0;
+        if (gw < stream_words) {
+#ifdef __CUDA_ARCH__
+            v = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(stream) + gw), 0, 0x0123);
+#else
+            const uint8_t *b = stream + 4 * (size_t)gw;
+            v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+#endif
+        }
+        words[stage_slot((uint32_t)i)] = v;
+    }
 }
 
 // One Huffman symbol from the window: returns the symbol, adds its code length to `len`. Codes that do not exist decode as
@@ -102,15 +149,15 @@ V5_HOSTDEV int huff_symbol(const DecTable &t, uint32_t win, int &len)
 // Decodes from state `s` until the bit position reaches `limit`; returns the number of blocks completed. WRITE: stores
 // every non-zero coefficient of block (block0 + completed) at coef[block * 64 + zigzag index] (DC as a difference);
 // blocks >= max_blocks (trailing padding bits decoded as symbols) are dropped.
-template <bool WRITE>
-V5_HOSTDEV uint32_t decode_span(const uint8_t *stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
+template <bool WRITE, class Src>
+V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
                                 int64_t block0, int64_t max_blocks)
 {
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
     while (p < limit) {
         const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
-        const uint32_t win = window32(stream, p);
+        const uint32_t win = stream.window(p);
         int len;
         if (z == 0) {
             int sz = huff_symbol(T.dc[comp], win, len);
@@ -159,7 +206,9 @@ struct HuffWindow {
 };
 
 struct HuffJob {
-    const uint8_t *stream;
+    const uint8_t *stream;                 // unstuffed stream (global memory), zero padded
+    StagedStream staged;                   // the current window of it (shared memory)
+    uint32_t stream_words;                 // 32-bit words that may be read from `stream`
     uint32_t total_bits, nsub;
     int bpm;
     int64_t max_blocks;
@@ -182,7 +231,7 @@ V5_HOSTDEV void huff_phase_first(int t, HuffWindow &W, const HuffJob &J, const D
     SubState st;
     if (t == 0) st = W.carry;
     else { st.p = j * SUB_BITS; st.c = 0; st.z = 0; }
-    W.info[t].n = decode_span<false>(J.stream, st, sub_limit(J, j), T, J.bpm, nullptr, 0, 0);
+    W.info[t].n = decode_span<false>(J.staged, st, sub_limit(J, j), T, J.bpm, nullptr, 0, 0);
     W.info[t].s = st;
     W.cur[t] = st;
     W.done[t] = 0;
@@ -198,7 +247,7 @@ V5_HOSTDEV void huff_phase_round(int t, int r, HuffWindow &W, const HuffJob &J, 
         return;
     }
     SubState st = W.cur[t];
-    const uint32_t n = decode_span<false>(J.stream, st, sub_limit(J, w0 + (uint32_t)k), T, J.bpm, nullptr, 0, 0);
+    const uint32_t n = decode_span<false>(J.staged, st, sub_limit(J, w0 + (uint32_t)k), T, J.bpm, nullptr, 0, 0);
     if (same_state(st, W.info[k].s)) W.done[t] = 1;                     // synchronised: the rest of the walk is already recorded
     W.info[k].s = st;                                                    // this thread entered k in a state at least as good
     W.info[k].n = n;                                                     // as the recorded one: its block count is the one to keep
@@ -211,7 +260,7 @@ V5_HOSTDEV void huff_phase_write(int t, HuffWindow &W, const HuffJob &J, const D
     const uint32_t j = w0 + (uint32_t)t;
     if (j >= J.nsub) return;
     SubState st = t == 0 ? W.carry : W.info[t - 1].s;
-    decode_span<true>(J.stream, st, sub_limit(J, j), T, J.bpm, J.coef, (int64_t)block0, J.max_blocks);
+    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, (int64_t)block0, J.max_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------- DC prediction
@@ -258,8 +307,8 @@ V5_DEV void idct_rows(const int16_t *ws, int j, uint8_t *dst, int pitch)
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = ws[8 * r + k];
         v5::idct8<1, true>(v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) dst[r * pitch + k] = (uint8_t)v5::clamp255(v[k]);
+        // plane rows are 8-byte aligned (plane offsets are multiples of 16, pitches multiples of 8)
+        *reinterpret_cast<v5::U2 *>(dst + r * pitch) = v5::U2{v5::pack4sat(v[0], v[1], v[2], v[3]), v5::pack4sat(v[4], v[5], v[6], v[7])};
     }
 }
 
@@ -388,6 +437,7 @@ __global__ void __launch_bounds__(1024) unstuff_kernel(const DecImage *images, c
 }
 
 struct HuffSmem {
+    uint32_t words[STAGE_WORDS];           // the window's share of the stream (128 KB + one row)
     DecTabSet T;
     HuffWindow W;
     uint32_t warp_sums[33];
@@ -396,7 +446,8 @@ struct HuffSmem {
 __global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
                                                           const uint32_t *stream_bits, int16_t *coef, int32_t *status)
 {
-    __shared__ HuffSmem S;
+    extern __shared__ __align__(16) uint8_t huff_smem_raw[];
+    HuffSmem &S = *reinterpret_cast<HuffSmem *>(huff_smem_raw);
     const int t = (int)threadIdx.x;
     const DecImage im = images[blockIdx.x];
     {
@@ -406,6 +457,9 @@ __global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images
     }
     HuffJob J;
     J.stream = streams + im.stream_off;
+    J.staged.words = S.words;
+    J.staged.base_word = 0;
+    J.stream_words = (uint32_t)((im.scan_len + 32) >> 2);               // the host reserves scan_len + 32 zeroed bytes
     J.total_bits = stream_bits[blockIdx.x];
     J.nsub = (J.total_bits + SUB_BITS - 1) / SUB_BITS;
     J.bpm = im.bpm;
@@ -419,6 +473,9 @@ __global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images
     }
     __syncthreads();
     for (uint32_t w0 = 0; w0 < J.nsub; w0 += HUFF_NT) {
+        J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+        stage_window(t, HUFF_NT, S.words, J.stream, J.staged.base_word, J.stream_words);
+        __syncthreads();
         huff_phase_first(t, S.W, J, S.T, w0);
         __syncthreads();
         for (int r = 1; r < HUFF_NT; r++) {

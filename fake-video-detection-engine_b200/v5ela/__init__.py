@@ -6,6 +6,9 @@ Public surface:
   as_records / features / combine                                                          (v5ela.records)
   gen_frame / gen_batch / gen_batch_torch  (synthetic keyframes)        (v5ela.synth)
   shard_range / analyze_sharded            (multi-GPU, one process per GPU, NCCL gather)   (v5ela.shard)
+  jpeg.encode_* / jpeg.decode_*            (baseline JPEG codec on the GPU)  (v5ela.jpeg)
+  analyze_jpeg_files(files)                (JPEG bytes in, records out: decode + analyse)   (v5ela.batch)
+  handoff.face_detections_on_device        (V1 crop rule on device-resident frames, §8f-4)  (v5ela.handoff)
 The drop-in node lives in ``nodes/V_nodes/v5_texture_ela.py`` next to this package.
 """
 from .records import RECORD_BYTES, RECORD_DTYPE, as_records, combine, features  # noqa: F401
@@ -13,7 +16,7 @@ from .synth import gen_batch, gen_batch_torch, gen_frame  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must not require the CUDA library (CPU-only tooling, tests)
-    if name in ("analyze_batch", "reduce_records", "get_handle", "spectrum_batch"):
+    if name in ("analyze_batch", "reduce_records", "get_handle", "spectrum_batch", "analyze_jpeg_files"):
         from . import batch
 
         return getattr(batch, name)

@@ -21,8 +21,8 @@ def info(data: bytes):
     """-> (height, width, channels) from the file's headers; raises V5ElaError for corrupt / unsupported files."""
     lib = _abi.load()
     h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-    buf = (ctypes.c_char * len(data)).from_buffer_copy(data)
-    rc = lib.v5ela_jpeg_info(ctypes.addressof(buf), len(data), ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
+    buf = np.frombuffer(data, np.uint8)                                    # no copy
+    rc = lib.v5ela_jpeg_info(buf.ctypes.data, len(data), ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
     if rc != 0:
         raise _abi.V5ElaError(rc, lib.v5ela_status_string(rc).decode())
     return h.value, w.value, c.value

@@ -111,8 +111,12 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     DecTabSet *T = new DecTabSet();
     T->dc[0] = F->dc[0]; T->dc[1] = F->dc[1]; T->ac[0] = F->ac[0]; T->ac[1] = F->ac[1];
     std::vector<int16_t> coef((size_t)im.blocks * 64, 0);
+    std::vector<uint32_t> staged(STAGE_WORDS, 0xA5A5A5A5u);
     HuffJob J;
     J.stream = stream.data();
+    J.staged.words = staged.data();
+    J.staged.base_word = 0;
+    J.stream_words = (uint32_t)(stream.size() / 4);
     J.total_bits = total_bits;
     J.nsub = (total_bits + SUB_BITS - 1) / SUB_BITS;
     J.bpm = im.bpm;
@@ -124,6 +128,8 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     W->base_blocks = 0;
     int max_rounds = 0;
     for (uint32_t w0 = 0; w0 < J.nsub; w0 += HUFF_NT) {
+        J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+        for (int t = 0; t < HUFF_NT; t++) stage_window(t, HUFF_NT, staged.data(), J.stream, J.staged.base_word, J.stream_words);
         for (int t = 0; t < HUFF_NT; t++) huff_phase_first(t, *W, J, *T, w0);
         for (int r = 1; r < HUFF_NT; r++) {
             for (int t = 0; t < HUFF_NT; t++) huff_phase_round(t, r, *W, J, *T, w0);

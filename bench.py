@@ -12,6 +12,7 @@ the NCCL gather of the per-frame records to rank 0.
               frame and the D2H copy of the records are inside the timed region.
   roofline  : fused kernel only — algorithmic bytes (3*H*W + 3144 per frame) / its CUDA-event duration, against the
               measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  e2e_from_jpeg_files : (N=1, extra) the same work starting from JPEG files in host memory — GPU decode + analyse.
   cpu_baseline : the oracle port of the reference's ELA core (Pillow/libjpeg-turbo + NumPy/OpenCV statistics) on all
               host cores, on a bounded sample of the same frames. Reported, not the target.
 """
@@ -308,6 +309,52 @@ def run_native_arm(args):
     e2e_ms = float(t.item())
     ok_e2e = bool(torch.equal(host_records, records.cpu()))
 
+    # ---- the same work starting from JPEG FILES in host memory, the form V1 hands keyframes/crops over in
+    # (cv2.imwrite default quality 95, v1_keyframes_facetrack.py:112,166): only compressed bytes cross PCIe; the GPU
+    # decodes, analyses, and the records come back. N=1 only (an extra figure, not the headline).
+    files_leg = None
+    if world == 1:
+        try:
+            from v5ela import jpeg
+            from v5ela.batch import analyze_jpeg_files
+
+            enc, enc_sizes = jpeg.encode_batch(frames, 95)
+            torch.cuda.synchronize()
+            enc, enc_sizes = enc.cpu().numpy(), enc_sizes.cpu().numpy()
+            # the files sit back to back in one page-locked arena (what a loader that reads files for the GPU would use)
+            offs = [0]
+            for i in range(n_local):
+                offs.append(offs[-1] + (int(enc_sizes[i]) + 63) // 64 * 64)
+            arena = torch.empty(offs[-1], dtype=torch.uint8, pin_memory=True)
+            arena_np = arena.numpy()
+            blobs = []
+            for i in range(n_local):
+                arena_np[offs[i]:offs[i] + enc_sizes[i]] = enc[i, :enc_sizes[i]]
+                blobs.append(arena_np[offs[i]:offs[i] + int(enc_sizes[i])])
+            del enc
+            Kf = max(2, min(K, 5))
+            out = None
+            for _ in range(2):
+                out = analyze_jpeg_files(blobs, quality=QUALITY, device=dev)
+                host_records.copy_(out["records"], non_blocking=True)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(analyze_batch(out["rgb"], quality=QUALITY)["records"].cpu(), host_records))
+            t0 = time.perf_counter()
+            for _ in range(Kf):
+                out = analyze_jpeg_files(blobs, quality=QUALITY, device=dev)
+                host_records.copy_(out["records"], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            files_leg = {"value": n_local * Kf / dt, "unit": UNIT, "steps": Kf,
+                         "h2d_bytes_per_step": int(sum(len(b) for b in blobs)), "d2h_bytes_per_step": n_local * RECORD_BYTES,
+                         "input": f"{n_local} JPEG files (4:2:0, quality 95, mean {sum(len(b) for b in blobs) / n_local / 1e3:.0f} kB) "
+                                  "in one pinned host arena; header parsing on the host, wall clock",
+                         "decode_status_ok": bool((out["status"] == 0).all().item()), "records_match_decoded_frames": same,
+                         "api": "v5ela_jpeg_decode + v5ela_analyze (C ABI)"}
+            del out
+        except Exception as e:  # an extra figure must not take the headline down with it
+            files_leg = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = load_peak()
         value = total * K / (ms_max * 1e-3)
@@ -331,6 +378,8 @@ def run_native_arm(args):
                                  "(DESIGN.md 4.4); int_issue = ncu figures of the committed profile",
                          "int_issue": load_issue_stats()},
         }
+        if files_leg is not None:
+            line["e2e_from_jpeg_files"] = files_leg
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "v5ela.h"
@@ -220,7 +221,7 @@ int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *wid
     if (!file_host || len <= 0 || !height || !width || !channels) return V5ELA_ERR_INVALID;
     v5j::FileInfo *F = new (std::nothrow) v5j::FileInfo();
     if (!F) return V5ELA_ERR_NOMEM;
-    const int rc = v5j::parse_file(file_host, (size_t)len, *F);
+    const int rc = v5j::parse_file(file_host, (size_t)len, *F, true);
     if (rc == v5j::JPEG_OK) {
         *height = F->h;
         *width = F->w;
@@ -236,12 +237,41 @@ namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Host-side helper threads for header parsing and the staging copy of large batches (a 1080p file is ~0.5 MB).
+template <class Fn>
+void parallel_for(int n, size_t bytes_hint, Fn fn)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = nt > 8 ? 8 : nt;
+    if (nt > n) nt = n;
+    if (nt <= 1 || bytes_hint < ((size_t)4 << 20)) {
+        for (int i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++)
+        pool.emplace_back([=]() {
+            for (int i = t; i < n; i += nt) fn(i);
+        });
+    for (auto &th : pool) th.join();
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 struct DecPlan {                               // host-side description of one chunk of files
     std::vector<v5j::DecImage> images;
     std::vector<int> file_index;
     size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0;
     int max_blocks = 0;
-    int64_t max_pixels = 0;
+    int64_t max_groups = 0;                    // 4-pixel groups of the largest image
 };
 
 }  // namespace
@@ -270,10 +300,17 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
     std::vector<v5j::FileInfo> info((size_t)n);
     std::vector<v5j::DecTabSet> tabsets;
     std::vector<std::vector<uint16_t>> qsets;
-    std::vector<int> tab_of((size_t)n), q_of((size_t)n);
+    std::vector<int> tab_of((size_t)n), q_of((size_t)n), parse_rc((size_t)n);
+    size_t total_len = 0;
+    bool all_pinned = true;
     for (int i = 0; i < n; i++) {
         if (!files_host[i] || lens[i] <= 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: null or empty file%s");
-        const int prc = v5j::parse_file(files_host[i], (size_t)lens[i], info[i]);
+        total_len += (size_t)lens[i];
+        all_pinned = all_pinned && is_pinned(files_host[i]);
+    }
+    parallel_for(n, total_len, [&](int i) { parse_rc[(size_t)i] = v5j::parse_file(files_host[i], (size_t)lens[i], info[(size_t)i]); });
+    for (int i = 0; i < n; i++) {
+        const int prc = parse_rc[(size_t)i];
         if (prc != v5j::JPEG_OK) {
             char which[64];
             snprintf(which, sizeof(which), " (file %d)", i);
@@ -335,7 +372,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         P->coef_blocks += (size_t)im.blocks;
         P->plane_bytes += align_up(planes, 16);
         if (im.blocks > P->max_blocks) P->max_blocks = im.blocks;
-        if ((int64_t)F.h * F.w > P->max_pixels) P->max_pixels = (int64_t)F.h * F.w;
+        if ((int64_t)F.h * ((F.w + 3) / 4) > P->max_groups) P->max_groups = (int64_t)F.h * ((F.w + 3) / 4);
         P->images.push_back(im);
         P->file_index.push_back(i);
     }
@@ -347,13 +384,16 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         const size_t off_q = off_tab + align_up(sizeof(v5j::DecTabSet) * tabsets.size(), 16);
         const size_t off_scan = off_q + align_up(256 * qsets.size(), 16);
         const size_t stage_bytes = off_scan + P.scan_bytes;
-        if (s->stage_host_cap < stage_bytes) {
+        // Files in pinned (page-locked) host memory are copied to the device straight from where they are — the caller keeps
+        // them alive until the stream has been synchronised; pageable files go through the handle's pinned staging buffer.
+        const size_t host_stage_bytes = all_pinned ? off_scan : stage_bytes;
+        if (s->stage_host_cap < host_stage_bytes) {
             V5_CUDA(h, cudaEventSynchronize(s->stage_free));
             if (s->stage_host) cudaFreeHost(s->stage_host);
             s->stage_host = nullptr;
             s->stage_host_cap = 0;
-            V5_CUDA(h, cudaHostAlloc((void **)&s->stage_host, stage_bytes + stage_bytes / 4, cudaHostAllocDefault));
-            s->stage_host_cap = stage_bytes + stage_bytes / 4;
+            V5_CUDA(h, cudaHostAlloc((void **)&s->stage_host, host_stage_bytes + host_stage_bytes / 4, cudaHostAllocDefault));
+            s->stage_host_cap = host_stage_bytes + host_stage_bytes / 4;
         }
         if ((rc = ensure(h, (void **)&s->d_stage, &s->stage_cap, stage_bytes))) return rc;
         if ((rc = ensure(h, &s->d_streams, &s->streams_cap, P.stream_bytes))) return rc;
@@ -362,17 +402,25 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         if ((rc = ensure(h, &s->d_bits, &s->bits_cap, sizeof(uint32_t) * (size_t)cn))) return rc;
         if ((rc = ensure(h, &s->d_status, &s->status_cap, sizeof(int32_t) * (size_t)cn))) return rc;
         V5_CUDA(h, cudaEventSynchronize(s->stage_free));                 // the previous upload no longer reads stage_host
-        for (int k = 0; k < cn; k++) {
-            v5j::DecImage &im = P.images[(size_t)k];
-            const int fi = P.file_index[(size_t)k];
-            memcpy(s->stage_host + off_scan + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len);
-            im.scan_off += (int64_t)off_scan;
-        }
+        for (int k = 0; k < cn; k++) P.images[(size_t)k].scan_off += (int64_t)off_scan;
+        if (!all_pinned)
+            parallel_for(cn, P.scan_bytes, [&](int k) {
+                const v5j::DecImage &im = P.images[(size_t)k];
+                const int fi = P.file_index[(size_t)k];
+                memcpy(s->stage_host + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len);
+            });
         memcpy(s->stage_host + off_img, P.images.data(), sizeof(v5j::DecImage) * (size_t)cn);
         memcpy(s->stage_host + off_tab, tabsets.data(), sizeof(v5j::DecTabSet) * tabsets.size());
         for (size_t k = 0; k < qsets.size(); k++) memcpy(s->stage_host + off_q + 256 * k, qsets[k].data(), 256);
-        V5_CUDA(h, cudaMemcpyAsync(s->d_stage, s->stage_host, stage_bytes, cudaMemcpyHostToDevice, st));
+        V5_CUDA(h, cudaMemcpyAsync(s->d_stage, s->stage_host, host_stage_bytes, cudaMemcpyHostToDevice, st));
         V5_CUDA(h, cudaEventRecord(s->stage_free, st));
+        if (all_pinned)
+            for (int k = 0; k < cn; k++) {
+                const v5j::DecImage &im = P.images[(size_t)k];
+                const int fi = P.file_index[(size_t)k];
+                V5_CUDA(h, cudaMemcpyAsync(s->d_stage + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len,
+                                           cudaMemcpyHostToDevice, st));
+            }
         V5_CUDA(h, cudaMemsetAsync(s->d_streams, 0, P.stream_bytes, st));
         V5_CUDA(h, cudaMemsetAsync(s->d_dcoef, 0, P.coef_blocks * 128, st));
 
@@ -391,7 +439,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         v5j::idct_kernel<<<dim3((unsigned)((P.max_blocks + 63) / 64), (unsigned)cn), 256, 0, st>>>(
             d_images, d_q, static_cast<const int16_t *>(s->d_dcoef), static_cast<uint8_t *>(s->d_planes));
         V5_CUDA(h, cudaGetLastError());
-        v5j::colour_kernel<<<dim3((unsigned)((P.max_pixels + 255) / 256), (unsigned)cn), 256, 0, st>>>(
+        v5j::colour_kernel<<<dim3((unsigned)((P.max_groups + 255) / 256), (unsigned)cn), 256, 0, st>>>(
             d_images, static_cast<const uint8_t *>(s->d_planes), d_rgb, d_gray);
         V5_CUDA(h, cudaGetLastError());
         if (d_status)                                                      // chunks keep file order: one contiguous range

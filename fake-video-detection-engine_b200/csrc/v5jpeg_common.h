@@ -179,7 +179,7 @@ struct FileInfo {
 // Parses the marker segments of one file. Supported: 8-bit baseline (SOF0/SOF1 Huffman), one component, or three
 // components sampled 2x2,1x1,1x1 with Cb and Cr sharing tables; a single scan; no restart interval. Everything the
 // reference's writers (cv2.imwrite, PIL save) produce is inside that set; anything else is JPEG_UNSUPPORTED.
-inline int parse_file(const uint8_t *d, size_t len, FileInfo &F)
+inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_only = false)
 {
     uint16_t qt[4][64];
     bool qt_ok[4] = {false, false, false, false};
@@ -272,10 +272,12 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F)
     }
     for (int c = 0; c < (F.ncomp == 3 ? 2 : 1); c++) {
         if (!qt_ok[tq[c]] || !huff[0][td[c]].ok || !huff[1][ta[c]].ok) return JPEG_CORRUPT;
+        if (headers_only) continue;
         memcpy(F.qt[c], qt[tq[c]], sizeof(F.qt[c]));
         if (!make_dec_table(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].n, F.dc[c])) return JPEG_CORRUPT;
         if (!make_dec_table(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].n, F.ac[c])) return JPEG_CORRUPT;
     }
+    if (headers_only) return JPEG_OK;
     if (F.ncomp == 1) {
         memcpy(F.qt[1], F.qt[0], sizeof(F.qt[0]));
         F.dc[1] = F.dc[0];

@@ -367,6 +367,48 @@ V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int 
     out[2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
 }
 
+// Four consecutive pixels x0 .. x0+3 (x0 a multiple of 4) of row y: same arithmetic as pixel_rgb with the chroma loads shared.
+// out: 12 bytes R G B R G B ...; pixels at or beyond the image width are left untouched.
+V5_HOSTDEV void pixels4_rgb(const DecImage &im, const uint8_t *planes, int x0, int y, uint8_t out[12])
+{
+    const uint8_t *yrow = planes + (int64_t)y * im.yw + x0;
+    if (im.ncomp == 1) {
+        for (int k = 0; k < 4 && x0 + k < im.w; k++) out[3 * k] = out[3 * k + 1] = out[3 * k + 2] = yrow[k];
+        return;
+    }
+    const uint8_t *cbp = planes + (int64_t)im.yw * im.yh, *crp = cbp + (int64_t)im.cw * im.ch;
+    const int hc = (im.h + 1) >> 1, wc = (im.w + 1) >> 1, cw = im.cw;
+    const int r = y >> 1, cx0 = x0 >> 1;
+    int nb = (y & 1) ? r + 1 : r - 1;
+    nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
+    const uint8_t *cb_r = cbp + (int64_t)r * cw, *cb_n = cbp + (int64_t)nb * cw, *cr_r = crp + (int64_t)r * cw, *cr_n = crp + (int64_t)nb * cw;
+    int sb[4], sr[4];                                                     // 3 * cur + neighbour row at chroma columns cx0-1 .. cx0+2
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int col = cx0 - 1 + j;
+        col = col < 0 ? 0 : (col > wc - 1 ? wc - 1 : col);
+        sb[j] = 3 * cb_r[col] + cb_n[col];
+        sr[j] = 3 * cr_r[col] + cr_n[col];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (x0 + k >= im.w) break;
+        const int j = 1 + (k >> 1), jn = (k & 1) ? j + 1 : j - 1, bias = (k & 1) ? 7 : 8;
+        int cb, cr;
+        if (wc <= 2) {
+            cb = cb_r[cx0 + (k >> 1)];
+            cr = cr_r[cx0 + (k >> 1)];
+        } else {
+            cb = (3 * sb[j] + sb[jn] + bias) >> 4;
+            cr = (3 * sr[j] + sr[jn] + bias) >> 4;
+        }
+        const int yy = yrow[k], cbd = cb - 128, crd = cr - 128;
+        out[3 * k] = (uint8_t)v5::clamp255(yy + ((91881 * crd + 32768) >> 16));
+        out[3 * k + 1] = (uint8_t)v5::clamp255(yy + ((-22554 * cbd - 46802 * crd + 32768) >> 16));
+        out[3 * k + 2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
+    }
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------- kernels
 __constant__ uint8_t kNaturalToZigzagDev[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
@@ -529,43 +571,68 @@ __global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_
     }
 }
 
-// 64 blocks per CTA, 4 threads per block. grid = (ceil(max blocks / 64), files)
+// 64 blocks per CTA, 4 threads per block; the 8 KB of coefficients and the two quantisation tables are staged in shared
+// memory with 128-bit loads. grid = (ceil(max blocks / 64), files)
 __global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const uint16_t *qtabs, const int16_t *coef, uint8_t *planes)
 {
+    __shared__ __align__(16) int16_t cz[64][64];
     __shared__ int16_t ws[64][64 + 8];
+    __shared__ uint16_t qt[2][64];
     __shared__ uint8_t zz[64];
     const DecImage im = images[blockIdx.y];
+    const int g0 = (int)blockIdx.x * 64;
+    if (g0 >= im.blocks) return;
+    const int nb = im.blocks - g0 < 64 ? im.blocks - g0 : 64;
     if (threadIdx.x < 64) zz[threadIdx.x] = kNaturalToZigzagDev[threadIdx.x];
+    if (threadIdx.x < 128) (&qt[0][0])[threadIdx.x] = qtabs[(int64_t)im.qt * 128 + threadIdx.x];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + (im.coef_off + g0) * 64);
+        uint4 *dst = reinterpret_cast<uint4 *>(&cz[0][0]);
+        for (int i = threadIdx.x; i < nb * 8; i += 256) dst[i] = __ldg(src + i);
+    }
     __syncthreads();
     const int lb = (int)threadIdx.x >> 2, j = (int)threadIdx.x & 3;
-    const int g = (int)blockIdx.x * 64 + lb;
-    const bool active = g < im.blocks;
+    const bool active = lb < nb;
     int pitch = 0, comp = 0;
     int64_t off = 0;
     if (active) {
-        off = block_dest(im, g, pitch, comp);
-        idct_cols(coef + (im.coef_off + g) * 64, qtabs + ((int64_t)im.qt * 2 + (comp ? 1 : 0)) * 64, zz, j, ws[lb]);
+        off = block_dest(im, g0 + lb, pitch, comp);
+        idct_cols(cz[lb], qt[comp ? 1 : 0], zz, j, ws[lb]);
     }
     __syncwarp();
     if (active) idct_rows(ws[lb], j, planes + im.plane_off + off, pitch);
 }
 
-// one thread per pixel. grid = (ceil(max pixels / 256), files)
+// one thread per 4 pixels of a row. grid = (ceil(max pixel groups / 256), files)
 __global__ void __launch_bounds__(256) colour_kernel(const DecImage *images, const uint8_t *planes, uint8_t *rgb_out, uint8_t *gray_out)
 {
     const DecImage im = images[blockIdx.y];
+    const int groups = (im.w + 3) >> 2;
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= (int64_t)im.h * im.w) return;
-    const int y = (int)(i / im.w), x = (int)(i - (int64_t)y * im.w);
+    if (i >= (int64_t)im.h * groups) return;
+    const int y = (int)(i / groups), x0 = 4 * (int)(i - (int64_t)y * groups);
     const uint8_t *pl = planes + im.plane_off;
-    if (im.gray_off >= 0) gray_out[im.gray_off + i] = pl[(int64_t)y * im.yw + x];
+    const int nvalid = im.w - x0 < 4 ? im.w - x0 : 4;
+    const int64_t px = (int64_t)y * im.w + x0;
+    if (im.gray_off >= 0) {
+        uint8_t *d = gray_out + im.gray_off + px;
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(pl + (int64_t)y * im.yw + x0);     // plane rows are 8-byte aligned
+        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t *>(d) = v;
+        else
+            for (int k = 0; k < nvalid; k++) d[k] = (uint8_t)(v >> (8 * k));
+    }
     if (im.rgb_off >= 0) {
-        uint8_t o[3];
-        pixel_rgb(im, pl, x, y, o);
-        uint8_t *d = rgb_out + im.rgb_off + 3 * i;
-        d[0] = o[0];
-        d[1] = o[1];
-        d[2] = o[2];
+        alignas(4) uint8_t o[12];
+        pixels4_rgb(im, pl, x0, y, o);
+        uint8_t *d = rgb_out + im.rgb_off + 3 * px;
+        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+            const uint32_t *ow = reinterpret_cast<const uint32_t *>(o);
+            reinterpret_cast<uint32_t *>(d)[0] = ow[0];
+            reinterpret_cast<uint32_t *>(d)[1] = ow[1];
+            reinterpret_cast<uint32_t *>(d)[2] = ow[2];
+        } else {
+            for (int k = 0; k < 3 * nvalid; k++) d[k] = o[k];
+        }
     }
 }
 #endif  // __CUDACC__

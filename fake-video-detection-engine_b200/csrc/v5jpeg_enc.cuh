@@ -80,6 +80,7 @@ struct alignas(16) CoefSmem {
     V5_HOSTDEV const uint8_t *c(int comp, int row) const { return px + 16 * ENC_TM * 16 + (comp * 8 + row) * (ENC_TM * 8); }
     int16_t ws[ENC_BLOCKS][64 + 8];    // per block workspace, natural order
     uint8_t zz[64];
+    alignas(16) uint8_t rgb[16][3 * 16 * ENC_TM];   // colour only: the strip's pixels, edges replicated
 };
 static_assert(8 * 8 * ENC_BLOCKS <= 16 * ENC_TM * 16 + 2 * 8 * ENC_TM * 8, "the one-component strip must fit the plane area");
 
@@ -94,7 +95,35 @@ V5_HOSTDEV int dummy_source(const EncGeo &g, int mx, int my, int i)
     }
 }
 
-V5_DEV void coef_load_colour(int tid, CoefSmem &S, const CoefParams &p, const uint8_t *frame, int tile_x, int my)
+// Stage the strip's RGB (16 lines x up to 256 px) in shared memory — 32-bit loads when the frame allows it — with the
+// right / bottom edges replicated (A.3), then convert 2x2 quads from there.
+V5_DEV void coef_stage_rgb(int tid, CoefSmem &S, const CoefParams &p, const uint8_t *frame, int tile_x, int my)
+{
+    const EncGeo &g = p.g;
+    const int x_begin = 16 * ENC_TM * tile_x;                            // first pixel column of the strip
+    int npx = g.w - x_begin;                                             // real pixels in the strip
+    npx = npx > 16 * ENC_TM ? 16 * ENC_TM : npx;
+    const int nbytes = 3 * npx;
+    const bool vec = ((reinterpret_cast<uintptr_t>(frame) | (uintptr_t)p.row_stride) & 3) == 0;   // 3 * x_begin is a multiple of 4
+    for (int l = 0; l < 16; l++) {
+        int y = 16 * my + l;
+        y = y < g.h - 1 ? y : g.h - 1;
+        const uint8_t *src = frame + (int64_t)y * p.row_stride + 3 * x_begin;
+        uint8_t *dst = S.rgb[l];
+        int done = 0;
+        if (vec) {
+            const int nw = nbytes >> 2;
+            for (int i = tid; i < nw; i += ENC_NT) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+            done = nw << 2;
+        }
+        for (int i = done + tid; i < nbytes; i += ENC_NT) dst[i] = src[i];
+        // columns right of the image replicate pixel W-1 up to the next MCU boundary
+        const int pad_px = 16 * ((npx + 15) / 16) - npx;
+        for (int i = tid; i < 3 * pad_px; i += ENC_NT) dst[nbytes + i] = src[nbytes - 3 + (i % 3)];
+    }
+}
+
+V5_DEV void coef_load_colour(int tid, CoefSmem &S, const CoefParams &p, int tile_x, int my)
 {
     const EncGeo &g = p.g;
     const int hc1 = ((g.h + 1) >> 1) - 1;
@@ -103,24 +132,26 @@ V5_DEV void coef_load_colour(int tid, CoefSmem &S, const CoefParams &p, const ui
         const int qy = q / (8 * ENC_TM), qx = q - qy * (8 * ENC_TM);
         if (qx >= 8 * mcus) continue;
         const int gqx = 8 * ENC_TM * tile_x + qx, j = 8 * my + qy;
-        const int x0 = 2 * gqx < g.w - 1 ? 2 * gqx : g.w - 1, x1 = 2 * gqx + 1 < g.w - 1 ? 2 * gqx + 1 : g.w - 1;
-        const int ly0 = 2 * j < g.h - 1 ? 2 * j : g.h - 1, ly1 = 2 * j + 1 < g.h - 1 ? 2 * j + 1 : g.h - 1;
+        // staged lines already replicate row H-1; the chroma rule differs below the image: it replicates the DOWNSAMPLED
+        // last row, i.e. averages rows (2 jc, min(2 jc + 1, H-1)) with jc = min(j, Hc-1)
         const int jc = j < hc1 ? j : hc1;
-        const int cy0 = 2 * jc, cy1 = 2 * jc + 1 < g.h - 1 ? 2 * jc + 1 : g.h - 1;
+        int l0 = 2 * jc - 16 * my, l1 = (2 * jc + 1 < g.h - 1 ? 2 * jc + 1 : g.h - 1) - 16 * my;
         int cb = 0, cr = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint8_t *px = frame + (int64_t)((k & 2) ? ly1 : ly0) * p.row_stride + 3 * ((k & 1) ? x1 : x0);
+            const uint8_t *px = &S.rgb[2 * qy + (k >> 1)][3 * (2 * qx + (k & 1))];
             const int r = px[0], gg = px[1], b = px[2];
             S.y(2 * qy + (k >> 1))[2 * qx + (k & 1)] = (uint8_t)((19595 * r + 38470 * gg + 7471 * b + 32768) >> 16);
             cb += (-11059 * r - 21709 * gg + 32768 * b + (128 << 16) + 32767) >> 16;
             cr += (32768 * r - 27439 * gg - 5329 * b + (128 << 16) + 32767) >> 16;
         }
-        if (cy0 != ly0 || cy1 != ly1) {                                  // padding rows below the image (A.3)
+        if (l0 != 2 * qy || l1 != 2 * qy + 1) {                          // padding rows below the image (A.3)
             cb = cr = 0;
+            // rows l0 / l1 may lie in an earlier MCU row only when this whole MCU row is padding, which never happens
+            // (mcuy = ceil(H / 16)), so they are inside the staged 16 lines
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint8_t *px = frame + (int64_t)((k & 2) ? cy1 : cy0) * p.row_stride + 3 * ((k & 1) ? x1 : x0);
+                const uint8_t *px = &S.rgb[(k & 2) ? l1 : l0][3 * (2 * qx + (k & 1))];
                 const int r = px[0], gg = px[1], b = px[2];
                 cb += (-11059 * r - 21709 * gg + 32768 * b + (128 << 16) + 32767) >> 16;
                 cr += (32768 * r - 27439 * gg - 5329 * b + (128 << 16) + 32767) >> 16;
@@ -292,7 +323,38 @@ struct BitSink {
     }
 };
 
+// Bit k set <=> coefficient k (zigzag order) of the block is non-zero. The block is 128 aligned bytes.
+V5_HOSTDEV uint64_t nonzero_mask(const int16_t *coef)
+{
+    uint64_t m = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(coef) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t b = ((w[k] & 0xffffu) ? 1u : 0u) | ((w[k] >> 16) ? 2u : 0u);
+            m |= (uint64_t)b << (8 * i + 2 * k);
+        }
+    }
+#else
+    for (int k = 0; k < 64; k++) m |= (uint64_t)(coef[k] != 0) << k;
+#endif
+    return m;
+}
+
+V5_HOSTDEV int lowest_bit(uint64_t m)
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
+
 // coef: the block's 64 coefficients in zigzag order; pred: DC of the predecessor block (0 at the start of the scan).
+// Only the non-zero coefficients are visited (T.81 F.1.2.2: run lengths are the gaps between them).
 template <class Sink>
 V5_HOSTDEV void encode_block(const int16_t *coef, int pred, const uint32_t *dc_tab, const uint32_t *ac_tab, Sink &sink)
 {
@@ -303,25 +365,25 @@ V5_HOSTDEV void encode_block(const int16_t *coef, int pred, const uint32_t *dc_t
         const uint32_t e = dc_tab[nb];
         sink.put(((e & 0xffffu) << nb) | ((uint32_t)t2 & ((1u << nb) - 1u)), (int)(e >> 16) + nb);
     }
-    int last = 63;
-    while (last > 0 && coef[last] == 0) last--;
-    int run = 0;
-    for (int k = 1; k <= last; k++) {
-        int t = coef[k];
-        if (t == 0) { run++; continue; }
+    uint64_t mask = nonzero_mask(coef) & ~(uint64_t)1;
+    int prev = 0;
+    while (mask) {
+        const int k = lowest_bit(mask);
+        mask &= mask - 1;
+        int run = k - prev - 1;
+        prev = k;
         while (run > 15) {
             const uint32_t z = ac_tab[0xF0];
             sink.put(z & 0xffffu, (int)(z >> 16));
             run -= 16;
         }
-        int t2 = t;
+        int t = coef[k], t2 = t;
         if (t < 0) { t = -t; t2--; }
         const int nb = bit_length((uint32_t)t);
         const uint32_t e = ac_tab[(run << 4) + nb];
         sink.put(((e & 0xffffu) << nb) | ((uint32_t)t2 & ((1u << nb) - 1u)), (int)(e >> 16) + nb);
-        run = 0;
     }
-    if (last < 63) {
+    if (prev < 63) {
         const uint32_t e = ac_tab[0];
         sink.put(e & 0xffffu, (int)(e >> 16));
     }
@@ -344,8 +406,13 @@ __global__ void __launch_bounds__(ENC_NT) coef_kernel(const __grid_constant__ Co
     const int mx0 = tile_x * per;
     const int mcus = g.mcux - mx0 < per ? g.mcux - mx0 : per;
     const int nblocks = mcus * g.bpm;
-    if (g.ncomp == 3) coef_load_colour(tid, S, p, frame, tile_x, my);
-    else coef_load_gray(tid, S, p, frame, tile_x, my);
+    if (g.ncomp == 3) {
+        coef_stage_rgb(tid, S, p, frame, tile_x, my);
+        __syncthreads();
+        coef_load_colour(tid, S, p, tile_x, my);
+    } else {
+        coef_load_gray(tid, S, p, frame, tile_x, my);
+    }
     __syncthreads();
     coef_rows(tid, S, g.ncomp, nblocks);
     __syncthreads();

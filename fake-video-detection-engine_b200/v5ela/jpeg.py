@@ -29,9 +29,10 @@ def info(data: bytes):
 
 
 def _file_table(files):
-    """ctypes arrays (pointers, lengths) over a list of bytes objects; the first return value keeps the buffers alive."""
+    """ctypes arrays (pointers, lengths) over a list of bytes objects / uint8 arrays (e.g. views into one pinned arena); the
+    first return value keeps the buffers alive."""
     n = len(files)
-    keep = [np.frombuffer(f, np.uint8) for f in files]
+    keep = [f if isinstance(f, np.ndarray) else np.frombuffer(f, np.uint8) for f in files]
     ptrs = (ctypes.c_void_p * n)(*[k.ctypes.data for k in keep])
     lens = (ctypes.c_int64 * n)(*[len(f) for f in files])
     return keep, ptrs, lens
@@ -122,8 +123,9 @@ def decode_host(files, want_rgb: bool = True, want_gray: bool = False, device: i
 
 
 def decode_batch(files, device=0, want_rgb: bool = True, want_gray: bool = False):
-    """files: list of bytes, all the same size -> {'rgb': uint8 CUDA tensor [N,H,W,3], 'gray': [N,H,W], 'status': int32 [N]}
-    asynchronous on the current stream (header parsing and the upload of the compressed bytes happen on the calling thread)."""
+    """files: list of bytes (or uint8 arrays), all the same size -> {'rgb': uint8 CUDA tensor [N,H,W,3], 'gray': [N,H,W],
+    'status': int32 [N]}, asynchronous on the current stream. Header parsing happens on the calling thread; pageable files are
+    staged before the call returns, files that are views into pinned memory are read asynchronously (keep the arena alive)."""
     import torch
 
     from .batch import get_handle

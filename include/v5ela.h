@@ -168,6 +168,9 @@ V5ELA_API int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, i
  * interval — everything PIL's and OpenCV's writers produce by default; anything else returns V5ELA_ERR_UNSUPPORTED and
  * v5ela_last_error names the file.
  *   files_host / lens : n complete JPEG files in HOST memory (they come from disk); sizes may differ from file to file.
+ *             Files that all live in page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied
+ *             to the device asynchronously from where they are — keep them alive until the stream has been synchronised;
+ *             pageable files are staged through a pinned buffer inside the handle before the call returns.
  *   d_rgb   : optional DEVICE buffer; file i is decoded to RGB (HWC; a one-component file is replicated) at byte offset
  *             rgb_offsets[i], or tightly packed in file order when rgb_offsets is NULL.
  *   d_gray  : optional DEVICE buffer; the luma plane alone (what IMREAD_GRAYSCALE returns), offsets likewise.

@@ -37,9 +37,11 @@ extern "C" int64_t v5jemu_encode(const uint8_t *img, int h, int w, int channels,
             memset(S, 0xA5, sizeof(CoefSmem));                              // poison
             memcpy(S->zz, kZigzag, 64);
             const int mx0 = tile_x * per, mcus = g.mcux - mx0 < per ? g.mcux - mx0 : per, nblocks = mcus * g.bpm;
-            for (int t = 0; t < ENC_NT; t++) {
-                if (channels == 3) coef_load_colour(t, *S, p, img, tile_x, my);
-                else coef_load_gray(t, *S, p, img, tile_x, my);
+            if (channels == 3) {
+                for (int t = 0; t < ENC_NT; t++) coef_stage_rgb(t, *S, p, img, tile_x, my);
+                for (int t = 0; t < ENC_NT; t++) coef_load_colour(t, *S, p, tile_x, my);
+            } else {
+                for (int t = 0; t < ENC_NT; t++) coef_load_gray(t, *S, p, img, tile_x, my);
             }
             for (int t = 0; t < ENC_NT; t++) coef_rows(t, *S, g.ncomp, nblocks);
             for (int t = 0; t < ENC_NT; t++) coef_cols(t, *S, p, nblocks);
@@ -165,9 +167,16 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
         for (int j = 0; j < 4; j++) idct_rows(ws, j, planes.data() + off, pitch);
     }
     for (int y = 0; y < im.h; y++)
-        for (int x = 0; x < im.w; x++) {
-            if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
-            if (rgb_out) pixel_rgb(im, planes.data(), x, y, rgb_out + ((size_t)y * im.w + x) * 3);
+        for (int x0 = 0; x0 < im.w; x0 += 4) {
+            uint8_t o[12], single[3];
+            pixels4_rgb(im, planes.data(), x0, y, o);                       // what the kernel runs
+            for (int k = 0; k < 4 && x0 + k < im.w; k++) {
+                const int x = x0 + k;
+                if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
+                pixel_rgb(im, planes.data(), x, y, single);                 // the one-pixel statement of the same arithmetic
+                if (memcmp(single, o + 3 * k, 3)) return -4;
+                if (rgb_out) memcpy(rgb_out + ((size_t)y * im.w + x) * 3, o + 3 * k, 3);
+            }
         }
     delete W; delete T; delete F;
     return ok ? 0 : -3;

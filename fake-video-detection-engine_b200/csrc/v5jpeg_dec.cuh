@@ -153,36 +153,30 @@ template <bool WRITE, class Src>
 V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
                                 int64_t block0, int64_t max_blocks)
 {
+    // One loop body for DC and AC symbols, selects instead of branches: the threads of a warp sit at unrelated places of
+    // their blocks, and every divergent path would be paid for by all of them.
+    //   DC symbol  = size;              run 0
+    //   AC symbol  = run << 4 | size;   00 = end of block, F0 = sixteen zeros (run 15, no value: the ++ below makes 16)
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
     while (p < limit) {
         const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
+        const bool is_dc = z == 0;
+        const DecTable &tab = is_dc ? T.dc[comp] : T.ac[comp];
         const uint32_t win = stream.window(p);
         int len;
-        if (z == 0) {
-            int sz = huff_symbol(T.dc[comp], win, len);
-            if (sz > 15) sz = 15;
-            if (WRITE && sz && block0 + done < max_blocks) {
-                const int v = (int)((win << len) >> (32 - sz));
-                coef[(block0 + done) * 64] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
-            }
-            p += (uint32_t)(len + sz);
-            z = 1;
-        } else {
-            const int rs = huff_symbol(T.ac[comp], win, len), r = rs >> 4, sz = rs & 15;
-            if (sz == 0) {
-                z = r == 15 ? z + 16 : 64;                               // ZRL / EOB
-                p += (uint32_t)len;
-            } else {
-                z += r;
-                if (WRITE && z < 64 && block0 + done < max_blocks) {
-                    const int v = (int)((win << len) >> (32 - sz));
-                    coef[(block0 + done) * 64 + z] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
-                }
-                z++;
-                p += (uint32_t)(len + sz);
-            }
+        const int sym = huff_symbol(tab, win, len);
+        const int run = is_dc ? 0 : sym >> 4;
+        int sz = is_dc ? sym : sym & 15;
+        sz = sz > 15 ? 15 : sz;
+        const bool eob = !is_dc && sym == 0;
+        z = eob ? 64 : z + run;
+        if (WRITE && sz && z < 64 && block0 + done < max_blocks) {
+            const int v = (int)((win << len) >> (32 - sz));
+            coef[(block0 + done) * 64 + z] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
         }
+        z++;
+        p += (uint32_t)(len + sz);
         if (z >= 64) {
             z = 0;
             c = c + 1 == bpm ? 0 : c + 1;
@@ -483,6 +477,8 @@ struct HuffSmem {
     DecTabSet T;
     HuffWindow W;
     uint32_t warp_sums[33];
+    uint32_t n_live;
+    uint16_t live[HUFF_NT];                // subsequences still walking (rounds >= 2)
 };
 
 __global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
@@ -520,9 +516,20 @@ __global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images
         __syncthreads();
         huff_phase_first(t, S.W, J, S.T, w0);
         __syncthreads();
-        for (int r = 1; r < HUFF_NT; r++) {
-            huff_phase_round(t, r, S.W, J, S.T, w0);
-            if (__syncthreads_and(S.W.done[t])) break;
+        // Round 1: almost every thread still walks. From round 2 on only the few subsequences that have not met a recorded
+        // state keep going: their indices are compacted into a list so that they share a few warps instead of keeping
+        // one lane busy in many.
+        huff_phase_round(t, 1, S.W, J, S.T, w0);
+        __syncthreads();
+        for (int r = 2; r < HUFF_NT; r++) {
+            if (t == 0) S.n_live = 0;
+            __syncthreads();
+            if (!S.W.done[t]) S.live[atomicAdd(&S.n_live, 1u)] = (uint16_t)t;
+            __syncthreads();
+            const uint32_t n_live = S.n_live;
+            if (n_live == 0) break;
+            if ((uint32_t)t < n_live) huff_phase_round((int)S.live[t], r, S.W, J, S.T, w0);
+            __syncthreads();
         }
         const bool active = w0 + (uint32_t)t < J.nsub;
         uint32_t sum;

@@ -78,9 +78,12 @@ struct alignas(16) CoefSmem {
     V5_HOSTDEV uint8_t *c(int comp, int row) { return px + 16 * ENC_TM * 16 + (comp * 8 + row) * (ENC_TM * 8); }
     V5_HOSTDEV const uint8_t *y(int row) const { return px + row * (ENC_TM * 16); }
     V5_HOSTDEV const uint8_t *c(int comp, int row) const { return px + 16 * ENC_TM * 16 + (comp * 8 + row) * (ENC_TM * 8); }
-    int16_t ws[ENC_BLOCKS][64 + 8];    // per block workspace, natural order
+    alignas(16) int16_t ws[ENC_BLOCKS][64 + 8];    // per block workspace, natural order (row stride 16 B, block stride 144 B)
     uint8_t zz[64];
     alignas(16) uint8_t rgb[16][3 * 16 * ENC_TM];   // colour only: the strip's pixels, edges replicated
+    // exact-division constants {recip, bias, b, -} per coefficient, [0] luma [1] chroma: one 128-bit shared load each
+    // (read straight from the kernel parameters they would be divergent constant-bank loads, which throttle the MIO queue)
+    alignas(16) uint32_t q[2][64][4];
 };
 static_assert(8 * 8 * ENC_BLOCKS <= 16 * ENC_TM * 16 + 2 * 8 * ENC_TM * 8, "the one-component strip must fit the plane area");
 
@@ -105,61 +108,50 @@ V5_DEV void coef_stage_rgb(int tid, CoefSmem &S, const CoefParams &p, const uint
     npx = npx > 16 * ENC_TM ? 16 * ENC_TM : npx;
     const int nbytes = 3 * npx;
     const bool vec = ((reinterpret_cast<uintptr_t>(frame) | (uintptr_t)p.row_stride) & 3) == 0;   // 3 * x_begin is a multiple of 4
-    for (int l = 0; l < 16; l++) {
+    const int nw = vec ? nbytes >> 2 : 0;                                // 32-bit words per line
+    const int pad3 = 3 * (16 * ((npx + 15) / 16) - npx);                 // replicate pixel W-1 up to the next MCU boundary
+    const int64_t col0 = 3 * (int64_t)x_begin;
+    for (int e = tid; e < 16 * nw; e += ENC_NT) {
+        const int l = e / nw, i = e - l * nw;
         int y = 16 * my + l;
         y = y < g.h - 1 ? y : g.h - 1;
-        const uint8_t *src = frame + (int64_t)y * p.row_stride + 3 * x_begin;
-        uint8_t *dst = S.rgb[l];
-        int done = 0;
-        if (vec) {
-            const int nw = nbytes >> 2;
-            for (int i = tid; i < nw; i += ENC_NT) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
-            done = nw << 2;
-        }
-        for (int i = done + tid; i < nbytes; i += ENC_NT) dst[i] = src[i];
-        // columns right of the image replicate pixel W-1 up to the next MCU boundary
-        const int pad_px = 16 * ((npx + 15) / 16) - npx;
-        for (int i = tid; i < 3 * pad_px; i += ENC_NT) dst[nbytes + i] = src[nbytes - 3 + (i % 3)];
+        reinterpret_cast<uint32_t *>(S.rgb[l])[i] = reinterpret_cast<const uint32_t *>(frame + (int64_t)y * p.row_stride + col0)[i];
+    }
+    const int rest = nbytes - 4 * nw + pad3;                             // bytes per line not covered by the word copies
+    for (int e = tid; e < 16 * rest; e += ENC_NT) {
+        const int l = e / rest, i = 4 * nw + (e - l * rest);
+        int y = 16 * my + l;
+        y = y < g.h - 1 ? y : g.h - 1;
+        const uint8_t *src = frame + (int64_t)y * p.row_stride + col0;
+        S.rgb[l][i] = i < nbytes ? src[i] : src[nbytes - 3 + ((i - nbytes) % 3)];
     }
 }
 
+// units of 2 lines x 8 px through the fused kernel's packed-byte conversion (v5::convert8x2: dp2a colour conversion,
+// h2v2 box filter with the 1,2,1,2 bias)
 V5_DEV void coef_load_colour(int tid, CoefSmem &S, const CoefParams &p, int tile_x, int my)
 {
     const EncGeo &g = p.g;
     const int hc1 = ((g.h + 1) >> 1) - 1;
     const int mcus = g.mcux - tile_x * ENC_TM < ENC_TM ? g.mcux - tile_x * ENC_TM : ENC_TM;
-    for (int q = tid; q < 8 * 8 * ENC_TM; q += ENC_NT) {                 // one 2x2 pixel quad per step
-        const int qy = q / (8 * ENC_TM), qx = q - qy * (8 * ENC_TM);
-        if (qx >= 8 * mcus) continue;
-        const int gqx = 8 * ENC_TM * tile_x + qx, j = 8 * my + qy;
-        // staged lines already replicate row H-1; the chroma rule differs below the image: it replicates the DOWNSAMPLED
-        // last row, i.e. averages rows (2 jc, min(2 jc + 1, H-1)) with jc = min(j, Hc-1)
-        const int jc = j < hc1 ? j : hc1;
-        int l0 = 2 * jc - 16 * my, l1 = (2 * jc + 1 < g.h - 1 ? 2 * jc + 1 : g.h - 1) - 16 * my;
-        int cb = 0, cr = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint8_t *px = &S.rgb[2 * qy + (k >> 1)][3 * (2 * qx + (k & 1))];
-            const int r = px[0], gg = px[1], b = px[2];
-            S.y(2 * qy + (k >> 1))[2 * qx + (k & 1)] = (uint8_t)((19595 * r + 38470 * gg + 7471 * b + 32768) >> 16);
-            cb += (-11059 * r - 21709 * gg + 32768 * b + (128 << 16) + 32767) >> 16;
-            cr += (32768 * r - 27439 * gg - 5329 * b + (128 << 16) + 32767) >> 16;
+    for (int u = tid; u < 8 * 2 * ENC_TM; u += ENC_NT) {
+        const int li = u / (2 * ENC_TM), ox = u - li * (2 * ENC_TM);
+        if (ox >= 2 * mcus) continue;
+        U2 y0, y1;
+        uint32_t cb, cr;
+        v5::convert8x2<true, true>(&S.rgb[2 * li][24 * ox], &S.rgb[2 * li + 1][24 * ox], y0, y1, cb, cr);
+        // staged lines already replicate row H-1; below the image the chroma rule differs: it replicates the DOWNSAMPLED last
+        // row, i.e. averages rows (2 jc, min(2 jc + 1, H-1)) with jc = min(j, Hc-1) — both inside this MCU row's 16 lines
+        const int j = 8 * my + li, jc = j < hc1 ? j : hc1;
+        const int l0 = 2 * jc - 16 * my, l1 = (2 * jc + 1 < g.h - 1 ? 2 * jc + 1 : g.h - 1) - 16 * my;
+        if (l0 != 2 * li || l1 != 2 * li + 1) {
+            U2 d0, d1;
+            v5::convert8x2<false, true>(&S.rgb[l0][24 * ox], &S.rgb[l1][24 * ox], d0, d1, cb, cr);
         }
-        if (l0 != 2 * qy || l1 != 2 * qy + 1) {                          // padding rows below the image (A.3)
-            cb = cr = 0;
-            // rows l0 / l1 may lie in an earlier MCU row only when this whole MCU row is padding, which never happens
-            // (mcuy = ceil(H / 16)), so they are inside the staged 16 lines
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint8_t *px = &S.rgb[(k & 2) ? l1 : l0][3 * (2 * qx + (k & 1))];
-                const int r = px[0], gg = px[1], b = px[2];
-                cb += (-11059 * r - 21709 * gg + 32768 * b + (128 << 16) + 32767) >> 16;
-                cr += (32768 * r - 27439 * gg - 5329 * b + (128 << 16) + 32767) >> 16;
-            }
-        }
-        const int bias = 1 + (gqx & 1);
-        S.c(0, qy)[qx] = (uint8_t)((cb + bias) >> 2);
-        S.c(1, qy)[qx] = (uint8_t)((cr + bias) >> 2);
+        *reinterpret_cast<U2 *>(S.y(2 * li) + 8 * ox) = y0;
+        *reinterpret_cast<U2 *>(S.y(2 * li + 1) + 8 * ox) = y1;
+        *reinterpret_cast<uint32_t *>(S.c(0, li) + 4 * ox) = cb;
+        *reinterpret_cast<uint32_t *>(S.c(1, li) + 4 * ox) = cr;
     }
 }
 
@@ -173,6 +165,17 @@ V5_DEV void coef_load_gray(int tid, CoefSmem &S, const CoefParams &p, const uint
         if (x >= 8 * blocks) continue;
         const int gx = 8 * ENC_BLOCKS * tile_x + x, gy = 8 * my + y;
         plane[y * (8 * ENC_BLOCKS) + x] = frame[(int64_t)(gy < g.h - 1 ? gy : g.h - 1) * p.row_stride + (gx < g.w - 1 ? gx : g.w - 1)];
+    }
+}
+
+V5_DEV void coef_load_quant(int tid, CoefSmem &S, const CoefParams &p)
+{
+    if (tid < 128) {
+        const int t = tid >> 6, i = tid & 63;
+        S.q[t][i][0] = p.q[t].recip[i];
+        S.q[t][i][1] = (uint32_t)p.q[t].bias[i];
+        S.q[t][i][2] = (uint32_t)p.q[t].b[i];
+        S.q[t][i][3] = 0;
     }
 }
 
@@ -192,7 +195,7 @@ V5_DEV const uint8_t *coef_block_src(const CoefSmem &S, int ncomp, int b, int &p
     return S.c(i - 4, 0) + 8 * m;
 }
 
-// thread (b, j): rows 2j, 2j+1 of block b -> ws (row pass of the forward DCT)
+// thread (b, j): rows 2j, 2j+1 of block b -> ws (row pass of the forward DCT); 64-bit loads, 128-bit stores
 V5_DEV void coef_rows(int tid, CoefSmem &S, int ncomp, int nblocks)
 {
     const int b = tid >> 2, j = tid & 3;
@@ -202,34 +205,40 @@ V5_DEV void coef_rows(int tid, CoefSmem &S, int ncomp, int nblocks)
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const int r = 2 * j + rr;
+        const U2 w = *reinterpret_cast<const U2 *>(src + r * pitch);
         int v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = src[r * pitch + k];
+        for (int k = 0; k < 4; k++) {
+            v[k] = (int)v5::byte_of(w.x, k);
+            v[4 + k] = (int)v5::byte_of(w.y, k);
+        }
         v5::fdct8<1, true>(v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) S.ws[b][8 * r + k] = (int16_t)v[k];
+        *reinterpret_cast<U4 *>(&S.ws[b][8 * r]) = U4{v5::pack_s16(v[0], v[1]), v5::pack_s16(v[2], v[3]), v5::pack_s16(v[4], v[5]), v5::pack_s16(v[6], v[7])};
     }
 }
 
-// thread (b, j): columns 2j, 2j+1 -> column pass, exact quantisation, back into ws
+// thread (b, j): columns 2j, 2j+1 (one 32-bit word per row) -> column pass, exact quantisation, back into ws
 V5_DEV void coef_cols(int tid, CoefSmem &S, const CoefParams &p, int nblocks)
 {
     const int b = tid >> 2, j = tid & 3;
     if (b >= nblocks) return;
-    const EncQuant &q = p.q[(p.g.ncomp == 3 && (b % 6) >= 4) ? 1 : 0];
+    const uint32_t(*q)[4] = S.q[(p.g.ncomp == 3 && (b % 6) >= 4) ? 1 : 0];
+    uint32_t *wsw = reinterpret_cast<uint32_t *>(S.ws[b]);               // row k = words 4k .. 4k+3
+    int a[8], c[8];
 #pragma unroll
-    for (int cc = 0; cc < 2; cc++) {
-        const int c = 2 * j + cc;
-        int v[8];
+    for (int k = 0; k < 8; k++) {
+        const uint32_t w = wsw[4 * k + j];
+        a[k] = v5::s16_lo(w);
+        c[k] = v5::s16_hi(w);
+    }
+    v5::fdct8<1, false>(a);
+    v5::fdct8<1, false>(c);
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = S.ws[b][8 * k + c];
-        v5::fdct8<1, false>(v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int i = 8 * k + c;
-            const uint32_t x = (uint32_t)(v[k] + (v[k] >> 31) + q.bias[i]);
-            S.ws[b][i] = (int16_t)((int)v5::umulhi32(x, q.recip[i]) - q.b[i]);
-        }
+    for (int k = 0; k < 8; k++) {
+        const int i = 8 * k + 2 * j;
+        const U4 qa = *reinterpret_cast<const U4 *>(q[i]), qc = *reinterpret_cast<const U4 *>(q[i + 1]);
+        const uint32_t xa = (uint32_t)(a[k] + (a[k] >> 31) + (int)qa.y), xc = (uint32_t)(c[k] + (c[k] >> 31) + (int)qc.y);
+        wsw[4 * k + j] = v5::pack_s16((int)v5::umulhi32(xa, qa.x) - (int)qa.z, (int)v5::umulhi32(xc, qc.x) - (int)qc.z);
     }
 }
 
@@ -402,6 +411,7 @@ __global__ void __launch_bounds__(ENC_NT) coef_kernel(const __grid_constant__ Co
     const EncGeo &g = p.g;
     const uint8_t *frame = p.img + (int64_t)img * p.frame_stride;
     if (tid < 64) S.zz[tid] = kZigzagDev[tid];
+    coef_load_quant(tid, S, p);
     const int per = g.ncomp == 3 ? ENC_TM : ENC_BLOCKS;                  // MCUs per strip
     const int mx0 = tile_x * per;
     const int mcus = g.mcux - mx0 < per ? g.mcux - mx0 : per;

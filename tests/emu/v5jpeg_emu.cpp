@@ -36,6 +36,7 @@ extern "C" int64_t v5jemu_encode(const uint8_t *img, int h, int w, int channels,
         for (int tile_x = 0; tile_x * per < g.mcux; tile_x++) {
             memset(S, 0xA5, sizeof(CoefSmem));                              // poison
             memcpy(S->zz, kZigzag, 64);
+            for (int t = 0; t < ENC_NT; t++) coef_load_quant(t, *S, p);
             const int mx0 = tile_x * per, mcus = g.mcux - mx0 < per ? g.mcux - mx0 : per, nblocks = mcus * g.bpm;
             if (channels == 3) {
                 for (int t = 0; t < ENC_NT; t++) coef_stage_rgb(t, *S, p, img, tile_x, my);

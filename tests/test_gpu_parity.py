@@ -255,3 +255,44 @@ def test_repeated_calls_are_deterministic():
         b = v5ela.analyze_batch(t)["records"]
         torch.cuda.synchronize()
         assert torch.equal(a, b)
+
+
+def test_two_host_threads_with_their_own_handles():
+    """The node may run next to V2/V3/V4 on LangGraph's worker threads: one handle per thread (thread-local in
+    v5ela.batch / v5ela.host), concurrent calls, identical results."""
+    import threading
+
+    import torch
+    import v5ela
+    from v5ela import host as v5host, jpeg
+
+    frames = gen_batch(20, 6, 200, 312, seed=9)
+    ref_recs, ref_resid = c_oracle.analyze(frames, 90, want_residual=True)
+    ref_file = c_oracle.jpeg_encode(frames[0], 75)
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(8):
+                if kind == 0:
+                    t = torch.from_numpy(frames).cuda()
+                    out = v5ela.analyze_batch(t, quality=90, want_residual=True)
+                    torch.cuda.synchronize()
+                    assert np.array_equal(out["residual"].cpu().numpy(), ref_resid)
+                    assert as_records(out["records"].cpu()).tobytes() == ref_recs.tobytes()
+                elif kind == 1:
+                    recs, resid, _ = v5host.analyze_frames_host(frames, quality=90, want_residual=True)
+                    assert recs.tobytes() == ref_recs.tobytes() and np.array_equal(resid, ref_resid)
+                else:
+                    data = jpeg.encode_host(frames[:1], 75)[0]
+                    assert data == ref_file
+                    assert np.array_equal(jpeg.decode_host([data])[0]["rgb"], c_oracle.jpeg_decode(ref_file)["rgb"])
+        except Exception as e:  # noqa: BLE001
+            errors.append((kind, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k % 3,)) for k in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert errors == []

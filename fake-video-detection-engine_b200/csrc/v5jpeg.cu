@@ -29,9 +29,13 @@ struct v5jpeg_state {
     size_t img_cap = 0, out_cap = 0, sizes_cap = 0;
     // decoder: one pinned staging buffer (descriptors | table sets | quantisation tables | scan segments) mirrored on the
     // device, plus the per-batch workspace (unstuffed streams, coefficients, sample planes)
-    uint8_t *stage_host = nullptr, *d_stage = nullptr;
-    size_t stage_host_cap = 0, stage_cap = 0;
-    cudaEvent_t stage_free = nullptr;          // the last upload from stage_host has completed
+    // Two of each, used alternately: the upload of one batch (on upload_stream) overlaps the kernels of the previous one.
+    uint8_t *stage_host[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
+    size_t stage_host_cap[2] = {0, 0}, stage_cap[2] = {0, 0};
+    cudaEvent_t uploaded[2] = {nullptr, nullptr};   // the upload into d_stage[b] (and out of stage_host[b]) has completed
+    cudaEvent_t consumed[2] = {nullptr, nullptr};   // the kernels that read d_stage[b] have completed
+    cudaStream_t upload_stream = nullptr;
+    int toggle = 0;
     void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr;
     size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0;
     uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
@@ -51,9 +55,13 @@ void v5jpeg_release(v5ela_handle *h)
     cudaFree(s->d_img);
     cudaFree(s->d_out);
     cudaFree(s->d_sizes);
-    if (s->stage_host) cudaFreeHost(s->stage_host);
-    if (s->stage_free) cudaEventDestroy(s->stage_free);
-    cudaFree(s->d_stage);
+    for (int b = 0; b < 2; b++) {
+        if (s->stage_host[b]) cudaFreeHost(s->stage_host[b]);
+        if (s->uploaded[b]) cudaEventDestroy(s->uploaded[b]);
+        if (s->consumed[b]) cudaEventDestroy(s->consumed[b]);
+        cudaFree(s->d_stage[b]);
+    }
+    if (s->upload_stream) cudaStreamDestroy(s->upload_stream);
     cudaFree(s->d_streams);
     cudaFree(s->d_dcoef);
     cudaFree(s->d_planes);
@@ -231,6 +239,25 @@ int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *wid
     return rc == v5j::JPEG_OK ? V5ELA_OK : (rc == v5j::JPEG_UNSUPPORTED ? V5ELA_ERR_UNSUPPORTED : V5ELA_ERR_INVALID);
 }
 
+/* n files at once: dims_out[3 i .. 3 i + 2] = height, width, channels of file i. Stops at the first unreadable file and returns
+ * its status; *bad_index (optional) names it. */
+int v5ela_jpeg_info_batch(const uint8_t *const *files_host, const int64_t *lens, int n, int32_t *dims_out, int *bad_index)
+{
+    if (!files_host || !lens || n < 0 || !dims_out) return V5ELA_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        int hh = 0, ww = 0, cc = 0;
+        const int rc = files_host[i] ? v5ela_jpeg_info(files_host[i], lens[i], &hh, &ww, &cc) : V5ELA_ERR_INVALID;
+        if (rc) {
+            if (bad_index) *bad_index = i;
+            return rc;
+        }
+        dims_out[3 * i] = hh;
+        dims_out[3 * i + 1] = ww;
+        dims_out[3 * i + 2] = cc;
+    }
+    return V5ELA_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -269,6 +296,7 @@ bool is_pinned(const void *p)
 struct DecPlan {                               // host-side description of one chunk of files
     std::vector<v5j::DecImage> images;
     std::vector<int> file_index;
+    std::vector<char> contiguous;              // file k follows file k-1 in host memory closely enough to share one upload
     size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0;
     int max_blocks = 0;
     int64_t max_groups = 0;                    // 4-pixel groups of the largest image
@@ -291,8 +319,12 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
     v5jpeg_state *s;
     int rc;
     if ((rc = jpeg_state(h, &s))) return rc;
-    if (!s->stage_free) {
-        V5_CUDA(h, cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+    if (!s->upload_stream) {
+        V5_CUDA(h, cudaStreamCreateWithFlags(&s->upload_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            V5_CUDA(h, cudaEventCreateWithFlags(&s->uploaded[b], cudaEventDisableTiming));
+            V5_CUDA(h, cudaEventCreateWithFlags(&s->consumed[b], cudaEventDisableTiming));
+        }
         V5_CUDA(h, cudaFuncSetAttribute(v5j::huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v5j::HuffSmem)));
     }
 
@@ -335,7 +367,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         q_of[i] = found;
     }
 
-    // ---- chunks of files whose workspace stays under ~2 GiB
+    // ---- chunks of files whose workspace stays under ~8 GiB (a 1080p file needs ~11 MB: coefficients, planes, streams)
     std::vector<DecPlan> plans(1);
     int64_t rgb_run = 0, gray_run = 0;
     for (int i = 0; i < n; i++) {
@@ -354,11 +386,25 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         const size_t planes = (size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch;
         const size_t need = F.scan_len * 2 + (size_t)im.blocks * 128 + planes + 256;
         DecPlan *P = &plans.back();
-        if (!P->images.empty() && (P->scan_bytes * 2 + P->coef_blocks * 128 + P->plane_bytes + need > ((size_t)2 << 30) || P->images.size() >= 65535)) {
+        if (!P->images.empty() && (P->scan_bytes * 2 + P->coef_blocks * 128 + P->plane_bytes + need > ((size_t)8 << 30) || P->images.size() >= 65535)) {
             plans.emplace_back();
             P = &plans.back();
         }
-        im.scan_off = (int64_t)P->scan_bytes;          // relative to the scan area of the staging buffer (fixed up below)
+        // Pinned files that follow each other in host memory (gap < 64 KB: headers, alignment padding) keep their relative
+        // distance on the device, so that the whole run goes up in one copy. scan_bytes = end of the used scan area.
+        size_t start = align_up(P->scan_bytes, 16);
+        char contig = 0;
+        if (all_pinned && !P->images.empty()) {
+            const int pi = P->file_index.back();
+            const uint8_t *prev_end = files_host[pi] + info[(size_t)pi].scan_off + info[(size_t)pi].scan_len;
+            const uint8_t *cur = files_host[i] + F.scan_off;
+            if (cur >= prev_end && (size_t)(cur - prev_end) < ((size_t)64 << 10)) {
+                contig = 1;
+                start = (size_t)(P->images.back().scan_off + P->images.back().scan_len) + (size_t)(cur - prev_end);
+            }
+        }
+        P->contiguous.push_back(contig);
+        im.scan_off = (int64_t)start;                  // relative to the scan area of the staging buffer (fixed up below)
         im.scan_len = (int64_t)F.scan_len;
         im.stream_off = (int64_t)P->stream_bytes;
         im.coef_off = (int64_t)P->coef_blocks;
@@ -367,7 +413,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         im.gray_off = d_gray ? (gray_offsets ? gray_offsets[i] : gray_run) : -1;
         rgb_run += (int64_t)F.h * F.w * 3;
         gray_run += (int64_t)F.h * F.w;
-        P->scan_bytes += align_up(F.scan_len, 16);
+        P->scan_bytes = start + F.scan_len;
         P->stream_bytes += align_up(F.scan_len + 32, 16);
         P->coef_blocks += (size_t)im.blocks;
         P->plane_bytes += align_up(planes, 16);
@@ -383,53 +429,67 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         const size_t off_img = 0, off_tab = align_up(sizeof(v5j::DecImage) * (size_t)cn, 16);
         const size_t off_q = off_tab + align_up(sizeof(v5j::DecTabSet) * tabsets.size(), 16);
         const size_t off_scan = off_q + align_up(256 * qsets.size(), 16);
-        const size_t stage_bytes = off_scan + P.scan_bytes;
+        const size_t stage_bytes = off_scan + align_up(P.scan_bytes, 16);
         // Files in pinned (page-locked) host memory are copied to the device straight from where they are — the caller keeps
         // them alive until the stream has been synchronised; pageable files go through the handle's pinned staging buffer.
         const size_t host_stage_bytes = all_pinned ? off_scan : stage_bytes;
-        if (s->stage_host_cap < host_stage_bytes) {
-            V5_CUDA(h, cudaEventSynchronize(s->stage_free));
-            if (s->stage_host) cudaFreeHost(s->stage_host);
-            s->stage_host = nullptr;
-            s->stage_host_cap = 0;
-            V5_CUDA(h, cudaHostAlloc((void **)&s->stage_host, host_stage_bytes + host_stage_bytes / 4, cudaHostAllocDefault));
-            s->stage_host_cap = host_stage_bytes + host_stage_bytes / 4;
+        const int b = s->toggle;
+        s->toggle ^= 1;
+        cudaStream_t up = s->upload_stream;
+        // host: the previous upload out of stage_host[b] is over; device: the kernels that read d_stage[b] are over
+        V5_CUDA(h, cudaEventSynchronize(s->uploaded[b]));
+        if (s->stage_host_cap[b] < host_stage_bytes) {
+            if (s->stage_host[b]) cudaFreeHost(s->stage_host[b]);
+            s->stage_host[b] = nullptr;
+            s->stage_host_cap[b] = 0;
+            V5_CUDA(h, cudaHostAlloc((void **)&s->stage_host[b], host_stage_bytes + host_stage_bytes / 4, cudaHostAllocDefault));
+            s->stage_host_cap[b] = host_stage_bytes + host_stage_bytes / 4;
         }
-        if ((rc = ensure(h, (void **)&s->d_stage, &s->stage_cap, stage_bytes))) return rc;
+        if ((rc = ensure(h, (void **)&s->d_stage[b], &s->stage_cap[b], stage_bytes))) return rc;
         if ((rc = ensure(h, &s->d_streams, &s->streams_cap, P.stream_bytes))) return rc;
         if ((rc = ensure(h, &s->d_dcoef, &s->dcoef_cap, P.coef_blocks * 128))) return rc;
         if ((rc = ensure(h, &s->d_planes, &s->planes_cap, P.plane_bytes))) return rc;
         if ((rc = ensure(h, &s->d_bits, &s->bits_cap, sizeof(uint32_t) * (size_t)cn))) return rc;
         if ((rc = ensure(h, &s->d_status, &s->status_cap, sizeof(int32_t) * (size_t)cn))) return rc;
-        V5_CUDA(h, cudaEventSynchronize(s->stage_free));                 // the previous upload no longer reads stage_host
+        uint8_t *stage_host = s->stage_host[b], *d_stage = s->d_stage[b];
         for (int k = 0; k < cn; k++) P.images[(size_t)k].scan_off += (int64_t)off_scan;
         if (!all_pinned)
-            parallel_for(cn, P.scan_bytes, [&](int k) {
+            parallel_for(cn, P.scan_bytes, [&](int k) {   // every scan segment to its planned place in the staging buffer
                 const v5j::DecImage &im = P.images[(size_t)k];
                 const int fi = P.file_index[(size_t)k];
-                memcpy(s->stage_host + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len);
+                memcpy(stage_host + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len);
             });
-        memcpy(s->stage_host + off_img, P.images.data(), sizeof(v5j::DecImage) * (size_t)cn);
-        memcpy(s->stage_host + off_tab, tabsets.data(), sizeof(v5j::DecTabSet) * tabsets.size());
-        for (size_t k = 0; k < qsets.size(); k++) memcpy(s->stage_host + off_q + 256 * k, qsets[k].data(), 256);
-        V5_CUDA(h, cudaMemcpyAsync(s->d_stage, s->stage_host, host_stage_bytes, cudaMemcpyHostToDevice, st));
-        V5_CUDA(h, cudaEventRecord(s->stage_free, st));
-        if (all_pinned)
-            for (int k = 0; k < cn; k++) {
-                const v5j::DecImage &im = P.images[(size_t)k];
+        memcpy(stage_host + off_img, P.images.data(), sizeof(v5j::DecImage) * (size_t)cn);
+        memcpy(stage_host + off_tab, tabsets.data(), sizeof(v5j::DecTabSet) * tabsets.size());
+        for (size_t k = 0; k < qsets.size(); k++) memcpy(stage_host + off_q + 256 * k, qsets[k].data(), 256);
+        V5_CUDA(h, cudaStreamWaitEvent(up, s->consumed[b], 0));
+        V5_CUDA(h, cudaMemcpyAsync(d_stage, stage_host, host_stage_bytes, cudaMemcpyHostToDevice, up));
+        if (all_pinned) {
+            // one copy per file, or per run of files that also sit back to back in host memory (a loader's arena): the
+            // device layout was planned with the same gaps, so a run is a single contiguous range
+            for (int k = 0; k < cn;) {
+                int e = k + 1;
+                while (e < cn && P.contiguous[(size_t)e]) e++;
+                const v5j::DecImage &first = P.images[(size_t)k], &last = P.images[(size_t)e - 1];
                 const int fi = P.file_index[(size_t)k];
-                V5_CUDA(h, cudaMemcpyAsync(s->d_stage + im.scan_off, files_host[fi] + info[(size_t)fi].scan_off, (size_t)im.scan_len,
-                                           cudaMemcpyHostToDevice, st));
+                const size_t bytes = (size_t)(last.scan_off + last.scan_len - first.scan_off);
+                V5_CUDA(h, cudaMemcpyAsync(d_stage + first.scan_off, files_host[fi] + info[(size_t)fi].scan_off, bytes,
+                                           cudaMemcpyHostToDevice, up));
+                k = e;
             }
+        }
+        V5_CUDA(h, cudaEventRecord(s->uploaded[b], up));
+        V5_CUDA(h, cudaStreamWaitEvent(st, s->uploaded[b], 0));
+        V5_CUDA(h, cudaStreamWaitEvent(st, s->consumed[b ^ 1], 0));      // the shared workspace: previous batch (any stream) is done
         V5_CUDA(h, cudaMemsetAsync(s->d_streams, 0, P.stream_bytes, st));
         V5_CUDA(h, cudaMemsetAsync(s->d_dcoef, 0, P.coef_blocks * 128, st));
 
-        const v5j::DecImage *d_images = reinterpret_cast<const v5j::DecImage *>(s->d_stage + off_img);
-        const v5j::DecTabSet *d_tabs = reinterpret_cast<const v5j::DecTabSet *>(s->d_stage + off_tab);
-        const uint16_t *d_q = reinterpret_cast<const uint16_t *>(s->d_stage + off_q);
+        const v5j::DecImage *d_images = reinterpret_cast<const v5j::DecImage *>(d_stage + off_img);
+        const v5j::DecTabSet *d_tabs = reinterpret_cast<const v5j::DecTabSet *>(d_stage + off_tab);
+        const uint16_t *d_q = reinterpret_cast<const uint16_t *>(d_stage + off_q);
         uint32_t *d_bits = static_cast<uint32_t *>(s->d_bits);
         int32_t *d_st = static_cast<int32_t *>(s->d_status);
-        v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, s->d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
+        v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
         V5_CUDA(h, cudaGetLastError());
         v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
                                                         static_cast<int16_t *>(s->d_dcoef), d_st);
@@ -444,6 +504,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         V5_CUDA(h, cudaGetLastError());
         if (d_status)                                                      // chunks keep file order: one contiguous range
             V5_CUDA(h, cudaMemcpyAsync(d_status + P.file_index[0], d_st, sizeof(int32_t) * (size_t)cn, cudaMemcpyDeviceToDevice, st));
+        V5_CUDA(h, cudaEventRecord(s->consumed[b], st));
         h->launches += 5;
     }
     return V5ELA_OK;

@@ -69,6 +69,15 @@ V5_HOSTDEV bool same_state(const SubState &a, const SubState &b) { return a.p ==
 // first. The stream buffer is padded with zero bytes, so reading a little past the end is harmless.
 struct ByteStream {                        // plain bytes in (global) memory
     const uint8_t *data;
+    V5_HOSTDEV uint32_t word(uint32_t w) const     // stream bits 32w .. 32w+31, most significant first
+    {
+#ifdef __CUDA_ARCH__
+        return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(data) + w), 0, 0x0123);
+#else
+        const uint8_t *b = data + 4 * (size_t)w;
+        return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+#endif
+    }
     V5_HOSTDEV uint32_t window(uint32_t p) const
     {
 #ifdef __CUDA_ARCH__
@@ -97,6 +106,7 @@ V5_HOSTDEV int stage_slot(uint32_t w)
 struct StagedStream {
     const uint32_t *words;                 // STAGE_WORDS entries
     uint32_t base_word;                    // stream word index of words[stage_slot(0)]
+    V5_HOSTDEV uint32_t word(uint32_t w) const { return words[stage_slot(w - base_word)]; }
     V5_HOSTDEV uint32_t window(uint32_t p) const
     {
         const uint32_t w = (p >> 5) - base_word;
@@ -125,6 +135,36 @@ V5_HOSTDEV void stage_window(int t, int nt, uint32_t *words, const uint8_t *stre
         words[stage_slot((uint32_t)i)] = v;
     }
 }
+
+// A 64-bit shift register over the stream: the window is its upper half, a symbol costs two shifts, and a word is loaded
+// only when fewer than 33 bits remain (about every fourth symbol) instead of two loads and a funnel shift per symbol.
+template <class Src>
+struct BitCursor {
+    const Src &src;
+    uint64_t buf;                          // the next `avail` stream bits, left aligned
+    uint32_t next_word;
+    int avail;
+    V5_HOSTDEV BitCursor(const Src &s, uint32_t p) : src(s)
+    {
+        const uint32_t w = p >> 5, sh = p & 31;
+        buf = (((uint64_t)s.word(w) << 32) | s.word(w + 1)) << sh;
+        avail = 64 - (int)sh;
+        next_word = w + 2;
+        if (avail <= 32) refill();
+    }
+    V5_HOSTDEV void refill()
+    {
+        buf |= (uint64_t)src.word(next_word++) << (32 - avail);
+        avail += 32;
+    }
+    V5_HOSTDEV uint32_t window() const { return (uint32_t)(buf >> 32); }
+    V5_HOSTDEV void consume(int n)         // n <= 31
+    {
+        buf <<= n;
+        avail -= n;
+        if (avail <= 32) refill();
+    }
+};
 
 // One Huffman symbol from the window: returns the symbol, adds its code length to `len`. Codes that do not exist decode as
 // symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
@@ -159,11 +199,13 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
     //   AC symbol  = run << 4 | size;   00 = end of block, F0 = sixteen zeros (run 15, no value: the ++ below makes 16)
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
+    if (p >= limit) return 0;
+    BitCursor<Src> cur(stream, p);
     while (p < limit) {
         const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
         const bool is_dc = z == 0;
         const DecTable &tab = is_dc ? T.dc[comp] : T.ac[comp];
-        const uint32_t win = stream.window(p);
+        const uint32_t win = cur.window();
         int len;
         const int sym = huff_symbol(tab, win, len);
         const int run = is_dc ? 0 : sym >> 4;
@@ -177,6 +219,7 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
         }
         z++;
         p += (uint32_t)(len + sz);
+        cur.consume(len + sz);
         if (z >= 64) {
             z = 0;
             c = c + 1 == bpm ? 0 : c + 1;

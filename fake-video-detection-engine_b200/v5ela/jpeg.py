@@ -28,6 +28,19 @@ def info(data: bytes):
     return h.value, w.value, c.value
 
 
+def info_batch(files, table=None):
+    """-> int32 array (N, 3) of (height, width, channels), one library call for the whole list."""
+    lib = _abi.load()
+    n = len(files)
+    keep, ptrs, lens = table or _file_table(files)
+    dims = np.zeros((n, 3), np.int32)
+    bad = ctypes.c_int(-1)
+    rc = lib.v5ela_jpeg_info_batch(ptrs, lens, n, dims.ctypes.data, ctypes.byref(bad))
+    if rc != 0:
+        raise _abi.V5ElaError(rc, f"{lib.v5ela_status_string(rc).decode()} (file {bad.value})")
+    return dims
+
+
 def _file_table(files):
     """ctypes arrays (pointers, lengths) over a list of bytes objects / uint8 arrays (e.g. views into one pinned arena); the
     first return value keeps the buffers alive."""
@@ -102,12 +115,13 @@ def decode_host(files, want_rgb: bool = True, want_gray: bool = False, device: i
     n = len(files)
     if n == 0:
         return []
-    dims = [info(f) for f in files]
+    table = _file_table(files)
+    dims = [tuple(int(v) for v in d) for d in info_batch(files, table)]
     px = np.array([h * w for h, w, _ in dims], np.int64)
     offs = np.concatenate([[0], np.cumsum(px)])
     rgb = np.empty(3 * int(offs[-1]), np.uint8) if want_rgb else None
     gray = np.empty(int(offs[-1]), np.uint8) if want_gray else None
-    keep, ptrs, lens = _file_table(files)
+    keep, ptrs, lens = table
     _handle(device).jpeg_decode_host(ptrs, lens, n, rgb.ctypes.data if want_rgb else None, None,
                                      gray.ctypes.data if want_gray else None, None)
     del keep
@@ -132,16 +146,17 @@ def decode_batch(files, device=0, want_rgb: bool = True, want_gray: bool = False
 
     n = len(files)
     dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
-    dims = {info(f)[:2] for f in files}
-    if len(dims) != 1:
-        raise ValueError("decode_batch needs files of one size; use decode_host for mixed sizes")
-    h, w = dims.pop()
+    table = _file_table(files)
+    dims = info_batch(files, table)
+    if n == 0 or (dims[:, :2] != dims[0, :2]).any():
+        raise ValueError("decode_batch needs at least one file and files of one size; use decode_host for mixed sizes")
+    h, w = int(dims[0, 0]), int(dims[0, 1])
     out = {"status": torch.zeros(n, dtype=torch.int32, device=dev)}
     if want_rgb:
         out["rgb"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
     if want_gray:
         out["gray"] = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    keep, ptrs, lens = _file_table(files)
+    keep, ptrs, lens = table
     get_handle(dev.index or 0).jpeg_decode(ptrs, lens, n, out["rgb"].data_ptr() if want_rgb else None, None,
                                            out["gray"].data_ptr() if want_gray else None, None, out["status"].data_ptr(),
                                            torch.cuda.current_stream(dev).cuda_stream)

@@ -176,8 +176,13 @@ V5ELA_API int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, i
  *   d_gray  : optional DEVICE buffer; the luma plane alone (what IMREAD_GRAYSCALE returns), offsets likewise.
  *   d_status: optional DEVICE array of n ints: 0, or -1 when the entropy-coded data of that file ended early.
  * Header parsing and the staging copy happen on the calling thread; the decode itself is asynchronous on `cuda_stream`.
+ * The compressed bytes are uploaded on an internal stream as soon as the call is made (so the upload of one batch overlaps
+ * the kernels of the previous one): the files must be complete in host memory at that moment.
  */
 V5ELA_API int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *width, int *channels);
+/* The same for n files in one call: dims_out[3i .. 3i+2] = height, width, channels; stops at the first unreadable file,
+ * returns its status and (optionally) its index. */
+V5ELA_API int v5ela_jpeg_info_batch(const uint8_t *const *files_host, const int64_t *lens, int n, int32_t *dims_out, int *bad_index);
 V5ELA_API int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n,
                       uint8_t *d_rgb, const int64_t *rgb_offsets, uint8_t *d_gray, const int64_t *gray_offsets,
                       int32_t *d_status, void *cuda_stream);

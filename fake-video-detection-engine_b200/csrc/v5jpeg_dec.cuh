@@ -464,7 +464,7 @@ __device__ __forceinline__ uint32_t dec_cta_scan(uint32_t v, uint32_t *warp_sums
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const uint32_t w = warp_sums[lane];
+        const uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0u;
         uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -53,8 +53,8 @@ def main():
         gray = frames[..., 1].contiguous()
         t_enc_g = timed(lambda: jpeg.encode_batch(gray, 95))
         print(f"{h}x{w} q{q}: mean file {sz.mean() / 1e3:8.1f} kB | encode RGB {cnt / t_enc * 1e3:9.0f} img/s ({t_enc:7.2f} ms)"
-              f" | encode gray q95 {cnt / t_enc_g * 1e3:9.0f} img/s | decode {cnt / t_dec * 1e3:9.0f} img/s (GPU {t_dec:7.2f} ms,"
-              f" wall incl. host parse+upload {t_dec_wall:7.2f} ms, first call {t_first:7.1f} ms) status ok={int((out['status'] == 0).all())}")
+              f" | encode gray q95 {cnt / t_enc_g * 1e3:9.0f} img/s | decode {cnt / t_dec_wall * 1e3:9.0f} img/s (wall clock per call incl. header"
+              f" parsing and upload {t_dec_wall:7.2f} ms back to back; one call alone {t_dec:7.2f} ms; first call {t_first:7.1f} ms) status ok={int((out['status'] == 0).all())}")
     # the CPU libraries on this box, one thread, same work
     from PIL import Image
     import cv2

@@ -834,14 +834,15 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
     {
         // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per
-        // pixel, up + down two more. The pixel in image column W-1 (if in this unit) is left out of the vector loop and
-        // done on its own below, mirroring W onto W-2; column -1 mirrors onto column 1 through the selected address.
+        // pixel, up + down two more. Mirroring (REFLECT_101) goes through the neighbour loads: column -1 reads column 1, and
+        // when the unit ends exactly at the image edge (every width that is a multiple of 8) column W reads column W-2. Only
+        // a unit cut by the edge (ragged widths) leaves its last pixel to the scalar code below.
         const U2 cw = *reinterpret_cast<const U2 *>(yc);
         const U2 uw = *reinterpret_cast<const U2 *>(yu);
         const U2 lw = *reinterpret_cast<const U2 *>(yd2);
-        const int edge = nvalid <= 8 ? nvalid - 1 : -1;
+        const int edge = nvalid < 8 ? nvalid - 1 : -1;
         const int nacc = edge >= 0 ? edge : 8;
-        const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = yc[8];
+        const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = nvalid == 8 ? yc[6] : yc[8];
         const uint32_t x[3] = {prmt(hl, cw.x, 0x6540u), prmt(cw.x, cw.y, 0x6543u), prmt(cw.y, hr, 0x7743u)};
         const uint32_t ud[2][2] = {{uw.x, lw.x}, {uw.y, lw.y}};
 #pragma unroll

@@ -39,7 +39,8 @@ struct v5jpeg_state {
     void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr;
     size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0;
     uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
-    size_t dec_rgb_cap = 0, dec_gray_cap = 0;
+    int32_t *d_dec_status = nullptr;
+    size_t dec_rgb_cap = 0, dec_gray_cap = 0, dec_status_cap = 0;
 };
 
 void v5jpeg_release(v5ela_handle *h)
@@ -69,6 +70,7 @@ void v5jpeg_release(v5ela_handle *h)
     cudaFree(s->d_status);
     cudaFree(s->d_dec_rgb);
     cudaFree(s->d_dec_gray);
+    cudaFree(s->d_dec_status);
     delete s;
     h->jpeg = nullptr;
 }
@@ -540,8 +542,8 @@ int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, co
     if (rgb_host && (rc = ensure(h, (void **)&s->d_dec_rgb, &s->dec_rgb_cap, (size_t)rgb_end))) return rc;
     if (gray_host && (rc = ensure(h, (void **)&s->d_dec_gray, &s->dec_gray_cap, (size_t)gray_end))) return rc;
     std::vector<int32_t> status((size_t)n, 0);
-    int32_t *d_status = nullptr;
-    V5_CUDA(h, cudaMalloc(&d_status, sizeof(int32_t) * (size_t)n));
+    if ((rc = ensure(h, (void **)&s->d_dec_status, &s->dec_status_cap, sizeof(int32_t) * (size_t)n))) return rc;
+    int32_t *d_status = s->d_dec_status;
     rc = v5ela_jpeg_decode(h, files_host, lens, n, rgb_host ? s->d_dec_rgb : nullptr, rgb_offsets, gray_host ? s->d_dec_gray : nullptr,
                            gray_offsets, d_status, st);
     if (rc == V5ELA_OK) {
@@ -556,7 +558,6 @@ int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, co
         const cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail(h, V5ELA_ERR_CUDA, "v5ela_jpeg_decode_host: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_status);
     if (rc) return rc;
     for (int i = 0; i < n; i++)
         if (status[(size_t)i] != 0) {

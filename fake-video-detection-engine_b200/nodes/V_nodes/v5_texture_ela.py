@@ -15,9 +15,10 @@ What runs on the B200 instead of Pillow/OpenCV/NumPy:
   * JPEG-encoding the artefacts ``ela_{i}.jpg`` (:80-81, quality 75), ``fft_{i}.jpg`` (:90-91, quality 95, one component) and,
     on request, the scratch file ``temp_ela_{i}.jpg`` (:66-67) through ``v5ela_jpeg_encode_host`` — the files equal the
     reference's byte for byte.
-  There is no CPU fallback for any of it: a missing library or GPU surfaces as that face's error, like any other analysis
-  failure. A crop that is not a JPEG at all, or a JPEG flavour outside the GPU decoder's set (progressive, 4:4:4, restart
-  markers — nothing V1 writes), is read with the reference's own two library calls and says so on stdout.
+  There is no CPU fallback for any of it: a missing library or GPU — or a crop outside the GPU decoder's set (not a JPEG,
+  progressive, 4:4:4, restart markers: nothing V1 writes) — surfaces as that face's error, like any other analysis failure
+  (reference :140-144). Reading and writing the files with Pillow/OpenCV instead is an explicit choice of the caller
+  (``v5_gpu_codec = False``), never something the node decides on its own.
 Optional state keys (defaults = the reference's literals): ``v5_quality`` 90, ``v5_max_faces`` 3, ``v5_device`` 0,
   ``v5_gpu_fft`` True (False: the reference's NumPy spectrum), ``v5_gpu_codec`` True (False: Pillow/OpenCV read and write the
   files), ``v5_keep_temp_jpeg`` False (the reference's scratch file, which nothing reads, is written only on request). The
@@ -67,20 +68,14 @@ def _rank_faces(detections, limit):
 
 def _read_crop(crop_path, device, gpu_codec):
     """The crop as RGB (reference :64) and as its luma plane (:83)."""
-    if gpu_codec:
-        from v5ela import _abi, jpeg
+    if not gpu_codec:
+        return np.asarray(Image.open(crop_path).convert("RGB")), cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
+    from v5ela import jpeg
 
-        with open(crop_path, "rb") as fh:
-            data = fh.read()
-        if data[:2] == b"\xff\xd8":
-            try:
-                planes = jpeg.decode_host([data], want_rgb=True, want_gray=True, device=device)[0]
-                return planes["rgb"], planes["gray"]
-            except _abi.V5ElaError as err:
-                if err.status != jpeg.UNSUPPORTED:
-                    raise
-        print(f"Node V5: {os.path.basename(crop_path)} is outside the GPU decoder's JPEG set; read with Pillow/OpenCV.")
-    return np.asarray(Image.open(crop_path).convert("RGB")), cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)
+    with open(crop_path, "rb") as fh:
+        data = fh.read()
+    planes = jpeg.decode_host([data], want_rgb=True, want_gray=True, device=device)[0]   # raises for unsupported files
+    return planes["rgb"], planes["gray"]
 
 
 def _write_jpeg(path, image, quality, device, gpu_codec):

@@ -150,3 +150,22 @@ def test_missing_gpu_is_reported_like_any_face_error(fixture_state, capsys):
     assert result["texture_ela_score"] == 0.0
     assert result["texture_ela_details"] == {"reason": "Analysis failed or no keys"}
     assert "Error analyzing face 0" in capsys.readouterr().out
+
+
+@pytest.mark.gpu
+def test_unsupported_crop_is_a_face_error_not_a_fallback(fixture_state, capsys):
+    """A progressive JPEG is outside the GPU decoder's set: the node reports it like any per-face failure (reference
+    :140-144) instead of silently reading it on the CPU; v5_gpu_codec=False is the caller's explicit switch."""
+    from PIL import Image
+
+    crop = fixture_state["face_detections"][0]["faces"][0]["crop_path"]
+    Image.open(crop).save(crop, "JPEG", quality=95, progressive=True)
+    env = {k: v for k, v in os.environ.items() if k != "OPENAI_API_KEY"}
+    with patch.dict(os.environ, env, clear=True):
+        result = run(dict(fixture_state))
+        out = capsys.readouterr().out
+        assert result["texture_ela_details"] == {"reason": "Analysis failed or no keys"}
+        assert "Error analyzing face 0" in out and "-5" in out
+        result = run(dict(fixture_state, v5_gpu_codec=False))
+    assert "ela_features" in result["texture_ela_details"]
+    assert os.path.exists(os.path.join(fixture_state["data_dir"], "ela_analysis", "ela_0.jpg"))

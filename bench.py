@@ -26,9 +26,17 @@ import subprocess
 import sys
 import time
 
-# stdout must carry exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly one JSON line. Native libraries write there too (NCCL prints its version banner to stdout at the
+# VERSION and WARN debug levels), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+# duplicate of the original stdout (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "fake-video-detection-engine_b200")
@@ -121,7 +129,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -382,7 +390,7 @@ def run_native_arm(args):
             line["e2e_from_jpeg_files"] = files_leg
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -233,6 +233,13 @@ def run_native_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU implementation (use --impl reference)")
     _abi.load()
+    try:    # run (and first-touch the pinned host buffers) on the CPU cores next to this rank's GPU: matters for `e2e` at N > 1
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -129,20 +129,45 @@ inline std::vector<uint8_t> file_header(int h, int w, int ncomp, const uint16_t 
 }
 
 // ---------------------------------------------------------------------------------------------------- decoder tables
-// Huffman decoding by a 16-bit window: look[w >> 7] resolves codes of <= 9 bits in one step ((len << 8) | symbol, 0 = longer);
-// longer codes walk maxcode[] (T.81 F.2.2.3). One table per (class, destination) actually used by the scan.
+// Huffman decoding by a window of the next stream bits: look[window >> 23] resolves codes of <= 9 bits in one step, longer
+// codes walk maxcode[] (T.81 F.2.2.3). What comes back is not the raw symbol but what the decoder does with it, packed:
+//   bits  0..4   code length
+//   bits  8..11  size   = number of value bits that follow the code (0 = none)
+//   bits 16..22  zinc   = how far the zigzag index moves: DC 1; AC run + 1; ZRL (F0) 16; end of block 64
+//   bits 24..29  total  = code length + size, what the bit position moves by
+// so that DC symbols, AC symbols, ZRL and EOB all run through the same few instructions. 0 = not a short code.
+#if defined(__CUDACC__)
+#define V5J_HOSTDEV __host__ __device__ __forceinline__
+#else
+#define V5J_HOSTDEV inline
+#endif
+V5J_HOSTDEV uint32_t pack_symbol(int sym, int len, bool is_dc)
+{
+    int size, zinc;
+    if (is_dc) {
+        size = sym > 15 ? 15 : sym;
+        zinc = 1;
+    } else {
+        size = sym & 15;
+        zinc = size ? (sym >> 4) + 1 : ((sym >> 4) == 15 ? 16 : 64);
+    }
+    return (uint32_t)len | ((uint32_t)size << 8) | ((uint32_t)zinc << 16) | ((uint32_t)(len + size) << 24);
+}
+
 struct DecTable {
-    uint16_t look[512];
-    int32_t maxcode[18];     // maxcode[len] for len 1..16, left-aligned compare is done on the fly; -1 = no codes
+    uint32_t look[512];
+    int32_t maxcode[18];     // maxcode[len] for len 1..16; -1 = no codes of that length
     int32_t valoff[17];      // symbol index = valoff[len] + code
     uint8_t vals[256];
+    uint32_t is_dc;
 };
 
-inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nvals, DecTable &t)
+inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nvals, bool is_dc, DecTable &t)
 {
     memset(&t, 0, sizeof(t));
     if (nvals > 256) return false;
     memcpy(t.vals, vals, (size_t)nvals);
+    t.is_dc = is_dc ? 1u : 0u;
     int k = 0;
     int32_t code = 0;
     for (int len = 1; len <= 16; len++) {
@@ -153,7 +178,7 @@ inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nval
             if (len <= 9)
                 for (int i = 0; i < cnt; i++) {
                     const int first = (code + i) << (9 - len);
-                    for (int f = 0; f < (1 << (9 - len)); f++) t.look[first + f] = (uint16_t)((len << 8) | vals[k + i]);
+                    for (int f = 0; f < (1 << (9 - len)); f++) t.look[first + f] = pack_symbol(vals[k + i], len, is_dc);
                 }
             code += cnt;
             k += cnt;
@@ -274,8 +299,8 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
         if (!qt_ok[tq[c]] || !huff[0][td[c]].ok || !huff[1][ta[c]].ok) return JPEG_CORRUPT;
         if (headers_only) continue;
         memcpy(F.qt[c], qt[tq[c]], sizeof(F.qt[c]));
-        if (!make_dec_table(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].n, F.dc[c])) return JPEG_CORRUPT;
-        if (!make_dec_table(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].n, F.ac[c])) return JPEG_CORRUPT;
+        if (!make_dec_table(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].n, true, F.dc[c])) return JPEG_CORRUPT;
+        if (!make_dec_table(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].n, false, F.ac[c])) return JPEG_CORRUPT;
     }
     if (headers_only) return JPEG_OK;
     if (F.ncomp == 1) {

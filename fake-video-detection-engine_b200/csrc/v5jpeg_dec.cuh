@@ -136,54 +136,17 @@ V5_HOSTDEV void stage_window(int t, int nt, uint32_t *words, const uint8_t *stre
     }
 }
 
-// A 64-bit shift register over the stream: the window is its upper half, a symbol costs two shifts, and a word is loaded
-// only when fewer than 33 bits remain (about every fourth symbol) instead of two loads and a funnel shift per symbol.
-template <class Src>
-struct BitCursor {
-    const Src &src;
-    uint64_t buf;                          // the next `avail` stream bits, left aligned
-    uint32_t next_word;
-    int avail;
-    V5_HOSTDEV BitCursor(const Src &s, uint32_t p) : src(s)
-    {
-        const uint32_t w = p >> 5, sh = p & 31;
-        buf = (((uint64_t)s.word(w) << 32) | s.word(w + 1)) << sh;
-        avail = 64 - (int)sh;
-        next_word = w + 2;
-        if (avail <= 32) refill();
-    }
-    V5_HOSTDEV void refill()
-    {
-        buf |= (uint64_t)src.word(next_word++) << (32 - avail);
-        avail += 32;
-    }
-    V5_HOSTDEV uint32_t window() const { return (uint32_t)(buf >> 32); }
-    V5_HOSTDEV void consume(int n)         // n <= 31
-    {
-        buf <<= n;
-        avail -= n;
-        if (avail <= 32) refill();
-    }
-};
-
-// One Huffman symbol from the window: returns the symbol, adds its code length to `len`. Codes that do not exist decode as
-// symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
-V5_HOSTDEV int huff_symbol(const DecTable &t, uint32_t win, int &len)
+// One Huffman symbol from the window, as the packed action word of v5jpeg_common.h (pack_symbol). Codes that do not exist
+// decode as symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
+V5_HOSTDEV uint32_t huff_action(const DecTable &t, uint32_t win)
 {
     const uint32_t look = t.look[win >> 23];
-    if (look) {
-        len = (int)(look >> 8);
-        return (int)(look & 0xff);
-    }
+    if (look) return look;
     for (int l = 10; l <= 16; l++) {
         const int32_t code = (int32_t)(win >> (32 - l));
-        if (code <= t.maxcode[l]) {
-            len = l;
-            return t.vals[(t.valoff[l] + code) & 0xff];
-        }
+        if (code <= t.maxcode[l]) return pack_symbol(t.vals[(t.valoff[l] + code) & 0xff], l, t.is_dc != 0);
     }
-    len = 16;
-    return 0;
+    return pack_symbol(0, 16, t.is_dc != 0);
 }
 
 // Decodes from state `s` until the bit position reaches `limit`; returns the number of blocks completed. WRITE: stores
@@ -195,31 +158,23 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
 {
     // One loop body for DC and AC symbols, selects instead of branches: the threads of a warp sit at unrelated places of
     // their blocks, and every divergent path would be paid for by all of them.
-    //   DC symbol  = size;              run 0
-    //   AC symbol  = run << 4 | size;   00 = end of block, F0 = sixteen zeros (run 15, no value: the ++ below makes 16)
+    // The table hands back what to do (pack_symbol): value bits to read, how far the zigzag index moves (end of block: 64).
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
-    if (p >= limit) return 0;
-    BitCursor<Src> cur(stream, p);
     while (p < limit) {
         const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
         const bool is_dc = z == 0;
         const DecTable &tab = is_dc ? T.dc[comp] : T.ac[comp];
-        const uint32_t win = cur.window();
-        int len;
-        const int sym = huff_symbol(tab, win, len);
-        const int run = is_dc ? 0 : sym >> 4;
-        int sz = is_dc ? sym : sym & 15;
-        sz = sz > 15 ? 15 : sz;
-        const bool eob = !is_dc && sym == 0;
-        z = eob ? 64 : z + run;
-        if (WRITE && sz && z < 64 && block0 + done < max_blocks) {
+        const uint32_t win = stream.window(p);
+        const uint32_t act = huff_action(tab, win);
+        const int len = (int)(act & 31u), sz = (int)((act >> 8) & 15u), zinc = (int)((act >> 16) & 127u), total = (int)(act >> 24);
+        const int pos = z + zinc - 1;                                    // where a value lands: DC 0, AC z + run
+        if (WRITE && sz && pos < 64 && block0 + done < max_blocks) {
             const int v = (int)((win << len) >> (32 - sz));
-            coef[(block0 + done) * 64 + z] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+            coef[(block0 + done) * 64 + pos] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
         }
-        z++;
-        p += (uint32_t)(len + sz);
-        cur.consume(len + sz);
+        z += zinc;
+        p += (uint32_t)total;
         if (z >= 64) {
             z = 0;
             c = c + 1 == bpm ? 0 : c + 1;

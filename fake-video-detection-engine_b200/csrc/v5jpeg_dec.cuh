@@ -32,7 +32,11 @@ namespace v5j {
 #ifndef V5J_SUB_BITS
 #define V5J_SUB_BITS 1024
 #endif
+#ifndef V5J_HUFF_CTAS
+#define V5J_HUFF_CTAS 1
+#endif
 constexpr int HUFF_NT = V5J_HUFF_NT;       // subsequences per window = threads of the decoding CTA
+constexpr int HUFF_CTAS = V5J_HUFF_CTAS;   // resident CTAs per SM the kernel is built for
 constexpr uint32_t SUB_BITS = V5J_SUB_BITS;   // bits per subsequence (> 31: a symbol never skips a whole subsequence)
 
 struct DecTabSet {                         // Huffman tables of one file: [0] luma, [1] chroma
@@ -100,8 +104,8 @@ constexpr int WINDOW_WORDS = HUFF_NT * SUB_WORDS;
 constexpr int STAGE_WORDS = WINDOW_WORDS + SUB_WORDS;                      // + one row: a symbol may end just past the window
 V5_HOSTDEV int stage_slot(uint32_t w)
 {
-    if (SUB_WORDS == 32) return (int)((w & ~31u) | ((w + (w >> 5)) & 31u));
-    return (int)w;                                                         // test builds with tiny subsequences: no swizzle
+    // rotate each subsequence's row of SUB_WORDS words by its row number (SUB_WORDS is a power of two)
+    return (int)((w & ~(uint32_t)(SUB_WORDS - 1)) | ((w + w / SUB_WORDS) & (uint32_t)(SUB_WORDS - 1)));
 }
 struct StagedStream {
     const uint32_t *words;                 // STAGE_WORDS entries
@@ -479,7 +483,7 @@ struct HuffSmem {
     uint16_t live[HUFF_NT];                // subsequences still walking (rounds >= 2)
 };
 
-__global__ void __launch_bounds__(HUFF_NT) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+__global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
                                                           const uint32_t *stream_bits, int16_t *coef, int32_t *status)
 {
     extern __shared__ __align__(16) uint8_t huff_smem_raw[];

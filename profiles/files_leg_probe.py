@@ -6,9 +6,10 @@ import numpy as np, torch, v5ela
 from v5ela import jpeg
 from v5ela.batch import analyze_batch
 
-n = 256
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+q = int(sys.argv[2]) if len(sys.argv) > 2 else 95
 frames = v5ela.gen_batch_torch(0, n, 1080, 1920, seed=0, device="cuda")
-enc, sizes = jpeg.encode_batch(frames, 95)
+enc, sizes = jpeg.encode_batch(frames, q)
 torch.cuda.synchronize()
 enc, sizes = enc.cpu().numpy(), sizes.cpu().numpy()
 offs = [0]

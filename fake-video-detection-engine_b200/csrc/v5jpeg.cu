@@ -36,8 +36,8 @@ struct v5jpeg_state {
     cudaEvent_t consumed[2] = {nullptr, nullptr};   // the kernels that read d_stage[b] have completed
     cudaStream_t upload_stream = nullptr;
     int toggle = 0;
-    void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr;
-    size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0;
+    void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr, *d_dc = nullptr;
+    size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0, dc_cap = 0;
     uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
     int32_t *d_dec_status = nullptr;
     size_t dec_rgb_cap = 0, dec_gray_cap = 0, dec_status_cap = 0;
@@ -68,6 +68,7 @@ void v5jpeg_release(v5ela_handle *h)
     cudaFree(s->d_planes);
     cudaFree(s->d_bits);
     cudaFree(s->d_status);
+    cudaFree(s->d_dc);
     cudaFree(s->d_dec_rgb);
     cudaFree(s->d_dec_gray);
     cudaFree(s->d_dec_status);
@@ -453,6 +454,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         if ((rc = ensure(h, &s->d_planes, &s->planes_cap, P.plane_bytes))) return rc;
         if ((rc = ensure(h, &s->d_bits, &s->bits_cap, sizeof(uint32_t) * (size_t)cn))) return rc;
         if ((rc = ensure(h, &s->d_status, &s->status_cap, sizeof(int32_t) * (size_t)cn))) return rc;
+        if ((rc = ensure(h, &s->d_dc, &s->dc_cap, sizeof(int16_t) * P.coef_blocks))) return rc;
         uint8_t *stage_host = s->stage_host[b], *d_stage = s->d_stage[b];
         for (int k = 0; k < cn; k++) P.images[(size_t)k].scan_off += (int64_t)off_scan;
         if (!all_pinned)
@@ -485,6 +487,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         V5_CUDA(h, cudaStreamWaitEvent(st, s->consumed[b ^ 1], 0));      // the shared workspace: previous batch (any stream) is done
         V5_CUDA(h, cudaMemsetAsync(s->d_streams, 0, P.stream_bytes, st));
         V5_CUDA(h, cudaMemsetAsync(s->d_dcoef, 0, P.coef_blocks * 128, st));
+        V5_CUDA(h, cudaMemsetAsync(s->d_dc, 0, sizeof(int16_t) * P.coef_blocks, st));
 
         const v5j::DecImage *d_images = reinterpret_cast<const v5j::DecImage *>(d_stage + off_img);
         const v5j::DecTabSet *d_tabs = reinterpret_cast<const v5j::DecTabSet *>(d_stage + off_tab);
@@ -494,12 +497,12 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
         V5_CUDA(h, cudaGetLastError());
         v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
-                                                        static_cast<int16_t *>(s->d_dcoef), d_st);
+                                                        static_cast<int16_t *>(s->d_dcoef), static_cast<int16_t *>(s->d_dc), d_st);
         V5_CUDA(h, cudaGetLastError());
-        v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dcoef));
+        v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dc));
         V5_CUDA(h, cudaGetLastError());
         v5j::idct_kernel<<<dim3((unsigned)((P.max_blocks + 63) / 64), (unsigned)cn), 256, 0, st>>>(
-            d_images, d_q, static_cast<const int16_t *>(s->d_dcoef), static_cast<uint8_t *>(s->d_planes));
+            d_images, d_q, static_cast<const int16_t *>(s->d_dcoef), static_cast<const int16_t *>(s->d_dc), static_cast<uint8_t *>(s->d_planes));
         V5_CUDA(h, cudaGetLastError());
         v5j::colour_kernel<<<dim3((unsigned)((P.max_groups + 255) / 256), (unsigned)cn), 256, 0, st>>>(
             d_images, static_cast<const uint8_t *>(s->d_planes), d_rgb, d_gray);

@@ -13,7 +13,8 @@
 //                   recorded state is the true one. A prefix sum of the blocks completed per subsequence gives every thread
 //                   its output position and a last pass decodes again, this time writing coefficients. Windows of 1024
 //                   subsequences are processed in order by the same CTA, carrying the exact state from one to the next.
-//   dc_kernel       one CTA per file: DC differences -> DC values (prefix sum per component, T.81 F.2.2.1)
+//   dc_kernel       one CTA per file: DC differences -> DC values (prefix sum per component, T.81 F.2.2.1) on a dense
+//                   int16-per-block array
 //   idct_kernel     dequantise + ISLOW inverse DCT, 4 threads per block -> sample planes
 //   colour_kernel   fancy upsample (A.7) + YCbCr -> RGB (A.8), and/or the luma plane alone
 //
@@ -154,11 +155,11 @@ V5_HOSTDEV uint32_t huff_action(const DecTable &t, uint32_t win)
 }
 
 // Decodes from state `s` until the bit position reaches `limit`; returns the number of blocks completed. WRITE: stores
-// every non-zero coefficient of block (block0 + completed) at coef[block * 64 + zigzag index] (DC as a difference);
+// every non-zero AC coefficient of block (block0 + completed) at coef[block * 64 + zigzag index] and its DC difference at dc[block];
 // blocks >= max_blocks (trailing padding bits decoded as symbols) are dropped.
 template <bool WRITE, class Src>
 V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
-                                int64_t block0, int64_t max_blocks)
+                                int16_t *dc, int64_t block0, int64_t max_blocks)
 {
     // One loop body for DC and AC symbols, selects instead of branches: the threads of a warp sit at unrelated places of
     // their blocks, and every divergent path would be paid for by all of them.
@@ -175,7 +176,10 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
         const int pos = z + zinc - 1;                                    // where a value lands: DC 0, AC z + run
         if (WRITE && sz && pos < 64 && block0 + done < max_blocks) {
             const int v = (int)((win << len) >> (32 - sz));
-            coef[(block0 + done) * 64 + pos] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+            // DC differences go to their own dense array (one int16 per block): the prefix sums that turn them into values
+            // then touch 2 bytes per block instead of one 128-byte line
+            int16_t *dst = is_dc ? dc + (block0 + done) : coef + (block0 + done) * 64 + pos;
+            *dst = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
         }
         z += zinc;
         p += (uint32_t)total;
@@ -209,6 +213,7 @@ struct HuffJob {
     int bpm;
     int64_t max_blocks;
     int16_t *coef;
+    int16_t *dc;                           // DC differences (later values), one per block
 };
 
 V5_HOSTDEV uint32_t sub_limit(const HuffJob &J, uint32_t j)
@@ -227,7 +232,7 @@ V5_HOSTDEV void huff_phase_first(int t, HuffWindow &W, const HuffJob &J, const D
     SubState st;
     if (t == 0) st = W.carry;
     else { st.p = j * SUB_BITS; st.c = 0; st.z = 0; }
-    W.info[t].n = decode_span<false>(J.staged, st, sub_limit(J, j), T, J.bpm, nullptr, 0, 0);
+    W.info[t].n = decode_span<false>(J.staged, st, sub_limit(J, j), T, J.bpm, nullptr, nullptr, 0, 0);
     W.info[t].s = st;
     W.cur[t] = st;
     W.done[t] = 0;
@@ -243,7 +248,7 @@ V5_HOSTDEV void huff_phase_round(int t, int r, HuffWindow &W, const HuffJob &J, 
         return;
     }
     SubState st = W.cur[t];
-    const uint32_t n = decode_span<false>(J.staged, st, sub_limit(J, w0 + (uint32_t)k), T, J.bpm, nullptr, 0, 0);
+    const uint32_t n = decode_span<false>(J.staged, st, sub_limit(J, w0 + (uint32_t)k), T, J.bpm, nullptr, nullptr, 0, 0);
     if (same_state(st, W.info[k].s)) W.done[t] = 1;                     // synchronised: the rest of the walk is already recorded
     W.info[k].s = st;                                                    // this thread entered k in a state at least as good
     W.info[k].n = n;                                                     // as the recorded one: its block count is the one to keep
@@ -256,26 +261,26 @@ V5_HOSTDEV void huff_phase_write(int t, HuffWindow &W, const HuffJob &J, const D
     const uint32_t j = w0 + (uint32_t)t;
     if (j >= J.nsub) return;
     SubState st = t == 0 ? W.carry : W.info[t - 1].s;
-    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, (int64_t)block0, J.max_blocks);
+    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)block0, J.max_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------- DC prediction
-// diff -> value for the blocks of one MCU given the running predictors; coefficients in place.
-V5_HOSTDEV void dc_apply_mcu(int16_t *mcu_coef, int bpm, int &py, int &pcb, int &pcr)
+// diff -> value for the blocks of one MCU (dense DC array: its bpm entries) given the running predictors; in place.
+V5_HOSTDEV void dc_apply_mcu(int16_t *mcu_dc, int bpm, int &py, int &pcb, int &pcr)
 {
     if (bpm == 1) {
-        py += mcu_coef[0];
-        mcu_coef[0] = (int16_t)py;
+        py += mcu_dc[0];
+        mcu_dc[0] = (int16_t)py;
         return;
     }
     for (int i = 0; i < 4; i++) {
-        py += mcu_coef[64 * i];
-        mcu_coef[64 * i] = (int16_t)py;
+        py += mcu_dc[i];
+        mcu_dc[i] = (int16_t)py;
     }
-    pcb += mcu_coef[64 * 4];
-    mcu_coef[64 * 4] = (int16_t)pcb;
-    pcr += mcu_coef[64 * 5];
-    mcu_coef[64 * 5] = (int16_t)pcr;
+    pcb += mcu_dc[4];
+    mcu_dc[4] = (int16_t)pcb;
+    pcr += mcu_dc[5];
+    mcu_dc[5] = (int16_t)pcr;
 }
 
 // ------------------------------------------------------------------------------------------- inverse DCT of a block
@@ -484,7 +489,7 @@ struct HuffSmem {
 };
 
 __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
-                                                          const uint32_t *stream_bits, int16_t *coef, int32_t *status)
+                                                          const uint32_t *stream_bits, int16_t *coef, int16_t *dc, int32_t *status)
 {
     extern __shared__ __align__(16) uint8_t huff_smem_raw[];
     HuffSmem &S = *reinterpret_cast<HuffSmem *>(huff_smem_raw);
@@ -505,6 +510,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
     J.bpm = im.bpm;
     J.max_blocks = im.blocks;
     J.coef = coef + im.coef_off * 64;
+    J.dc = dc + im.coef_off;
     if (t == 0) {
         S.W.carry.p = 0;
         S.W.carry.c = 0;
@@ -550,23 +556,23 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
 }
 
 // DC differences -> values. One CTA per file; thread t owns MCU chunk_base + t, three CTA scans per chunk of 1024 MCUs.
-__global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_t *coef)
+__global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_t *dc)
 {
     __shared__ uint32_t warp_sums[33];
     const DecImage im = images[blockIdx.x];
-    int16_t *base = coef + im.coef_off * 64;
+    int16_t *base = dc + im.coef_off;
     const int mcus = im.mcux * im.mcuy;
     int run[3] = {0, 0, 0};
     for (int m0 = 0; m0 < mcus; m0 += 1024) {
         const int m = m0 + (int)threadIdx.x;
-        int16_t *mc = base + (int64_t)m * im.bpm * 64;
+        int16_t *mc = base + (int64_t)m * im.bpm;
         int d[3] = {0, 0, 0};
         if (m < mcus) {
             if (im.bpm == 1) d[0] = mc[0];
             else {
-                d[0] = mc[0] + mc[64] + mc[128] + mc[192];
-                d[1] = mc[256];
-                d[2] = mc[320];
+                d[0] = mc[0] + mc[1] + mc[2] + mc[3];
+                d[1] = mc[4];
+                d[2] = mc[5];
             }
         }
         int pred[3];
@@ -582,7 +588,8 @@ __global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_
 
 // 64 blocks per CTA, 4 threads per block; the 8 KB of coefficients and the two quantisation tables are staged in shared
 // memory with 128-bit loads. grid = (ceil(max blocks / 64), files)
-__global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const uint16_t *qtabs, const int16_t *coef, uint8_t *planes)
+__global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const uint16_t *qtabs, const int16_t *coef, const int16_t *dc,
+                                                   uint8_t *planes)
 {
     __shared__ __align__(16) int16_t cz[64][64];
     __shared__ int16_t ws[64][64 + 8];
@@ -599,6 +606,8 @@ __global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const
         uint4 *dst = reinterpret_cast<uint4 *>(&cz[0][0]);
         for (int i = threadIdx.x; i < nb * 8; i += 256) dst[i] = __ldg(src + i);
     }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) cz[threadIdx.x][0] = dc[im.coef_off + g0 + threadIdx.x];        // DC values live in their own array
     __syncthreads();
     const int lb = (int)threadIdx.x >> 2, j = (int)threadIdx.x & 3;
     const bool active = lb < nb;

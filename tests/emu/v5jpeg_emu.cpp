@@ -125,6 +125,8 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     J.bpm = im.bpm;
     J.max_blocks = im.blocks;
     J.coef = coef.data();
+    std::vector<int16_t> dcv((size_t)im.blocks, 0);
+    J.dc = dcv.data();
     HuffWindow *W = new HuffWindow();
     memset(W, 0xA5, sizeof(*W));
     W->carry.p = 0; W->carry.c = 0; W->carry.z = 0;
@@ -155,7 +157,8 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     const bool ok = W->base_blocks >= (uint32_t)im.blocks;
     if (rounds_out) *rounds_out = max_rounds;
     int py = 0, pcb = 0, pcr = 0;
-    for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&coef[(size_t)mcu * im.bpm * 64], im.bpm, py, pcb, pcr);
+    for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&dcv[(size_t)mcu * im.bpm], im.bpm, py, pcb, pcr);
+    for (int g = 0; g < im.blocks; g++) coef[(size_t)g * 64] = dcv[(size_t)g];     // what idct_kernel does while staging a block
     if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
     std::vector<uint8_t> planes((size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch);
     uint8_t n2z[64];

@@ -302,7 +302,7 @@ struct DecPlan {                               // host-side description of one c
     std::vector<char> contiguous;              // file k follows file k-1 in host memory closely enough to share one upload
     size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0;
     int max_blocks = 0;
-    int64_t max_groups = 0;                    // 4-pixel groups of the largest image
+    int64_t max_groups = 0;                    // 8-pixel groups of the largest image
 };
 
 }  // namespace
@@ -421,7 +421,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         P->coef_blocks += (size_t)im.blocks;
         P->plane_bytes += align_up(planes, 16);
         if (im.blocks > P->max_blocks) P->max_blocks = im.blocks;
-        if ((int64_t)F.h * ((F.w + 3) / 4) > P->max_groups) P->max_groups = (int64_t)F.h * ((F.w + 3) / 4);
+        if ((int64_t)F.h * ((F.w + 7) / 8) > P->max_groups) P->max_groups = (int64_t)F.h * ((F.w + 7) / 8);
         P->images.push_back(im);
         P->file_index.push_back(i);
     }

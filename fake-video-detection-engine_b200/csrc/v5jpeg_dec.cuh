@@ -284,19 +284,24 @@ V5_HOSTDEV void dc_apply_mcu(int16_t *mcu_dc, int bpm, int &py, int &pcb, int &p
 }
 
 // ------------------------------------------------------------------------------------------- inverse DCT of a block
-// thread j of 4: columns 2j, 2j+1 (dequantised) -> ws; then rows 2j, 2j+1 -> 8 clamped samples each
-V5_DEV void idct_cols(const int16_t *coef_zz, const uint16_t *qt, const uint8_t *zz, int j, int16_t *ws)
+// `nat`: the block's 64 coefficients in NATURAL order (8 rows of 8 int16, 16-byte rows), `qt` likewise. Thread j of 4 takes
+// columns 2j, 2j+1 — one 32-bit word per row — dequantises, runs the column pass and leaves int16 pairs in ws; then rows
+// 2j, 2j+1 (one 128-bit load each) -> 8 clamped samples each.
+V5_DEV void idct_cols(const int16_t *nat, const uint16_t *qt, int j, int16_t *ws)
 {
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(nat), *qw = reinterpret_cast<const uint32_t *>(qt);
+    uint32_t *ww = reinterpret_cast<uint32_t *>(ws);
+    int a[8], b[8];
 #pragma unroll
-    for (int cc = 0; cc < 2; cc++) {
-        const int c = 2 * j + cc;
-        int v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (int)coef_zz[zz[8 * k + c]] * (int)qt[8 * k + c];
-        v5::idct8<1, false>(v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) ws[8 * k + c] = (int16_t)v[k];
+    for (int k = 0; k < 8; k++) {
+        const uint32_t c = cw[4 * k + j], q = qw[4 * k + j];
+        a[k] = v5::s16_lo(c) * (int)(q & 0xffffu);
+        b[k] = v5::s16_hi(c) * (int)(q >> 16);
     }
+    v5::idct8<1, false>(a);
+    v5::idct8<1, false>(b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ww[4 * k + j] = v5::pack_s16(a[k], b[k]);
 }
 
 V5_DEV void idct_rows(const int16_t *ws, int j, uint8_t *dst, int pitch)
@@ -304,9 +309,8 @@ V5_DEV void idct_rows(const int16_t *ws, int j, uint8_t *dst, int pitch)
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const int r = 2 * j + rr;
-        int v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = ws[8 * r + k];
+        const v5::U4 w = *reinterpret_cast<const v5::U4 *>(ws + 8 * r);
+        int v[8] = {v5::s16_lo(w.x), v5::s16_hi(w.x), v5::s16_lo(w.y), v5::s16_hi(w.y), v5::s16_lo(w.z), v5::s16_hi(w.z), v5::s16_lo(w.w), v5::s16_hi(w.w)};
         v5::idct8<1, true>(v);
         // plane rows are 8-byte aligned (plane offsets are multiples of 16, pitches multiples of 8)
         *reinterpret_cast<v5::U2 *>(dst + r * pitch) = v5::U2{v5::pack4sat(v[0], v[1], v[2], v[3]), v5::pack4sat(v[4], v[5], v[6], v[7])};
@@ -368,42 +372,59 @@ V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int 
     out[2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
 }
 
-// Four consecutive pixels x0 .. x0+3 (x0 a multiple of 4) of row y: same arithmetic as pixel_rgb with the chroma loads shared.
-// out: 12 bytes R G B R G B ...; pixels at or beyond the image width are left untouched.
-V5_HOSTDEV void pixels4_rgb(const DecImage &im, const uint8_t *planes, int x0, int y, uint8_t out[12])
+// Eight consecutive pixels x0 .. x0+7 (x0 a multiple of 8) of row y: same arithmetic as pixel_rgb with the loads shared —
+// two 32-bit words of luma and, per chroma component and row, one aligned word plus the two neighbours beside it.
+// out: 24 bytes R G B R G B ...; pixels at or beyond the image width are left untouched.
+V5_HOSTDEV uint32_t load_u32(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const uint32_t *>(p);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+
+V5_HOSTDEV void pixels8_rgb(const DecImage &im, const uint8_t *planes, int x0, int y, uint8_t out[24])
 {
     const uint8_t *yrow = planes + (int64_t)y * im.yw + x0;
+    const uint32_t yw[2] = {load_u32(yrow), load_u32(yrow + 4)};
+    const int nvalid = im.w - x0 < 8 ? im.w - x0 : 8;
     if (im.ncomp == 1) {
-        for (int k = 0; k < 4 && x0 + k < im.w; k++) out[3 * k] = out[3 * k + 1] = out[3 * k + 2] = yrow[k];
+        for (int k = 0; k < nvalid; k++) out[3 * k] = out[3 * k + 1] = out[3 * k + 2] = (uint8_t)(yw[k >> 2] >> (8 * (k & 3)));
         return;
     }
     const uint8_t *cbp = planes + (int64_t)im.yw * im.yh, *crp = cbp + (int64_t)im.cw * im.ch;
     const int hc = (im.h + 1) >> 1, wc = (im.w + 1) >> 1, cw = im.cw;
-    const int r = y >> 1, cx0 = x0 >> 1;
+    const int r = y >> 1, cx0 = x0 >> 1;                                  // cx0 is a multiple of 4
     int nb = (y & 1) ? r + 1 : r - 1;
     nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
-    const uint8_t *cb_r = cbp + (int64_t)r * cw, *cb_n = cbp + (int64_t)nb * cw, *cr_r = crp + (int64_t)r * cw, *cr_n = crp + (int64_t)nb * cw;
-    int sb[4], sr[4];                                                     // 3 * cur + neighbour row at chroma columns cx0-1 .. cx0+2
+    const uint8_t *rows[4] = {cbp + (int64_t)r * cw, cbp + (int64_t)nb * cw, crp + (int64_t)r * cw, crp + (int64_t)nb * cw};
+    const int cl = cx0 > 0 ? cx0 - 1 : 0, cr_ = cx0 + 4 < wc ? cx0 + 4 : wc - 1;   // neighbours beside the word, clamped
+    int s[2][6];                                                          // 3 * cur + neighbour row at chroma columns cx0-1 .. cx0+4
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int col = cx0 - 1 + j;
-        col = col < 0 ? 0 : (col > wc - 1 ? wc - 1 : col);
-        sb[j] = 3 * cb_r[col] + cb_n[col];
-        sr[j] = 3 * cr_r[col] + cr_n[col];
+    for (int c = 0; c < 2; c++) {
+        const uint32_t wr = load_u32(rows[2 * c] + cx0), wn = load_u32(rows[2 * c + 1] + cx0);
+        s[c][0] = 3 * rows[2 * c][cl] + rows[2 * c + 1][cl];
+        s[c][5] = 3 * rows[2 * c][cr_] + rows[2 * c + 1][cr_];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int col = cx0 + j < wc ? j : wc - 1 - cx0;                    // columns past the last one repeat it (col >= 0: cx0 < wc)
+            s[c][1 + j] = 3 * (int)((wr >> (8 * col)) & 0xffu) + (int)((wn >> (8 * col)) & 0xffu);
+        }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (x0 + k >= im.w) break;
+    for (int k = 0; k < 8; k++) {
+        if (k >= nvalid) break;
         const int j = 1 + (k >> 1), jn = (k & 1) ? j + 1 : j - 1, bias = (k & 1) ? 7 : 8;
         int cb, cr;
         if (wc <= 2) {
-            cb = cb_r[cx0 + (k >> 1)];
-            cr = cr_r[cx0 + (k >> 1)];
+            cb = rows[0][cx0 + (k >> 1)];
+            cr = rows[2][cx0 + (k >> 1)];
         } else {
-            cb = (3 * sb[j] + sb[jn] + bias) >> 4;
-            cr = (3 * sr[j] + sr[jn] + bias) >> 4;
+            cb = (3 * s[0][j] + s[0][jn] + bias) >> 4;
+            cr = (3 * s[1][j] + s[1][jn] + bias) >> 4;
         }
-        const int yy = yrow[k], cbd = cb - 128, crd = cr - 128;
+        const int yy = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xffu), cbd = cb - 128, crd = cr - 128;
         out[3 * k] = (uint8_t)v5::clamp255(yy + ((91881 * crd + 32768) >> 16));
         out[3 * k + 1] = (uint8_t)v5::clamp255(yy + ((-22554 * cbd - 46802 * crd + 32768) >> 16));
         out[3 * k + 2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
@@ -412,6 +433,9 @@ V5_HOSTDEV void pixels4_rgb(const DecImage &im, const uint8_t *planes, int x0, i
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------- kernels
+__constant__ uint8_t kZigzagToNaturalDev[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                                41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                                30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 __constant__ uint8_t kNaturalToZigzagDev[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
                                                 41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
                                                 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
@@ -586,28 +610,35 @@ __global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_
     }
 }
 
-// 64 blocks per CTA, 4 threads per block; the 8 KB of coefficients and the two quantisation tables are staged in shared
-// memory with 128-bit loads. grid = (ceil(max blocks / 64), files)
+// 64 blocks per CTA, 4 threads per block. The 8 KB of coefficients come in with 128-bit loads and are scattered into natural
+// order on the way into shared memory (one 16-bit store per coefficient, once), so that both passes work on packed words.
+// grid = (ceil(max blocks / 64), files)
 __global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const uint16_t *qtabs, const int16_t *coef, const int16_t *dc,
                                                    uint8_t *planes)
 {
-    __shared__ __align__(16) int16_t cz[64][64];
-    __shared__ int16_t ws[64][64 + 8];
-    __shared__ uint16_t qt[2][64];
-    __shared__ uint8_t zz[64];
+    __shared__ __align__(16) int16_t nat[64][64 + 8];                      // natural order; 144-byte block stride
+    __shared__ __align__(16) int16_t ws[64][64 + 8];
+    __shared__ __align__(16) uint16_t qt[2][64];
+    __shared__ uint8_t z2n[64];
     const DecImage im = images[blockIdx.y];
     const int g0 = (int)blockIdx.x * 64;
     if (g0 >= im.blocks) return;
     const int nb = im.blocks - g0 < 64 ? im.blocks - g0 : 64;
-    if (threadIdx.x < 64) zz[threadIdx.x] = kNaturalToZigzagDev[threadIdx.x];
+    if (threadIdx.x < 64) z2n[threadIdx.x] = kZigzagToNaturalDev[threadIdx.x];
     if (threadIdx.x < 128) (&qt[0][0])[threadIdx.x] = qtabs[(int64_t)im.qt * 128 + threadIdx.x];
+    __syncthreads();
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(coef + (im.coef_off + g0) * 64);
-        uint4 *dst = reinterpret_cast<uint4 *>(&cz[0][0]);
-        for (int i = threadIdx.x; i < nb * 8; i += 256) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < nb * 8; i += 256) {                  // 8 consecutive zigzag positions of one block
+            const uint4 v = __ldg(src + i);
+            const int b = i >> 3, k0 = (i & 7) * 8;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) nat[b][z2n[k0 + e]] = (int16_t)(w[e >> 1] >> (16 * (e & 1)));
+        }
     }
     __syncthreads();
-    if ((int)threadIdx.x < nb) cz[threadIdx.x][0] = dc[im.coef_off + g0 + threadIdx.x];        // DC values live in their own array
+    if ((int)threadIdx.x < nb) nat[threadIdx.x][0] = dc[im.coef_off + g0 + threadIdx.x];        // DC values live in their own array
     __syncthreads();
     const int lb = (int)threadIdx.x >> 2, j = (int)threadIdx.x & 3;
     const bool active = lb < nb;
@@ -615,39 +646,39 @@ __global__ void __launch_bounds__(256) idct_kernel(const DecImage *images, const
     int64_t off = 0;
     if (active) {
         off = block_dest(im, g0 + lb, pitch, comp);
-        idct_cols(cz[lb], qt[comp ? 1 : 0], zz, j, ws[lb]);
+        idct_cols(nat[lb], qt[comp ? 1 : 0], j, ws[lb]);
     }
     __syncwarp();
     if (active) idct_rows(ws[lb], j, planes + im.plane_off + off, pitch);
 }
 
-// one thread per 4 pixels of a row. grid = (ceil(max pixel groups / 256), files)
+// one thread per 8 pixels of a row. grid = (ceil(max pixel groups / 256), files)
 __global__ void __launch_bounds__(256) colour_kernel(const DecImage *images, const uint8_t *planes, uint8_t *rgb_out, uint8_t *gray_out)
 {
     const DecImage im = images[blockIdx.y];
-    const int groups = (im.w + 3) >> 2;
+    const int groups = (im.w + 7) >> 3;
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= (int64_t)im.h * groups) return;
-    const int y = (int)(i / groups), x0 = 4 * (int)(i - (int64_t)y * groups);
+    const int y = (int)(i / groups), x0 = 8 * (int)(i - (int64_t)y * groups);
     const uint8_t *pl = planes + im.plane_off;
-    const int nvalid = im.w - x0 < 4 ? im.w - x0 : 4;
+    const int nvalid = im.w - x0 < 8 ? im.w - x0 : 8;
     const int64_t px = (int64_t)y * im.w + x0;
     if (im.gray_off >= 0) {
         uint8_t *d = gray_out + im.gray_off + px;
-        const uint32_t v = *reinterpret_cast<const uint32_t *>(pl + (int64_t)y * im.yw + x0);     // plane rows are 8-byte aligned
-        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t *>(d) = v;
+        const uint2 v = *reinterpret_cast<const uint2 *>(pl + (int64_t)y * im.yw + x0);          // plane rows are 8-byte aligned
+        if (nvalid == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) *reinterpret_cast<uint2 *>(d) = v;
         else
-            for (int k = 0; k < nvalid; k++) d[k] = (uint8_t)(v >> (8 * k));
+            for (int k = 0; k < nvalid; k++) d[k] = (uint8_t)((k < 4 ? v.x : v.y) >> (8 * (k & 3)));
     }
     if (im.rgb_off >= 0) {
-        alignas(4) uint8_t o[12];
-        pixels4_rgb(im, pl, x0, y, o);
+        alignas(8) uint8_t o[24];
+        pixels8_rgb(im, pl, x0, y, o);
         uint8_t *d = rgb_out + im.rgb_off + 3 * px;
-        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) {
-            const uint32_t *ow = reinterpret_cast<const uint32_t *>(o);
-            reinterpret_cast<uint32_t *>(d)[0] = ow[0];
-            reinterpret_cast<uint32_t *>(d)[1] = ow[1];
-            reinterpret_cast<uint32_t *>(d)[2] = ow[2];
+        if (nvalid == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+            const uint2 *ow = reinterpret_cast<const uint2 *>(o);
+            reinterpret_cast<uint2 *>(d)[0] = ow[0];
+            reinterpret_cast<uint2 *>(d)[1] = ow[1];
+            reinterpret_cast<uint2 *>(d)[2] = ow[2];
         } else {
             for (int k = 0; k < 3 * nvalid; k++) d[k] = o[k];
         }

@@ -161,20 +161,21 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     for (int g = 0; g < im.blocks; g++) coef[(size_t)g * 64] = dcv[(size_t)g];     // what idct_kernel does while staging a block
     if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
     std::vector<uint8_t> planes((size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch);
-    uint8_t n2z[64];
-    for (int i = 0; i < 64; i++) n2z[kZigzag[i]] = (uint8_t)i;
     for (int g = 0; g < im.blocks; g++) {
         int pitch, comp;
         const int64_t off = block_dest(im, g, pitch, comp);
-        int16_t ws[64];
-        for (int j = 0; j < 4; j++) idct_cols(&coef[(size_t)g * 64], F->qt[comp ? 1 : 0], n2z, j, ws);
+        alignas(16) int16_t nat[64], ws[64];
+        for (int k = 0; k < 64; k++) nat[kZigzag[k]] = coef[(size_t)g * 64 + k];       // the kernel scatters while staging
+        alignas(16) uint16_t qt[64];
+        memcpy(qt, F->qt[comp ? 1 : 0], sizeof(qt));
+        for (int j = 0; j < 4; j++) idct_cols(nat, qt, j, ws);
         for (int j = 0; j < 4; j++) idct_rows(ws, j, planes.data() + off, pitch);
     }
     for (int y = 0; y < im.h; y++)
-        for (int x0 = 0; x0 < im.w; x0 += 4) {
-            uint8_t o[12], single[3];
-            pixels4_rgb(im, planes.data(), x0, y, o);                       // what the kernel runs
-            for (int k = 0; k < 4 && x0 + k < im.w; k++) {
+        for (int x0 = 0; x0 < im.w; x0 += 8) {
+            uint8_t o[24], single[3];
+            pixels8_rgb(im, planes.data(), x0, y, o);                       // what the kernel runs
+            for (int k = 0; k < 8 && x0 + k < im.w; k++) {
                 const int x = x0 + k;
                 if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
                 pixel_rgb(im, planes.data(), x, y, single);                 // the one-pixel statement of the same arithmetic

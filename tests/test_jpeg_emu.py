@@ -137,3 +137,80 @@ def test_unsupported_files_are_refused(emu):
     ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3])
     with pytest.raises(ValueError):
         emu_decode(emu, enc.tobytes())
+
+
+# ---------------------------------------------------------------------------------------------- header parser robustness
+def _segments(data):
+    """[(marker, payload bytes)] of the header part, and the rest (entropy data + EOI)."""
+    out, i = [], 2
+    while True:
+        assert data[i] == 0xFF
+        m = data[i + 1]
+        length = (data[i + 2] << 8) | data[i + 3]
+        out.append((m, data[i + 4:i + 2 + length]))
+        i += 2 + length
+        if m == 0xDA:
+            return out, data[i:]
+
+
+def _assemble(segs, rest):
+    b = bytearray(b"\xff\xd8")
+    for m, payload in segs:
+        b += bytes([0xFF, m]) + (len(payload) + 2).to_bytes(2, "big") + payload
+    return bytes(b) + rest
+
+
+def test_parser_accepts_equivalent_header_layouts(emu):
+    """Other writers lay the same baseline stream out differently: all tables in one DHT / DQT segment, 16-bit quantisation
+    entries, comment and application segments, fill bytes before markers. Decoded pixels must not change."""
+    rgb = golden_frame({"spec": ["gen", 5, 1], "h": 70, "w": 90})
+    buf = io.BytesIO()
+    Image.fromarray(rgb).save(buf, "JPEG", quality=85)
+    data = buf.getvalue()
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+    segs, rest = _segments(data)
+    dht = b"".join(p for m, p in segs if m == 0xC4)
+    dqt = b"".join(p for m, p in segs if m == 0xDB)
+    merged = [(m, p) for m, p in segs if m not in (0xC4, 0xDB, 0xC0, 0xDA)]
+    merged += [(0xFE, b"a comment"), (0xE1, b"Exif\x00\x00" + bytes(40)), (0xDB, dqt), (0xC4, dht)]
+    merged += [(m, p) for m, p in segs if m in (0xC0, 0xDA)]
+    variant = _assemble(merged, rest)
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(variant)).convert("RGB")), ref)      # Pillow agrees it is the same image
+    assert np.array_equal(emu_decode(emu, variant)["rgb"], ref)
+    # 16-bit quantisation table entries (Pq = 1)
+    wide = bytearray()
+    j = 0
+    while j < len(dqt):
+        wide += bytes([0x10 | dqt[j]]) + b"".join(bytes([0, v]) for v in dqt[j + 1:j + 65])
+        j += 65
+    v16 = _assemble([(m, bytes(wide) if m == 0xDB else p) for m, p in merged], rest)
+    assert np.array_equal(emu_decode(emu, v16)["rgb"], ref)
+    # fill bytes (FF FF) before a marker
+    i = variant.index(b"\xff\xc0")
+    assert np.array_equal(emu_decode(emu, variant[:i] + b"\xff\xff" + variant[i:])["rgb"], ref)
+    # trailing garbage after EOI
+    assert np.array_equal(emu_decode(emu, data + b"\x00\x01garbage\xff")["rgb"], ref)
+
+
+def test_parser_refuses_what_the_kernels_do_not_implement(emu):
+    rgb = golden_frame({"spec": ["gen", 5, 1], "h": 40, "w": 48})
+    buf = io.BytesIO()
+    Image.fromarray(rgb).save(buf, "JPEG", quality=85)
+    data = buf.getvalue()
+    i = data.index(b"\xff\xc0")
+    twelve = bytearray(data)
+    twelve[i + 4] = 12                                                   # sample precision
+    with pytest.raises(ValueError):
+        emu_decode(emu, bytes(twelve))
+    cmyk = io.BytesIO()
+    Image.fromarray(np.dstack([rgb, rgb[..., 0]]), "CMYK").save(cmyk, "JPEG", quality=85)
+    with pytest.raises(ValueError):
+        emu_decode(emu, cmyk.getvalue())
+    for kw in ({"subsampling": 1}, {"subsampling": 0}):                  # 4:2:2, 4:4:4
+        b2 = io.BytesIO()
+        Image.fromarray(rgb).save(b2, "JPEG", quality=85, **kw)
+        with pytest.raises(ValueError):
+            emu_decode(emu, b2.getvalue())
+    for bad in (b"", b"\xff\xd8", data[:20], b"\x89PNG\r\n\x1a\n" + bytes(32), data[:i + 4]):
+        with pytest.raises(ValueError):
+            emu_decode(emu, bad)

@@ -335,6 +335,7 @@ def run_native_arm(args):
 
             enc, enc_sizes = jpeg.encode_batch(frames, 95)                  # warm-up (workspace allocation), then timed once
             torch.cuda.synchronize()
+            del enc, enc_sizes                                              # let the timed call reuse the 1.6 GB output block
             e0.record()
             enc, enc_sizes = jpeg.encode_batch(frames, 95)
             e1.record()

@@ -131,10 +131,11 @@ int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, 
     }
     V5_CUDA(h, cudaMemcpyAsync(s->d_header, header.data(), header.size(), cudaMemcpyHostToDevice, st));
 
-    // images per pass: keep the workspace (coefficients 128 B/block, offsets, unstuffed stream) under ~1 GiB
+    // images per pass: keep the workspace (coefficients 128 B/block, offsets, unstuffed stream) under ~8 GiB (one pass for a
+    // few hundred 1080p frames: the per-image-CTA kernels cost the same for 8 images as for 148)
     const int64_t raw_words = (out_stride_bytes + 3) / 4;
     const size_t per_image = (size_t)g.blocks * (128 + 4) + (size_t)raw_words * 4 + 16;
-    int chunk = (int)((size_t)(1u << 30) / per_image);
+    int chunk = (int)(((size_t)8 << 30) / per_image);
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
     if (chunk > 65535) chunk = 65535;

@@ -37,7 +37,8 @@ struct v5jpeg_state {
     cudaStream_t upload_stream = nullptr;
     int toggle = 0;
     void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr, *d_dc = nullptr;
-    size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0, dc_cap = 0;
+    void *d_sub_info = nullptr, *d_sub_block0 = nullptr;
+    size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0, dc_cap = 0, sub_info_cap = 0, sub_block0_cap = 0;
     uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
     int32_t *d_dec_status = nullptr;
     size_t dec_rgb_cap = 0, dec_gray_cap = 0, dec_status_cap = 0;
@@ -69,6 +70,8 @@ void v5jpeg_release(v5ela_handle *h)
     cudaFree(s->d_bits);
     cudaFree(s->d_status);
     cudaFree(s->d_dc);
+    cudaFree(s->d_sub_info);
+    cudaFree(s->d_sub_block0);
     cudaFree(s->d_dec_rgb);
     cudaFree(s->d_dec_gray);
     cudaFree(s->d_dec_status);
@@ -301,7 +304,8 @@ struct DecPlan {                               // host-side description of one c
     std::vector<v5j::DecImage> images;
     std::vector<int> file_index;
     std::vector<char> contiguous;              // file k follows file k-1 in host memory closely enough to share one upload
-    size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0;
+    size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0, subs = 0;
+    uint32_t max_windows = 1;
     int max_blocks = 0;
     int64_t max_groups = 0;                    // 8-pixel groups of the largest image
 };
@@ -330,6 +334,8 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
             V5_CUDA(h, cudaEventCreateWithFlags(&s->consumed[b], cudaEventDisableTiming));
         }
         V5_CUDA(h, cudaFuncSetAttribute(v5j::huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v5j::HuffSmem)));
+        V5_CUDA(h, cudaFuncSetAttribute(v5j::huffman_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v5j::HuffSmem)));
+        V5_CUDA(h, cudaFuncSetAttribute(v5j::huffman_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(v5j::HuffSmem)));
     }
 
     // ---- parse every file; unique Huffman table sets and quantisation table pairs
@@ -412,6 +418,11 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         im.scan_len = (int64_t)F.scan_len;
         im.stream_off = (int64_t)P->stream_bytes;
         im.coef_off = (int64_t)P->coef_blocks;
+        im.sub_off = (int64_t)P->subs;
+        const size_t nsub_max = (F.scan_len * 8 + v5j::SUB_BITS - 1) / v5j::SUB_BITS + 1;
+        P->subs += nsub_max;
+        const uint32_t wmax = (uint32_t)((nsub_max + v5j::HUFF_NT - 1) / v5j::HUFF_NT);
+        if (wmax > P->max_windows) P->max_windows = wmax;
         im.plane_off = (int64_t)P->plane_bytes;
         im.rgb_off = d_rgb ? (rgb_offsets ? rgb_offsets[i] : rgb_run) : -1;
         im.gray_off = d_gray ? (gray_offsets ? gray_offsets[i] : gray_run) : -1;
@@ -456,6 +467,8 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         if ((rc = ensure(h, &s->d_bits, &s->bits_cap, sizeof(uint32_t) * (size_t)cn))) return rc;
         if ((rc = ensure(h, &s->d_status, &s->status_cap, sizeof(int32_t) * (size_t)cn))) return rc;
         if ((rc = ensure(h, &s->d_dc, &s->dc_cap, sizeof(int16_t) * P.coef_blocks))) return rc;
+        if ((rc = ensure(h, &s->d_sub_info, &s->sub_info_cap, sizeof(v5j::SubInfo) * P.subs))) return rc;
+        if ((rc = ensure(h, &s->d_sub_block0, &s->sub_block0_cap, sizeof(uint32_t) * P.subs))) return rc;
         uint8_t *stage_host = s->stage_host[b], *d_stage = s->d_stage[b];
         for (int k = 0; k < cn; k++) P.images[(size_t)k].scan_off += (int64_t)off_scan;
         if (!all_pinned)
@@ -497,9 +510,30 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         int32_t *d_st = static_cast<int32_t *>(s->d_status);
         v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
         V5_CUDA(h, cudaGetLastError());
-        v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, static_cast<const uint8_t *>(s->d_streams), d_bits,
-                                                        static_cast<int16_t *>(s->d_dcoef), static_cast<int16_t *>(s->d_dc), d_st);
-        V5_CUDA(h, cudaGetLastError());
+        // Huffman decoding in three launches: synchronisation (the windows of a file shared out among `parts` CTAs so that a
+        // small batch still fills the GPU), boundary fix-up + block offsets, then one CTA per window writes coefficients.
+        // (a batch of at least one file per SM gains nothing from splitting files: parts = 1, no blind starts, no fix-up walks)
+        unsigned parts = (unsigned)(h->sm_count / cn);
+        parts = parts < 1 ? 1 : (parts > 16 ? 16 : parts);
+        parts = parts > P.max_windows ? P.max_windows : parts;
+        const uint8_t *d_str = static_cast<const uint8_t *>(s->d_streams);
+        v5j::SubInfo *d_sub_info = static_cast<v5j::SubInfo *>(s->d_sub_info);
+        uint32_t *d_sub_block0 = static_cast<uint32_t *>(s->d_sub_block0);
+        const char *force = getenv("V5ELA_HUFF_PATH");                    // tests: "one" / "three" force a path
+        const bool one_launch = force ? force[0] == 'o' : h->sm_count / cn < 2;   // no room for two parts per file: nothing to gain
+        if (one_launch) {
+            v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, d_str, d_bits, static_cast<int16_t *>(s->d_dcoef),
+                                                                            static_cast<int16_t *>(s->d_dc), d_st);
+            V5_CUDA(h, cudaGetLastError());
+        } else {
+            v5j::huffman_sync_kernel<<<dim3(parts, (unsigned)cn), v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, d_str, d_bits, d_sub_info);
+            V5_CUDA(h, cudaGetLastError());
+            v5j::huffman_fixup_kernel<<<cn, 1024, 0, st>>>(d_images, d_tabs, d_str, d_bits, parts, d_sub_info, d_sub_block0, d_st);
+            V5_CUDA(h, cudaGetLastError());
+            v5j::huffman_write_kernel<<<dim3(P.max_windows, (unsigned)cn), v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(
+                d_images, d_tabs, d_str, d_bits, d_sub_info, d_sub_block0, static_cast<int16_t *>(s->d_dcoef), static_cast<int16_t *>(s->d_dc));
+            V5_CUDA(h, cudaGetLastError());
+        }
         v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dc));
         V5_CUDA(h, cudaGetLastError());
         v5j::idct_kernel<<<dim3((unsigned)((P.max_blocks + 63) / 64), (unsigned)cn), 256, 0, st>>>(
@@ -511,7 +545,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         if (d_status)                                                      // chunks keep file order: one contiguous range
             V5_CUDA(h, cudaMemcpyAsync(d_status + P.file_index[0], d_st, sizeof(int32_t) * (size_t)cn, cudaMemcpyDeviceToDevice, st));
         V5_CUDA(h, cudaEventRecord(s->consumed[b], st));
-        h->launches += 5;
+        h->launches += one_launch ? 5 : 7;
     }
     return V5ELA_OK;
 }

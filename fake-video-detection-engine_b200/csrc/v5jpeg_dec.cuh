@@ -53,6 +53,7 @@ struct DecImage {
     int64_t scan_off, scan_len;            // entropy-coded segment inside the uploaded file bytes
     int64_t stream_off;                    // unstuffed stream inside the stream buffer (16-byte aligned)
     int64_t coef_off;                      // first block inside the coefficient buffer
+    int64_t sub_off;                       // first subsequence inside the per-subsequence arrays (sub_info, sub_block0)
     int64_t plane_off;                     // Y plane inside the plane buffer; Cb follows, then Cr
     int64_t rgb_off, gray_off;             // output positions (bytes), -1 = not wanted
 };
@@ -201,8 +202,8 @@ struct HuffWindow {
     SubInfo info[HUFF_NT];                 // info[t]: exit state of subsequence w0 + t, blocks completed inside it
     SubState cur[HUFF_NT];                 // travelling state of thread t
     uint8_t done[HUFF_NT];
-    SubState carry;                        // exact state at the start of the window
-    uint32_t base_blocks;                  // blocks completed before the window
+    SubState carry;                        // state at the start of the window (exact, or a part's blind start)
+    uint32_t base_blocks;                  // huffman_kernel: blocks completed before the window
 };
 
 struct HuffJob {
@@ -262,6 +263,51 @@ V5_HOSTDEV void huff_phase_write(int t, HuffWindow &W, const HuffJob &J, const D
     if (j >= J.nsub) return;
     SubState st = t == 0 ? W.carry : W.info[t - 1].s;
     decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)block0, J.max_blocks);
+}
+
+// ---- small batches: a file's windows spread over several CTAs -------------------------------------------------------------
+// A file's windows are shared out among `parts` CTAs (huffman_sync_kernel); part q owns windows part_first(q) .. part_first(q+1)-1.
+V5_HOSTDEV uint32_t window_count(uint32_t nsub) { return (nsub + (uint32_t)HUFF_NT - 1) / (uint32_t)HUFF_NT; }
+V5_HOSTDEV uint32_t part_count(uint32_t nsub, uint32_t max_parts)
+{
+    const uint32_t w = window_count(nsub);
+    return w < max_parts ? (w ? w : 1u) : (max_parts ? max_parts : 1u);
+}
+V5_HOSTDEV uint32_t part_first(uint32_t q, uint32_t parts, uint32_t windows) { return (uint32_t)(((uint64_t)q * windows) / parts); }
+
+// Boundary fix-up between two parts: every part but the first began blind, so its records are only true from the point where
+// its own chain fell into step. The walker enters subsequence j0 (the first of a part) in the TRUE state — the exit state of
+// the subsequence before it — and re-records subsequences until it leaves one in the recorded state. One thread, reading the
+// stream in place. Returns the number of subsequences it had to re-record. A walker that reaches the end of its part without
+// meeting a recorded state has changed the next part's entry state; the caller notices and redoes that boundary.
+V5_HOSTDEV uint32_t fixup_walk(const uint8_t *stream, uint32_t total_bits, const DecTabSet &T, int bpm, SubInfo *sub_info,
+                               uint32_t j0, uint32_t j_end /* first subsequence of the next part: a walker stays inside its part */)
+{
+    ByteStream bs;
+    bs.data = stream;
+    SubState st = sub_info[j0 - 1].s;
+    uint32_t rewritten = 0;
+    for (uint32_t j = j0; j < j_end; j++) {
+        const uint64_t e = (uint64_t)(j + 1) * SUB_BITS;
+        const uint32_t n = decode_span<false>(bs, st, e < total_bits ? (uint32_t)e : total_bits, T, bpm, nullptr, nullptr, 0, 0);
+        const bool met = same_state(st, sub_info[j].s);
+        sub_info[j].s = st;
+        sub_info[j].n = n;                                               // counted from the true entry state
+        if (met) break;
+        rewritten++;
+    }
+    return rewritten;
+}
+
+// write pass of one window (huffman_write_kernel): entry state and first block index come from the per-subsequence records
+V5_HOSTDEV void huff_write_sub(int t, const HuffJob &J, const DecTabSet &T, uint32_t w0, const SubInfo *sub_info, const uint32_t *sub_block0)
+{
+    const uint32_t j = w0 + (uint32_t)t;
+    if (j >= J.nsub) return;
+    SubState st;
+    if (j == 0) { st.p = 0; st.c = 0; st.z = 0; }
+    else st = sub_info[j - 1].s;
+    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)sub_block0[j], J.max_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------- DC prediction
@@ -512,6 +558,8 @@ struct HuffSmem {
     uint16_t live[HUFF_NT];                // subsequences still walking (rounds >= 2)
 };
 
+// Large batches (at least one file per SM): the whole job in one launch, one CTA per file — synchronise a window, scan, write
+// its coefficients, carry the exact state into the next window.
 __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
                                                           const uint32_t *stream_bits, int16_t *coef, int16_t *dc, int32_t *status)
 {
@@ -577,6 +625,151 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
     }
     // a well-formed stream holds exactly `blocks` blocks (trailing pad bits may decode into at most a few phantom ones)
     if (t == 0) status[blockIdx.x] = S.W.base_blocks >= (uint32_t)im.blocks ? 0 : -1;
+}
+
+// Small batches: three launches, so that a handful of files still fill the GPU.
+// Pass 1: synchronisation. grid = (max parts, files); CTA (q, f) walks the windows of part q of file f in order and leaves the
+// exit state and block count of every subsequence in sub_info. Part 0 starts in the true state, the others blind.
+__global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_sync_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+                                                               const uint32_t *stream_bits, SubInfo *sub_info_all)
+{
+    extern __shared__ __align__(16) uint8_t huff_smem_raw[];
+    HuffSmem &S = *reinterpret_cast<HuffSmem *>(huff_smem_raw);
+    const int t = (int)threadIdx.x;
+    const DecImage im = images[blockIdx.y];
+    HuffJob J;
+    J.stream = streams + im.stream_off;
+    J.staged.words = S.words;
+    J.staged.base_word = 0;
+    J.stream_words = (uint32_t)((im.scan_len + 32) >> 2);               // the host reserves scan_len + 32 zeroed bytes
+    J.total_bits = stream_bits[blockIdx.y];
+    J.nsub = (J.total_bits + SUB_BITS - 1) / SUB_BITS;
+    J.bpm = im.bpm;
+    J.max_blocks = im.blocks;
+    J.coef = nullptr;
+    J.dc = nullptr;
+    const uint32_t windows = window_count(J.nsub), parts = part_count(J.nsub, gridDim.x);
+    if (blockIdx.x >= parts || windows == 0) return;
+    const uint32_t w_first = part_first(blockIdx.x, parts, windows), w_end = part_first(blockIdx.x + 1, parts, windows);
+    SubInfo *sub_info = sub_info_all + im.sub_off;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&tabsets[im.tabset]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
+        for (int i = t; i < (int)(sizeof(DecTabSet) / 4); i += HUFF_NT) dst[i] = src[i];
+    }
+    if (t == 0) {
+        S.W.carry.p = w_first * (uint32_t)HUFF_NT * SUB_BITS;          // true for part 0; a blind guess otherwise
+        S.W.carry.c = 0;
+        S.W.carry.z = 0;
+    }
+    __syncthreads();
+    for (uint32_t w = w_first; w < w_end; w++) {
+        const uint32_t w0 = w * (uint32_t)HUFF_NT;
+        J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+        stage_window(t, HUFF_NT, S.words, J.stream, J.staged.base_word, J.stream_words);
+        __syncthreads();
+        huff_phase_first(t, S.W, J, S.T, w0);
+        __syncthreads();
+        // Round 1: almost every thread still walks. From round 2 on only the few subsequences that have not met a recorded
+        // state keep going: their indices are compacted into a list so that they share a few warps instead of keeping
+        // one lane busy in many.
+        huff_phase_round(t, 1, S.W, J, S.T, w0);
+        __syncthreads();
+        for (int r = 2; r < HUFF_NT; r++) {
+            if (t == 0) S.n_live = 0;
+            __syncthreads();
+            if (!S.W.done[t]) S.live[atomicAdd(&S.n_live, 1u)] = (uint16_t)t;
+            __syncthreads();
+            const uint32_t n_live = S.n_live;
+            if (n_live == 0) break;
+            if ((uint32_t)t < n_live) huff_phase_round((int)S.live[t], r, S.W, J, S.T, w0);
+            __syncthreads();
+        }
+        if (w0 + (uint32_t)t < J.nsub) sub_info[w0 + t] = S.W.info[t];
+        if (t == 0) {
+            const uint32_t last = J.nsub - w0 < (uint32_t)HUFF_NT ? J.nsub - w0 - 1 : HUFF_NT - 1;
+            S.W.carry = S.W.info[last].s;
+        }
+        __syncthreads();
+    }
+}
+
+// Pass 2: part boundaries and block offsets. One CTA per file. Lane 0 of warp q re-records the first subsequences of part q
+// from the true state (all boundaries at once); thread 0 then checks that every walker did start from a state nobody changed
+// afterwards (it redoes the walk otherwise: that needs a whole part of subsequences that never fall into step); an exclusive
+// scan of the block counts gives every subsequence its first block.
+__global__ void __launch_bounds__(1024) huffman_fixup_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+                                                             const uint32_t *stream_bits, uint32_t max_parts, SubInfo *sub_info_all,
+                                                             uint32_t *sub_block0_all, int32_t *status)
+{
+    __shared__ uint32_t warp_sums[33];
+    __shared__ SubState started_from[32];
+    const DecImage im = images[blockIdx.x];
+    const uint8_t *stream = streams + im.stream_off;
+    const uint32_t total_bits = stream_bits[blockIdx.x], nsub = (total_bits + SUB_BITS - 1) / SUB_BITS;
+    const uint32_t windows = window_count(nsub), parts = part_count(nsub, max_parts);
+    SubInfo *sub_info = sub_info_all + im.sub_off;
+    uint32_t *sub_block0 = sub_block0_all + im.sub_off;
+    const DecTabSet &T = tabsets[im.tabset];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0 && warp >= 1 && warp < parts) {
+        const uint32_t j0 = part_first(warp, parts, windows) * (uint32_t)HUFF_NT;
+        uint32_t j_end = part_first(warp + 1, parts, windows) * (uint32_t)HUFF_NT;
+        j_end = j_end < nsub ? j_end : nsub;
+        started_from[warp] = sub_info[j0 - 1].s;
+        fixup_walk(stream, total_bits, T, im.bpm, sub_info, j0, j_end);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (uint32_t q = 1; q < parts; q++) {                            // in order: each check sees the final state before it
+            const uint32_t j0 = part_first(q, parts, windows) * (uint32_t)HUFF_NT;
+            uint32_t j_end = part_first(q + 1, parts, windows) * (uint32_t)HUFF_NT;
+            j_end = j_end < nsub ? j_end : nsub;
+            if (!same_state(started_from[q], sub_info[j0 - 1].s)) fixup_walk(stream, total_bits, T, im.bpm, sub_info, j0, j_end);
+        }
+    __syncthreads();
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < nsub; base += 1024) {
+        const uint32_t j = base + threadIdx.x;
+        uint32_t sum;
+        const uint32_t ex = dec_cta_scan(j < nsub ? sub_info[j].n : 0u, warp_sums, &sum);
+        if (j < nsub) sub_block0[j] = running + ex;
+        running += sum;
+    }
+    // a well-formed stream holds exactly `blocks` blocks (trailing pad bits may decode into at most a few phantom ones)
+    if (threadIdx.x == 0) status[blockIdx.x] = running >= (uint32_t)im.blocks ? 0 : -1;
+}
+
+// Pass 3: coefficients. grid = (max windows, files): every window of every file is a CTA of its own.
+__global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_write_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+                                                                const uint32_t *stream_bits, const SubInfo *sub_info_all,
+                                                                const uint32_t *sub_block0_all, int16_t *coef, int16_t *dc)
+{
+    extern __shared__ __align__(16) uint8_t huff_smem_raw[];
+    HuffSmem &S = *reinterpret_cast<HuffSmem *>(huff_smem_raw);
+    const int t = (int)threadIdx.x;
+    const DecImage im = images[blockIdx.y];
+    HuffJob J;
+    J.stream = streams + im.stream_off;
+    J.staged.words = S.words;
+    J.stream_words = (uint32_t)((im.scan_len + 32) >> 2);
+    J.total_bits = stream_bits[blockIdx.y];
+    J.nsub = (J.total_bits + SUB_BITS - 1) / SUB_BITS;
+    J.bpm = im.bpm;
+    J.max_blocks = im.blocks;
+    J.coef = coef + im.coef_off * 64;
+    J.dc = dc + im.coef_off;
+    const uint32_t w0 = blockIdx.x * (uint32_t)HUFF_NT;
+    if (w0 >= J.nsub) return;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&tabsets[im.tabset]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
+        for (int i = t; i < (int)(sizeof(DecTabSet) / 4); i += HUFF_NT) dst[i] = src[i];
+    }
+    J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+    stage_window(t, HUFF_NT, S.words, J.stream, J.staged.base_word, J.stream_words);
+    __syncthreads();
+    huff_write_sub(t, J, S.T, w0, sub_info_all + im.sub_off, sub_block0_all + im.sub_off);
 }
 
 // DC differences -> values. One CTA per file; thread t owns MCU chunk_base + t, three CTA scans per chunk of 1024 MCUs.

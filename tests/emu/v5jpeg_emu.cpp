@@ -127,6 +127,11 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     J.coef = coef.data();
     std::vector<int16_t> dcv((size_t)im.blocks, 0);
     J.dc = dcv.data();
+#ifndef V5J_EMU_PARTS
+#define V5J_EMU_PARTS 0
+#endif
+#if V5J_EMU_PARTS == 0
+    // ---- huffman_kernel: one CTA per file, windows in order, coefficients written window by window
     HuffWindow *W = new HuffWindow();
     memset(W, 0xA5, sizeof(*W));
     W->carry.p = 0; W->carry.c = 0; W->carry.z = 0;
@@ -155,6 +160,71 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
         W->base_blocks = run;
     }
     const bool ok = W->base_blocks >= (uint32_t)im.blocks;
+#else
+    // ---- huffman_sync_kernel / huffman_fixup_kernel / huffman_write_kernel
+    HuffWindow *W = new HuffWindow();
+    int max_rounds = 0;
+    // pass 1 (huffman_sync_kernel): the file's windows shared out among `parts` CTAs; part 0 starts true, the others blind
+    std::vector<SubInfo> sub_info(J.nsub + 1);
+    std::vector<uint32_t> sub_block0(J.nsub + 1, 0xA5A5A5A5u);
+    const uint32_t windows = window_count(J.nsub), parts = part_count(J.nsub, V5J_EMU_PARTS);
+    for (uint32_t q = parts; q-- > 0;) {                                    // any order: the parts are independent CTAs
+        memset(W, 0xA5, sizeof(*W));
+        const uint32_t w_first = part_first(q, parts, windows), w_end = part_first(q + 1, parts, windows);
+        W->carry.p = w_first * (uint32_t)HUFF_NT * SUB_BITS; W->carry.c = 0; W->carry.z = 0;
+        for (uint32_t w = w_first; w < w_end; w++) {
+            const uint32_t w0 = w * (uint32_t)HUFF_NT;
+            J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+            for (int t = 0; t < HUFF_NT; t++) stage_window(t, HUFF_NT, staged.data(), J.stream, J.staged.base_word, J.stream_words);
+            for (int t = 0; t < HUFF_NT; t++) huff_phase_first(t, *W, J, *T, w0);
+            for (int r = 1; r < HUFF_NT; r++) {
+                for (int t = 0; t < HUFF_NT; t++) huff_phase_round(t, r, *W, J, *T, w0);
+                bool all = true;
+                for (int t = 0; t < HUFF_NT; t++) all = all && W->done[t];
+                if (r > max_rounds) max_rounds = r;
+                if (all) break;
+            }
+            for (int t = 0; t < HUFF_NT; t++)
+                if (w0 + (uint32_t)t < J.nsub) sub_info[w0 + t] = W->info[t];
+            const uint32_t last = J.nsub - w0 < (uint32_t)HUFF_NT ? J.nsub - w0 - 1 : HUFF_NT - 1;
+            W->carry = W->info[last].s;
+        }
+    }
+    // pass 2 (huffman_fixup_kernel): all boundary walks from the recorded states, then the in-order check, then the scan
+    std::vector<SubState> started_from(parts + 1);
+    auto bounds = [&](uint32_t q, uint32_t &j0, uint32_t &j_end) {
+        j0 = part_first(q, parts, windows) * (uint32_t)HUFF_NT;
+        j_end = part_first(q + 1, parts, windows) * (uint32_t)HUFF_NT;
+        j_end = j_end < J.nsub ? j_end : J.nsub;
+    };
+    for (uint32_t q = 1; q < parts; q++) started_from[q] = sub_info[part_first(q, parts, windows) * (uint32_t)HUFF_NT - 1].s;
+    for (uint32_t q = parts; q-- > 1;) {                                    // "concurrent": each from the state it saw at the start
+        uint32_t j0, j_end;
+        bounds(q, j0, j_end);
+        SubInfo saved = sub_info[j0 - 1];
+        sub_info[j0 - 1].s = started_from[q];
+        fixup_walk(J.stream, J.total_bits, *T, J.bpm, sub_info.data(), j0, j_end);
+        sub_info[j0 - 1] = saved;
+    }
+    for (uint32_t q = 1; q < parts; q++) {
+        uint32_t j0, j_end;
+        bounds(q, j0, j_end);
+        if (!same_state(started_from[q], sub_info[j0 - 1].s)) fixup_walk(J.stream, J.total_bits, *T, J.bpm, sub_info.data(), j0, j_end);
+    }
+    uint32_t total_blocks = 0;
+    for (uint32_t j = 0; j < J.nsub; j++) {
+        sub_block0[j] = total_blocks;
+        total_blocks += sub_info[j].n;
+    }
+    // pass 3 (huffman_write_kernel): one CTA per window
+    for (uint32_t w = windows; w-- > 0;) {
+        const uint32_t w0 = w * (uint32_t)HUFF_NT;
+        J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
+        for (int t = 0; t < HUFF_NT; t++) stage_window(t, HUFF_NT, staged.data(), J.stream, J.staged.base_word, J.stream_words);
+        for (int t = HUFF_NT - 1; t >= 0; t--) huff_write_sub(t, J, *T, w0, sub_info.data(), sub_block0.data());
+    }
+    const bool ok = total_blocks >= (uint32_t)im.blocks;
+#endif
     if (rounds_out) *rounds_out = max_rounds;
     int py = 0, pcb = 0, pcr = 0;
     for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&dcv[(size_t)mcu * im.bpm], im.bpm, py, pcb, pcr);

@@ -39,11 +39,14 @@ def _build(tag, defs):
     return lib
 
 
-@pytest.fixture(scope="module", params=["full", "tiny"])
+@pytest.fixture(scope="module", params=["full", "tiny", "full_parts", "tiny_parts"])
 def emu(request):
-    """'full': the shipped window (1024 subsequences of 1024 bits). 'tiny': 8 subsequences of 64 bits per window, so that
-    even small files cross many windows and need many synchronisation rounds."""
-    defs = [] if request.param == "full" else ["-DV5J_HUFF_NT=8", "-DV5J_SUB_BITS=64"]
+    """'full': the shipped window (1024 subsequences of 1024 bits), the one-launch kernel's flow. 'tiny': 8 subsequences of
+    64 bits per window, so that even small files cross many windows and need many synchronisation rounds. 'full_parts' /
+    'tiny_parts': the three-launch flow with every file's windows shared out among up to 3 / 5 independent parts (blind
+    starts, boundary fix-up walks)."""
+    defs = {"full": [], "tiny": ["-DV5J_HUFF_NT=8", "-DV5J_SUB_BITS=64"], "full_parts": ["-DV5J_EMU_PARTS=3"],
+            "tiny_parts": ["-DV5J_HUFF_NT=8", "-DV5J_SUB_BITS=64", "-DV5J_EMU_PARTS=5"]}[request.param]
     return _build(request.param, defs)
 
 

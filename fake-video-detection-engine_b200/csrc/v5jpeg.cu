@@ -520,7 +520,8 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         v5j::SubInfo *d_sub_info = static_cast<v5j::SubInfo *>(s->d_sub_info);
         uint32_t *d_sub_block0 = static_cast<uint32_t *>(s->d_sub_block0);
         const char *force = getenv("V5ELA_HUFF_PATH");                    // tests: "one" / "three" force a path
-        const bool one_launch = force ? force[0] == 'o' : h->sm_count / cn < 2;   // no room for two parts per file: nothing to gain
+        // nothing to gain from splitting when there is no room for two parts per file, or no file has more than one window
+        const bool one_launch = force ? force[0] == 'o' : (h->sm_count / cn < 2 || P.max_windows < 2);
         if (one_launch) {
             v5j::huffman_kernel<<<cn, v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(d_images, d_tabs, d_str, d_bits, static_cast<int16_t *>(s->d_dcoef),
                                                                             static_cast<int16_t *>(s->d_dc), d_st);

@@ -482,10 +482,6 @@ V5_HOSTDEV void pixels8_rgb(const DecImage &im, const uint8_t *planes, int x0, i
 __constant__ uint8_t kZigzagToNaturalDev[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-__constant__ uint8_t kNaturalToZigzagDev[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
-                                                41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
-                                                46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
-
 __device__ __forceinline__ uint32_t dec_cta_scan(uint32_t v, uint32_t *warp_sums, uint32_t *sum)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -302,8 +302,7 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
         if (!make_dec_table(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].n, true, F.dc[c])) return JPEG_CORRUPT;
         if (!make_dec_table(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].n, false, F.ac[c])) return JPEG_CORRUPT;
     }
-    if (headers_only) return JPEG_OK;
-    if (F.ncomp == 1) {
+    if (!headers_only && F.ncomp == 1) {
         memcpy(F.qt[1], F.qt[0], sizeof(F.qt[0]));
         F.dc[1] = F.dc[0];
         F.ac[1] = F.ac[0];
@@ -324,6 +323,13 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
         }
     }
     F.scan_len = e - F.scan_off;
+    // Every block costs at least two bits (a one-bit DC code and a one-bit end-of-block code): a header that promises more
+    // blocks than the data can hold is damaged or truncated, and must not size any buffer.
+    {
+        const uint64_t m = F.ncomp == 3 ? 16 : 8;
+        const uint64_t blocks = ((uint64_t)(F.w + m - 1) / m) * ((uint64_t)(F.h + m - 1) / m) * (F.ncomp == 3 ? 6 : 1);
+        if (blocks * 2 > (uint64_t)F.scan_len * 8) return JPEG_CORRUPT;
+    }
     return JPEG_OK;
 }
 

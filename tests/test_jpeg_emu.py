@@ -217,3 +217,17 @@ def test_parser_refuses_what_the_kernels_do_not_implement(emu):
     for bad in (b"", b"\xff\xd8", data[:20], b"\x89PNG\r\n\x1a\n" + bytes(32), data[:i + 4]):
         with pytest.raises(ValueError):
             emu_decode(emu, bad)
+
+
+def test_header_that_promises_more_than_the_data_holds_is_refused(emu):
+    """A damaged SOF (65535 x 65535) over a few kilobytes of data must be refused before anything is sized by it."""
+    rgb = golden_frame({"spec": ["gen", 5, 1], "h": 40, "w": 48})
+    buf = io.BytesIO()
+    Image.fromarray(rgb).save(buf, "JPEG", quality=85)
+    data = bytearray(buf.getvalue())
+    i = data.index(b"\xff\xc0")
+    data[i + 5:i + 9] = b"\xff\xff\xff\xff"
+    with pytest.raises(ValueError):
+        emu_decode(emu, bytes(data))
+    with pytest.raises(ValueError):
+        emu_decode(emu, buf.getvalue()[:len(buf.getvalue()) // 8 + 700])      # truncated early: too few bits for the blocks

@@ -44,6 +44,8 @@ def lib():
         L.v5jo_info.restype = ctypes.c_int
         L.v5jo_info.argtypes = [u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                 ctypes.POINTER(ctypes.c_int)]
+        L.v5jo_layout.restype = ctypes.c_int
+        L.v5jo_layout.argtypes = [u8p, ctypes.c_size_t] + [ctypes.POINTER(ctypes.c_int)] * 3
         L.v5jo_decode.restype = ctypes.c_int
         L.v5jo_decode.argtypes = [u8p, ctypes.c_size_t, u8p, u8p, i16p]
         assert L.v5o_record_bytes() == RECORD_DTYPE.itemsize
@@ -135,13 +137,25 @@ def jpeg_info(data: bytes):
     return h.value, w.value, c.value
 
 
+def jpeg_layout(data: bytes):
+    """-> (hs, vs, restart_interval): luma blocks per MCU across / down, MCUs per restart interval (0 = none)."""
+    buf = np.frombuffer(data, np.uint8)
+    hs, vs, ri = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib().v5jo_layout(_u8(buf), len(data), ctypes.byref(hs), ctypes.byref(vs), ctypes.byref(ri))
+    if rc != 0:
+        raise ValueError(f"v5jo_layout: {rc}")
+    return hs.value, vs.value, ri.value
+
+
 def jpeg_decode(data: bytes, want_coef: bool = False):
     """-> dict(rgb (H,W,3), gray (H,W)[, coef]) decoded like libjpeg's defaults (ISLOW, fancy upsampling)."""
     h, w, c = jpeg_info(data)
     buf = np.frombuffer(data, np.uint8)
     rgb = np.empty((h, w, 3), np.uint8)
     gray = np.empty((h, w), np.uint8)
-    coef = np.zeros((jpeg_blocks(h, w, c), 64), np.int16) if want_coef else None
+    hs, vs, _ = jpeg_layout(data)
+    mcus = ((h + 8 * vs - 1) // (8 * vs)) * ((w + 8 * hs - 1) // (8 * hs))
+    coef = np.zeros((mcus * (hs * vs + 2 if c == 3 else 1), 64), np.int16) if want_coef else None
     rc = lib().v5jo_decode(_u8(buf), len(data), _u8(rgb), _u8(gray),
                            coef.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)) if want_coef else None)
     if rc != 0:

@@ -490,7 +490,9 @@ static int parse_headers(const uint8_t *d, size_t len, jhead_t *H)
         i += L;
     }
     if (!H->scan_off || H->h <= 0 || H->w <= 0 || H->progressive) return -2;
-    if (H->ncomp == 3 && !(H->hs[0] == 2 && H->vs[0] == 2 && H->hs[1] == 1 && H->vs[1] == 1 && H->hs[2] == 1 && H->vs[2] == 1)) return -2;
+    /* chroma layouts Pillow / OpenCV can write: 4:2:0 (2x2), 4:2:2 (2x1), 4:4:4 (1x1), chroma components always 1x1 */
+    if (H->ncomp == 3 && !(H->hs[1] == 1 && H->vs[1] == 1 && H->hs[2] == 1 && H->vs[2] == 1 &&
+                           ((H->hs[0] == 2 && H->vs[0] == 2) || (H->hs[0] == 2 && H->vs[0] == 1) || (H->hs[0] == 1 && H->vs[0] == 1)))) return -2;
     for (int c = 0; c < H->ncomp; c++)
         if (!H->qt_present[H->tq[c]] || !H->dc[H->td[c]].present || !H->ac[H->ta[c]].present) return -1;
     return 0;
@@ -503,6 +505,18 @@ int v5jo_info(const uint8_t *data, size_t len, int *h, int *w, int *ncomp)
     const int rc = parse_headers(data, len, &H);
     if (rc) return rc;
     *h = H.h; *w = H.w; *ncomp = H.ncomp;
+    return 0;
+}
+
+/* Luma sampling factors (2x2 = 4:2:0, 2x1 = 4:2:2, 1x1 = 4:4:4 or one component) and the restart interval in MCUs. */
+int v5jo_layout(const uint8_t *data, size_t len, int *hs, int *vs, int *restart_interval)
+{
+    jhead_t H;
+    const int rc = parse_headers(data, len, &H);
+    if (rc) return rc;
+    *hs = H.ncomp == 3 ? H.hs[0] : 1;
+    *vs = H.ncomp == 3 ? H.vs[0] : 1;
+    *restart_interval = H.restart_interval;
     return 0;
 }
 
@@ -533,9 +547,10 @@ int v5jo_decode(const uint8_t *data, size_t len, uint8_t *rgb_out, uint8_t *y_ou
     jhead_t H;
     int rc = parse_headers(data, len, &H);
     if (rc) return rc;
-    const int h = H.h, w = H.w, mcu = H.ncomp == 3 ? 16 : 8;
-    const int mcux = (w + mcu - 1) / mcu, mcuy = (h + mcu - 1) / mcu;
-    const int yw = mcux * mcu, yh = mcuy * mcu, cw = yw / 2, ch = yh / 2;
+    const int h = H.h, w = H.w;
+    const int hs = H.ncomp == 3 ? H.hs[0] : 1, vs = H.ncomp == 3 ? H.vs[0] : 1;       /* luma blocks per MCU: hs x vs */
+    const int mcux = (w + 8 * hs - 1) / (8 * hs), mcuy = (h + 8 * vs - 1) / (8 * vs);
+    const int yw = mcux * 8 * hs, yh = mcuy * 8 * vs, cw = mcux * 8, ch = mcuy * 8;
     uint8_t *yp = malloc((size_t)yw * yh), *cbp = NULL, *crp = NULL;
     if (H.ncomp == 3) { cbp = malloc((size_t)cw * ch); crp = malloc((size_t)cw * ch); }
     if (!yp || (H.ncomp == 3 && (!cbp || !crp))) { free(yp); free(cbp); free(crp); return -1; }
@@ -552,9 +567,9 @@ int v5jo_decode(const uint8_t *data, size_t len, uint8_t *rgb_out, uint8_t *y_ou
                 pred[0] = pred[1] = pred[2] = 0;
                 until_restart = H.restart_interval;
             }
-            const int nb = H.ncomp == 3 ? 6 : 1;
+            const int ny = hs * vs, nb = H.ncomp == 3 ? ny + 2 : 1;
             for (int i = 0; i < nb; i++) {
-                const int comp = H.ncomp == 1 ? 0 : (i < 4 ? 0 : i - 3);
+                const int comp = H.ncomp == 1 ? 0 : (i < ny ? 0 : i - ny + 1);
                 int16_t coef[64];
                 memset(coef, 0, sizeof(coef));
                 int s = decode_symbol(&B, &H.dc[H.td[comp]]);
@@ -575,7 +590,7 @@ int v5jo_decode(const uint8_t *data, size_t len, uint8_t *rgb_out, uint8_t *y_ou
                 if (coef_out)
                     for (int k = 0; k < 64; k++) coef_out[(nblk + (size_t)i) * 64 + k] = coef[k_zigzag[k]];
                 if (comp == 0) {
-                    const int by = H.ncomp == 3 ? 2 * my + (i >> 1) : my, bx = H.ncomp == 3 ? 2 * mx + (i & 1) : mx;
+                    const int by = vs * my + i / hs, bx = hs * mx + i % hs;
                     block_inverse(coef, H.qt[H.tq[0]], yp + (size_t)(8 * by) * yw + 8 * bx, yw);
                 } else {
                     block_inverse(coef, H.qt[H.tq[comp]], (comp == 1 ? cbp : crp) + (size_t)(8 * my) * cw + 8 * mx, cw);
@@ -594,18 +609,24 @@ int v5jo_decode(const uint8_t *data, size_t len, uint8_t *rgb_out, uint8_t *y_ou
                 o[0] = o[1] = o[2] = v;
             }
     } else if (rgb_out) {
-        const int hc = (h + 1) / 2, wc = (w + 1) / 2;
-        for (int y = 0; y < h; y++) {                    /* A.7 fancy upsample + A.8 colour conversion */
-            int r = y >> 1, nbr = (y & 1) ? r + 1 : r - 1;
-            if (nbr < 0) nbr = 0;
-            if (nbr > hc - 1) nbr = hc - 1;
+        /* chroma sample for pixel (x, y): libjpeg's upsamplers with do_fancy_upsampling (jdsample.c)
+         *   2x2: h2v2 "triangle" filter      2x1: h2v1 fancy, 3/4 : 1/4 along the row      1x1: none
+         * both fancy forms fall back to plain replication when the downsampled width is <= 2 */
+        const int hc = (h + vs - 1) / vs, wc = (w + hs - 1) / hs;
+        for (int y = 0; y < h; y++) {
+            int r = y / vs, nbr = r;
+            if (vs == 2) {
+                nbr = (y & 1) ? r + 1 : r - 1;
+                if (nbr < 0) nbr = 0;
+                if (nbr > hc - 1) nbr = hc - 1;
+            }
             for (int x = 0; x < w; x++) {
-                const int cx = x >> 1;
+                const int cx = x / hs;
                 int cb, cr;
-                if (wc <= 2) {
+                if (hs == 1 || wc <= 2) {
                     cb = cbp[(size_t)r * cw + cx];
                     cr = crp[(size_t)r * cw + cx];
-                } else {
+                } else if (vs == 2) {
                     int nx = (x & 1) ? cx + 1 : cx - 1;
                     if (nx < 0) nx = 0;
                     if (nx > wc - 1) nx = wc - 1;
@@ -616,6 +637,16 @@ int v5jo_decode(const uint8_t *data, size_t len, uint8_t *rgb_out, uint8_t *y_ou
                     s0 = 3 * crp[(size_t)r * cw + cx] + crp[(size_t)nbr * cw + cx];
                     s1 = 3 * crp[(size_t)r * cw + nx] + crp[(size_t)nbr * cw + nx];
                     cr = (3 * s0 + s1 + bias) >> 4;
+                } else {                                 /* h2v1 fancy: the first and last output samples copy their input */
+                    const int nx = (x & 1) ? cx + 1 : cx - 1;
+                    if (nx < 0 || nx > wc - 1) {
+                        cb = cbp[(size_t)r * cw + cx];
+                        cr = crp[(size_t)r * cw + cx];
+                    } else {
+                        const int bias = (x & 1) ? 2 : 1;
+                        cb = (3 * cbp[(size_t)r * cw + cx] + cbp[(size_t)r * cw + nx] + bias) >> 2;
+                        cr = (3 * crp[(size_t)r * cw + cx] + crp[(size_t)r * cw + nx] + bias) >> 2;
+                    }
                 }
                 const int32_t yy = yp[(size_t)y * yw + x], cbd = cb - 128, crd = cr - 128;
                 uint8_t *o = rgb_out + ((size_t)y * w + x) * 3;

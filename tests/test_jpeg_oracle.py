@@ -95,9 +95,31 @@ def test_decoder_takes_custom_tables_and_restart_markers():
     assert np.array_equal(c_oracle.jpeg_decode(enc.tobytes())["rgb"][..., ::-1], ref[..., ::-1])
 
 
+def test_decoder_takes_the_other_chroma_layouts_and_restart_intervals():
+    """4:4:4 and 4:2:2 files (Pillow subsampling=0 / 1; libjpeg's h2v1 fancy upsampler, jdsample.c), with and without
+    restart intervals, decode to the pixels Pillow / OpenCV produce."""
+    rng = np.random.default_rng(11)
+    for it in range(45):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 110))
+        q = int(rng.choice([5, 50, 75, 90, 95, 100]))
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if it % 3 == 0:
+            rgb = cv2.GaussianBlur(rgb, (0, 0), 2.5)
+        for ss in (0, 1, 2):
+            kw = {"restart_marker_blocks": int(rng.integers(1, 7))} if it % 2 else {}
+            buf = io.BytesIO()
+            Image.fromarray(rgb).save(buf, "JPEG", quality=q, subsampling=ss, **kw)
+            data = buf.getvalue()
+            hs, vs, ri = c_oracle.jpeg_layout(data)
+            assert (hs, vs) == ((1, 1), (2, 1), (2, 2))[ss] and (ri > 0) == bool(kw)
+            out = c_oracle.jpeg_decode(data, want_coef=True)
+            assert np.array_equal(out["rgb"], np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))), (h, w, q, ss)
+            assert np.array_equal(out["gray"], cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)), (h, w, q, ss)
+
+
 def test_unsupported_flavours_are_reported():
     rgb = golden_frame({"spec": ["gen", 1, 2], "h": 40, "w": 40})
-    for kw in ({"subsampling": 0}, {"progressive": True}):
+    for kw in ({"progressive": True},):
         buf = io.BytesIO()
         Image.fromarray(rgb).save(buf, "JPEG", quality=80, **kw)
         with pytest.raises(ValueError):

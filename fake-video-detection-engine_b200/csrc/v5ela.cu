@@ -23,6 +23,7 @@ static_assert(sizeof(v5::Smem) <= (227 * 1024) / v5::MIN_CTAS - 1024, "MIN_CTAS 
 
 namespace v5 {
 
+template <bool FAST>
 __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_co
         __syncthreads();
         const int work = (int)S.next_work;
         if (work >= total_work) break;
-        process_work_item(S, p, work, acc_store);                // ends with a CTA barrier: next_work may be rewritten
+        process_work_item<FAST>(S, p, work, acc_store);          // ends with a CTA barrier: next_work may be rewritten
     }
 }
 
@@ -177,7 +178,9 @@ int v5ela_create(int device, v5ela_handle **out)
     h->sm_count = prop.multiProcessorCount;
     v5::quant_tables(h->quality, h->luma, h->chroma);
     DeviceGuard guard(device);
-    if (cudaFuncSetAttribute(v5::ela_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(v5::ela_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(v5::Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(v5::ela_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(v5::Smem)) != cudaSuccess) {
         delete h;
         return V5ELA_ERR_CUDA;
@@ -263,7 +266,8 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
     const int grid = total < max_ctas ? (int)total : max_ctas;
     const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
     if (prof) V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used], st));
-    v5::ela_fused_kernel<<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    if (v5::fast_path_ok(p)) v5::ela_fused_kernel<true><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    else v5::ela_fused_kernel<false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
     V5_CUDA(h, cudaGetLastError());
     if (prof) {
         V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used + 1], st));

@@ -131,6 +131,29 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 #endif
 
+// Byte-lane selector constants of the residual stage. As literals ptxas rematerialises each one with a UMOV in front of
+// (almost) every use — 3 % of the kernel's issue slots; as a table in constant memory four of them arrive with one
+// uniform 128-bit load (LDCU.128). Index = 4 * family + byte lane.
+enum { SEL_ONE = 0, SEL_THREE = 4, SEL_FOUR = 8, SEL_HALF = 12, SEL_LAP = 16 };   // SEL_HALF: 0x8000 (rounding of the colour conversion)
+#ifndef V5_CONST_SEL
+#define V5_CONST_SEL 1
+#endif
+#if defined(__CUDACC__) && V5_CONST_SEL
+static __constant__ uint32_t kSelTab[20] = {1u,       1u << 8,    1u << 16,    1u << 24,  3u,     3u << 8, 3u << 16, 3u << 24, 4u, 4u << 8,
+                                            4u << 16, 4u << 24,   0x8000u,     0u,        0u,      0u,
+                                            0x01fc01u, 0x01fc0100u, 0xfc010000u, 0x000001fcu};
+#endif
+#if defined(__CUDA_ARCH__) && V5_CONST_SEL
+V5_DEV uint32_t sel_const(int i) { return kSelTab[i]; }
+#else
+V5_HOSTDEV constexpr uint32_t sel_const(int i)
+{
+    return i < 12 ? (i < 4 ? 1u : (i < 8 ? 3u : 4u)) << (8 * (i & 3))
+                  : (i < 16 ? (i == 12 ? 0x8000u : 0u)
+                            : (i == 16 ? 0x01fc01u : (i == 17 ? 0x01fc0100u : (i == 18 ? 0xfc010000u : 0x000001fcu))));
+}
+#endif
+
 // Integer dot products on packed bytes (IDP on the FMA pipe): they replace byte extraction (PRMT on the ALU pipe).
 //   dp4a_us(a, b, c) = c + sum_i u8(a.byte[i]) * s8(b.byte[i])
 //   dp2a_lo/hi_su(a, b, c) = c + s16(a.lo) * u8(b.byte[0|2]) + s16(a.hi) * u8(b.byte[1|3]);  _uu: a halves unsigned
@@ -168,7 +191,7 @@ V5_DEV int dp2a_hi_uu(uint32_t a, uint32_t b, int c)
 // histogram update: bin = byte k of word; the bin's shared address comes out of one dp4a (base + 4 * byte)
 V5_DEV void hist_add(uint32_t *hist_c, uint32_t word, int k)
 {
-    const uint32_t addr = (uint32_t)dp4a_us(word, 4u << (8 * k), (int)(uint32_t)__cvta_generic_to_shared(hist_c));
+    const uint32_t addr = (uint32_t)dp4a_us(word, sel_const(SEL_FOUR + k), (int)(uint32_t)__cvta_generic_to_shared(hist_c));
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
 }
 #else
@@ -265,7 +288,11 @@ struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one
 //                  pixels from global memory (L2 hits: the band went through L2 moments ago), 24-line luma ring.
 constexpr int RGB_BUFS = MIN_CTAS >= 3 ? 1 : 2;
 constexpr int RING = RGB_BUFS == 2 ? 32 : 24;   // yorig ring lines: 16 of the current band + 2 carried
-constexpr int RINGD = 24;               // ydec ring lines (16 + 1 carried)
+#ifndef V5_RINGD
+#define V5_RINGD (RGB_BUFS == 2 ? 32 : 24)
+#endif
+constexpr int RINGD = V5_RINGD;         // ydec ring lines (16 + 1 carried); a power of two where shared memory allows: the
+                                        // ring index is computed per 8-pixel unit
 
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
@@ -314,6 +341,7 @@ V5_DEV int ring16(int r, int l)                                        // yorig 
 }
 V5_DEV int ringd(int r, int l)                                         // ydec line; l in [-1, 15]
 {
+    if (RINGD == 32) return (16 * (r & 1) + l) & 31;
     int i = 16 * (r % 3) + l;                                           // 16r mod 24 cycles 0,16,8
     i = i >= RINGD ? i - RINGD : i;
     i = i >= RINGD ? i - RINGD : i;
@@ -573,6 +601,10 @@ struct BlockTask {
     bool active;
 };
 
+// FAST (here and below): the width is a multiple of 16 and no residual map is wanted — every 8-pixel unit and every block
+// of a strip lies inside the image horizontally, so the per-unit edge predicates and the residual store compile away. The
+// host picks the instantiation (fast_path_ok); both are the same arithmetic.
+template <bool FAST>
 V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, int r, bool want_y)
 {
     BlockTask t;
@@ -586,7 +618,7 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     if (blk < nl) {
         const int br = blk >= 2 * tw ? 1 : 0, bc = blk - br * 2 * tw;
         // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
-        if (16 * r + 8 * br >= p.h || 16 * g.m0 + 8 * bc >= p.w) return t;
+        if (16 * r + 8 * br >= p.h || (!FAST && 16 * g.m0 + 8 * bc >= p.w)) return t;
         const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
         t.in = &S.yorig[row][col];
         t.out = &S.ydec[ringd(r, 8 * br)][col];
@@ -607,9 +639,10 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     return t;
 }
 
+template <bool FAST>
 V5_DEV BlockTask block_task_of(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y, int round)
 {
-    return block_task(round * (NT / 4) + (tid >> 5) * 8 + ((tid & 31) >> 2), S, p, g, r, want_y);
+    return block_task<FAST>(round * (NT / 4) + (tid >> 5) * 8 + ((tid & 31) >> 2), S, p, g, r, want_y);
 }
 
 V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
@@ -707,10 +740,10 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
         return;
     }
     int cs[6];                                                  // cs[j+1] = 3*c[r][j] + c[nb][j], j = -1..4
-    cs[0] = dp4a_us(c0, 3u << 24, dp4a_us(n0, 1u << 24, 0));
+    cs[0] = dp4a_us(c0, sel_const(SEL_THREE + 3), dp4a_us(n0, sel_const(SEL_ONE + 3), 0));
 #pragma unroll
-    for (int j = 0; j < 4; j++) cs[1 + j] = dp4a_us(c1, 3u << (8 * j), dp4a_us(n1, 1u << (8 * j), 0));
-    cs[5] = dp4a_us(c2, 3u, dp4a_us(n2, 1u, 0));
+    for (int j = 0; j < 4; j++) cs[1 + j] = dp4a_us(c1, sel_const(SEL_THREE + j), dp4a_us(n1, sel_const(SEL_ONE + j), 0));
+    cs[5] = dp4a_us(c2, sel_const(SEL_THREE), dp4a_us(n2, sel_const(SEL_ONE), 0));
     if (gcx0 == 0) cs[0] = cs[1];                               // left image edge: neighbour clamps to column 0
     if (gcx0 + 4 > wc1) {                                       // right image edge inside / just after this unit
 #pragma unroll
@@ -726,12 +759,13 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
 }
 
 // 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
+template <bool FAST>
 V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
 {
     const int y = 16 * r + l;                                   // global pixel row
     const int gx0 = 16 * g.m0 + 8 * ox;                         // global pixel column of this unit
     const int col = 16 + 8 * ox;                                // band smem column
-    const int nvalid = p.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8)
+    const int nvalid = p.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8; FAST: >= 8)
 
     // ---- chroma upsample (A.7)
     const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = ((p.w + 1) >> 1) - 1;
@@ -783,7 +817,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     int rec[24];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int ykr = (int)prmt(ydw[k >> 2], 0x00008000u, 0x4054u + ((uint32_t)(k & 3) << 8));   // bytes: 00 80 Y 00
+        const int ykr = (int)prmt(ydw[k >> 2], sel_const(SEL_HALF), 0x4054u + ((uint32_t)(k & 3) << 8));   // bytes: 00 80 Y 00
         const int cbv = cb[k], crv = cr[k];
         rec[3 * k] = (91881 * crv + ykr) >> 16;                // clamped to 0..255 by the saturating pack below
         rec[3 * k + 1] = (-22554 * cbv + (-46802 * crv + ykr)) >> 16;
@@ -792,7 +826,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
 #pragma unroll
     for (int i = 0; i < 6; i++)
         dw[i] = absdiff4(ow[i], pack4sat(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
-    if (g.resid) {
+    if (!FAST && g.resid) {
         uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
         if (nvalid >= 8 && p.resid_vec_ok) {
 #pragma unroll
@@ -805,7 +839,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     }
     // Histogram: every unit adds all 24 bytes unconditionally; a unit cut by the right image edge first zeroes the bytes
     // of its outside pixels and takes them out of bin 0 again (rare, keeps the common path free of per-byte predicates).
-    if (nvalid < 8) {
+    if (!FAST && nvalid < 8) {
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const int vb = 3 * nvalid - 4 * i;                  // valid bytes in word i
@@ -840,7 +874,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
         const U2 cw = *reinterpret_cast<const U2 *>(yc);
         const U2 uw = *reinterpret_cast<const U2 *>(yu);
         const U2 lw = *reinterpret_cast<const U2 *>(yd2);
-        const int edge = nvalid < 8 ? nvalid - 1 : -1;
+        const int edge = !FAST && nvalid < 8 ? nvalid - 1 : -1;
         const int nacc = edge >= 0 ? edge : 8;
         const uint32_t hl = gx0 == 0 ? yc[wide] : yc[-1], hr = nvalid == 8 ? yc[6] : yc[8];
         const uint32_t x[3] = {prmt(hl, cw.x, 0x6540u), prmt(cw.x, cw.y, 0x6543u), prmt(cw.y, hr, 0x7743u)};
@@ -848,22 +882,22 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int w0 = k >> 2, s0 = k & 3;                  // window e[k..k+2] starts at byte s0 of x[w0]
-            int lap = dp4a_us(ud[w0][0], 1u << (8 * s0), dp4a_us(ud[w0][1], 1u << (8 * s0), 0));      // up + down
+            int lap = dp4a_us(ud[w0][0], sel_const(SEL_ONE + s0), dp4a_us(ud[w0][1], sel_const(SEL_ONE + s0), 0));   // up + down
             if (s0 <= 1) {
-                lap = dp4a_us(x[w0], 0x01fc01u << (8 * s0), lap);
+                lap = dp4a_us(x[w0], sel_const(SEL_LAP + s0), lap);                                   // 01 fc 01 << 8 s0
             } else if (s0 == 2) {
-                lap = dp4a_us(x[w0 + 1], 0x00000001u, dp4a_us(x[w0], 0xfc010000u, lap));
+                lap = dp4a_us(x[w0 + 1], sel_const(SEL_ONE), dp4a_us(x[w0], sel_const(SEL_LAP + 2), lap));
             } else {
-                lap = dp4a_us(x[w0 + 1], 0x000001fcu, dp4a_us(x[w0], 0x01000000u, lap));
+                lap = dp4a_us(x[w0 + 1], sel_const(SEL_LAP + 3), dp4a_us(x[w0], sel_const(SEL_ONE + 3), lap));
             }
             lap = lap < 0 ? -lap : lap;
-            if (k < nacc) {
+            if (FAST || k < nacc) {
                 sabs += (uint32_t)lap;
                 ssq += (uint32_t)(lap * lap);
                 mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
             }
         }
-        if (edge >= 0) {
+        if (!FAST && edge >= 0) {
             const int ctr = yc[edge];
             const int side = wide ? (edge == 0 && gx0 == 0 ? ctr : (int)yc[edge - 1]) : ctr;
             int lap = 2 * side + (int)yu[edge] + (int)yd2[edge] - 4 * ctr;
@@ -879,6 +913,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
 }
 
 // Iteration r finishes pixel rows 16r-1 .. 16r+14 (clipped to the segment and the image).
+template <bool FAST>
 V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r)
 {
     const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
@@ -887,8 +922,8 @@ V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, Thr
     for (int u = tid; u < 16 * n8; u += NT) {
         const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
-        if (y < ylo || y >= yhi || 16 * g.m0 + 8 * ox >= p.w) continue;
-        residual_unit(S, p, g, acc, r, l, ox);
+        if (y < ylo || y >= yhi || (!FAST && 16 * g.m0 + 8 * ox >= p.w)) continue;
+        residual_unit<FAST>(S, p, g, acc, r, l, ox);
     }
 }
 

@@ -13,7 +13,7 @@ namespace v5 {
 // V5_BLOCK_TASK / V5_GET_TASK: the block-stage task of a thread is computed once per round on the device and once per
 // sub-stage loop in the emulator.
 #ifdef __CUDA_ARCH__
-#define V5_BLOCK_TASK(t) const BlockTask t = block_task_of((int)threadIdx.x, S, p, g, r, want_y, round);
+#define V5_BLOCK_TASK(t) const BlockTask t = block_task_of<FAST>((int)threadIdx.x, S, p, g, r, want_y, round);
 #define V5_GET_TASK(t) (void)0
 #define V5_FOR_WARP(...)                     \
     {                                        \
@@ -33,7 +33,7 @@ namespace v5 {
     __syncthreads();
 #else
 #define V5_BLOCK_TASK(t)
-#define V5_GET_TASK(t) const BlockTask t = block_task_of(tid, S, p, g, r, want_y, round)
+#define V5_GET_TASK(t) const BlockTask t = block_task_of<FAST>(tid, S, p, g, r, want_y, round)
 #define V5_FOR_WARP(...)                     \
     for (int tid = 0; tid < NT; tid++) {     \
         ThreadAcc &acc = acc_store[tid];     \
@@ -99,6 +99,7 @@ inline void flush_global(int tid, Smem &S, v5ela_record *rec)
 }
 #endif
 
+template <bool FAST>
 V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *acc_store)
 {
     Geo g;
@@ -161,7 +162,7 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             }
             V5_FOR_THREADS((void)0)
         }
-        V5_FOR_THREADS(stage_residual(tid, S, p, g, acc, r))
+        V5_FOR_THREADS(stage_residual<FAST>(tid, S, p, g, acc, r))
     }
 
     V5_FOR_THREADS(flush_partials(tid, S, acc))

@@ -37,7 +37,8 @@ struct v5jpeg_state {
     cudaStream_t upload_stream = nullptr;
     int toggle = 0;
     void *d_streams = nullptr, *d_dcoef = nullptr, *d_planes = nullptr, *d_bits = nullptr, *d_status = nullptr, *d_dc = nullptr;
-    void *d_sub_info = nullptr, *d_sub_block0 = nullptr;
+    void *d_sub_info = nullptr, *d_sub_block0 = nullptr, *d_rst = nullptr;
+    size_t rst_cap = 0;
     size_t streams_cap = 0, dcoef_cap = 0, planes_cap = 0, bits_cap = 0, status_cap = 0, dc_cap = 0, sub_info_cap = 0, sub_block0_cap = 0;
     uint8_t *d_dec_rgb = nullptr, *d_dec_gray = nullptr;
     int32_t *d_dec_status = nullptr;
@@ -72,6 +73,7 @@ void v5jpeg_release(v5ela_handle *h)
     cudaFree(s->d_dc);
     cudaFree(s->d_sub_info);
     cudaFree(s->d_sub_block0);
+    cudaFree(s->d_rst);
     cudaFree(s->d_dec_rgb);
     cudaFree(s->d_dec_gray);
     cudaFree(s->d_dec_status);
@@ -306,6 +308,8 @@ struct DecPlan {                               // host-side description of one c
     std::vector<char> contiguous;              // file k follows file k-1 in host memory closely enough to share one upload
     size_t scan_bytes = 0, stream_bytes = 0, coef_blocks = 0, plane_bytes = 0, subs = 0;
     uint32_t max_windows = 1;
+    size_t rst_entries = 0;                    // interval starts of the files with restart markers
+    int max_intervals = 0;
     int max_blocks = 0;
     int64_t max_groups = 0;                    // 8-pixel groups of the largest image
 };
@@ -357,7 +361,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
             char which[64];
             snprintf(which, sizeof(which), " (file %d)", i);
             return prc == v5j::JPEG_UNSUPPORTED
-                       ? fail(h, V5ELA_ERR_UNSUPPORTED, "v5ela_jpeg_decode: not 8-bit baseline 4:2:0 / one-component JPEG without restarts%s", which)
+                       ? fail(h, V5ELA_ERR_UNSUPPORTED, "v5ela_jpeg_decode: not an 8-bit baseline one-component / 4:2:0 / 4:2:2 / 4:4:4 JPEG%s", which)
                        : fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: corrupt JPEG headers%s", which);
         }
         v5j::DecTabSet ts;
@@ -384,15 +388,9 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         const v5j::FileInfo &F = info[i];
         v5j::DecImage im;
         memset(&im, 0, sizeof(im));
-        im.h = F.h; im.w = F.w; im.ncomp = F.ncomp;
-        const int m = F.ncomp == 3 ? 16 : 8;
-        im.mcux = (F.w + m - 1) / m; im.mcuy = (F.h + m - 1) / m;
-        im.bpm = F.ncomp == 3 ? 6 : 1;
-        im.blocks = im.mcux * im.mcuy * im.bpm;
+        v5j::dec_geometry(im, F.h, F.w, F.ncomp, F.hs, F.vs);
         im.tabset = tab_of[i];
         im.qt = q_of[i];
-        im.yw = im.mcux * m; im.yh = im.mcuy * m;
-        im.cw = F.ncomp == 3 ? im.yw / 2 : 0; im.ch = F.ncomp == 3 ? im.yh / 2 : 0;
         const size_t planes = (size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch;
         const size_t need = F.scan_len * 2 + (size_t)im.blocks * 128 + planes + 256;
         DecPlan *P = &plans.back();
@@ -423,6 +421,13 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         P->subs += nsub_max;
         const uint32_t wmax = (uint32_t)((nsub_max + v5j::HUFF_NT - 1) / v5j::HUFF_NT);
         if (wmax > P->max_windows) P->max_windows = wmax;
+        if (F.restart > 0) {                           // restart intervals: one start position per interval
+            const int n_int = (im.mcux * im.mcuy + F.restart - 1) / F.restart;
+            im.restart = F.restart;
+            im.rst_off = (int32_t)P->rst_entries;
+            P->rst_entries += (size_t)n_int;
+            if (n_int > P->max_intervals) P->max_intervals = n_int;
+        }
         im.plane_off = (int64_t)P->plane_bytes;
         im.rgb_off = d_rgb ? (rgb_offsets ? rgb_offsets[i] : rgb_run) : -1;
         im.gray_off = d_gray ? (gray_offsets ? gray_offsets[i] : gray_run) : -1;
@@ -469,6 +474,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         if ((rc = ensure(h, &s->d_dc, &s->dc_cap, sizeof(int16_t) * P.coef_blocks))) return rc;
         if ((rc = ensure(h, &s->d_sub_info, &s->sub_info_cap, sizeof(v5j::SubInfo) * P.subs))) return rc;
         if ((rc = ensure(h, &s->d_sub_block0, &s->sub_block0_cap, sizeof(uint32_t) * P.subs))) return rc;
+        if ((rc = ensure(h, &s->d_rst, &s->rst_cap, sizeof(uint32_t) * (P.rst_entries + 1)))) return rc;
         uint8_t *stage_host = s->stage_host[b], *d_stage = s->d_stage[b];
         for (int k = 0; k < cn; k++) P.images[(size_t)k].scan_off += (int64_t)off_scan;
         if (!all_pinned)
@@ -502,13 +508,14 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         V5_CUDA(h, cudaMemsetAsync(s->d_streams, 0, P.stream_bytes, st));
         V5_CUDA(h, cudaMemsetAsync(s->d_dcoef, 0, P.coef_blocks * 128, st));
         V5_CUDA(h, cudaMemsetAsync(s->d_dc, 0, sizeof(int16_t) * P.coef_blocks, st));
+        if (P.rst_entries) V5_CUDA(h, cudaMemsetAsync(s->d_rst, 0, sizeof(uint32_t) * P.rst_entries, st));
 
         const v5j::DecImage *d_images = reinterpret_cast<const v5j::DecImage *>(d_stage + off_img);
         const v5j::DecTabSet *d_tabs = reinterpret_cast<const v5j::DecTabSet *>(d_stage + off_tab);
         const uint16_t *d_q = reinterpret_cast<const uint16_t *>(d_stage + off_q);
         uint32_t *d_bits = static_cast<uint32_t *>(s->d_bits);
         int32_t *d_st = static_cast<int32_t *>(s->d_status);
-        v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, d_stage, static_cast<uint8_t *>(s->d_streams), d_bits);
+        v5j::unstuff_kernel<<<cn, 1024, 0, st>>>(d_images, d_stage, static_cast<uint8_t *>(s->d_streams), d_bits, static_cast<uint32_t *>(s->d_rst));
         V5_CUDA(h, cudaGetLastError());
         // Huffman decoding in three launches: synchronisation (the windows of a file shared out among `parts` CTAs so that a
         // small batch still fills the GPU), boundary fix-up + block offsets, then one CTA per window writes coefficients.
@@ -534,6 +541,13 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
             v5j::huffman_write_kernel<<<dim3(P.max_windows, (unsigned)cn), v5j::HUFF_NT, sizeof(v5j::HuffSmem), st>>>(
                 d_images, d_tabs, d_str, d_bits, d_sub_info, d_sub_block0, static_cast<int16_t *>(s->d_dcoef), static_cast<int16_t *>(s->d_dc));
             V5_CUDA(h, cudaGetLastError());
+        }
+        if (P.max_intervals > 0) {                                         // files with restart intervals: one thread per interval
+            v5j::huffman_rst_kernel<<<dim3((unsigned)((P.max_intervals + 127) / 128), (unsigned)cn), 128, 0, st>>>(
+                d_images, d_tabs, d_str, d_bits, static_cast<const uint32_t *>(s->d_rst), static_cast<int16_t *>(s->d_dcoef),
+                static_cast<int16_t *>(s->d_dc), d_st);
+            V5_CUDA(h, cudaGetLastError());
+            h->launches += 1;
         }
         v5j::dc_kernel<<<cn, 1024, 0, st>>>(d_images, static_cast<int16_t *>(s->d_dc));
         V5_CUDA(h, cudaGetLastError());

@@ -196,14 +196,19 @@ enum { JPEG_OK = 0, JPEG_CORRUPT = -1, JPEG_UNSUPPORTED = -2 };
 
 struct FileInfo {
     int h = 0, w = 0, ncomp = 0;
+    int hs = 1, vs = 1;       // luma sampling factors = luma blocks per MCU across / down (chroma is always 1 x 1)
+    int restart = 0;          // restart interval in MCUs (DRI), 0 = none
     uint16_t qt[2][64];       // natural order: [0] the luma component's table, [1] the chroma components' (same for both)
     DecTable dc[2], ac[2];    // [0] luma, [1] chroma
     size_t scan_off = 0, scan_len = 0;   // entropy-coded segment inside the file (stuffed bytes included, EOI excluded)
 };
 
 // Parses the marker segments of one file. Supported: 8-bit baseline (SOF0/SOF1 Huffman), one component, or three
-// components sampled 2x2,1x1,1x1 with Cb and Cr sharing tables; a single scan; no restart interval. Everything the
-// reference's writers (cv2.imwrite, PIL save) produce is inside that set; anything else is JPEG_UNSUPPORTED.
+// components with the luma sampled 2x2 (4:2:0), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma, Cb and Cr sharing tables;
+// a single scan; with or without restart intervals. Everything the reference's writers (cv2.imwrite, PIL save) produce by
+// default is 4:2:0 without restarts; the other layouts and the restart markers are what PIL's `subsampling=` /
+// `restart_marker_blocks=` and cv2's IMWRITE_JPEG_SAMPLING_FACTOR / IMWRITE_JPEG_RST_INTERVAL can ask for.
+// Anything else is JPEG_UNSUPPORTED.
 inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_only = false)
 {
     uint16_t qt[4][64];
@@ -288,10 +293,14 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
         i += L;
     }
     if (!have_sos || F.h <= 0 || F.w <= 0) return JPEG_CORRUPT;
-    if (restart) return JPEG_UNSUPPORTED;
+    F.restart = restart;
+    F.hs = F.vs = 1;                                         // one component: the scan is not interleaved, MCU = one block
     if (F.ncomp == 3) {
-        if (!(hs[0] == 2 && vs[0] == 2 && hs[1] == 1 && vs[1] == 1 && hs[2] == 1 && vs[2] == 1)) return JPEG_UNSUPPORTED;
+        if (!(hs[1] == 1 && vs[1] == 1 && hs[2] == 1 && vs[2] == 1)) return JPEG_UNSUPPORTED;
+        if (!((hs[0] == 2 && vs[0] == 2) || (hs[0] == 2 && vs[0] == 1) || (hs[0] == 1 && vs[0] == 1))) return JPEG_UNSUPPORTED;
         if (tq[1] != tq[2] || td[1] != td[2] || ta[1] != ta[2]) return JPEG_UNSUPPORTED;
+        F.hs = hs[0];
+        F.vs = vs[0];
     } else if (hs[0] != vs[0]) {
         return JPEG_UNSUPPORTED;
     }
@@ -318,7 +327,7 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
             const void *hit = e + 1 < len ? memchr(d + e, 0xFF, len - 1 - e) : nullptr;
             if (!hit) { e = len; break; }
             e = (size_t)(static_cast<const uint8_t *>(hit) - d);
-            if (d[e + 1] != 0x00) break;
+            if (d[e + 1] != 0x00 && !(restart && d[e + 1] >= 0xD0 && d[e + 1] <= 0xD7)) break;
             e += 2;
         }
     }
@@ -326,8 +335,8 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
     // Every block costs at least two bits (a one-bit DC code and a one-bit end-of-block code): a header that promises more
     // blocks than the data can hold is damaged or truncated, and must not size any buffer.
     {
-        const uint64_t m = F.ncomp == 3 ? 16 : 8;
-        const uint64_t blocks = ((uint64_t)(F.w + m - 1) / m) * ((uint64_t)(F.h + m - 1) / m) * (F.ncomp == 3 ? 6 : 1);
+        const uint64_t mw = 8 * (uint64_t)F.hs, mh = 8 * (uint64_t)F.vs;
+        const uint64_t blocks = ((uint64_t)(F.w + mw - 1) / mw) * ((uint64_t)(F.h + mh - 1) / mh) * (F.ncomp == 3 ? (uint64_t)(F.hs * F.vs + 2) : 1);
         if (blocks * 2 > (uint64_t)F.scan_len * 8) return JPEG_CORRUPT;
     }
     return JPEG_OK;

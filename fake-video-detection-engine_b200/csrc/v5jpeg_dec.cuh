@@ -1,9 +1,11 @@
 // v5jpeg_dec.cuh — baseline JPEG decoder on the GPU: what the reference does with
 // Image.open(crop).convert('RGB') (v5_texture_ela.py:64) and cv2.imread(crop, IMREAD_GRAYSCALE) (:83) on the crop files V1
-// wrote with cv2.imwrite (v1_keyframes_facetrack.py:166) — libjpeg's defaults: ISLOW inverse DCT, fancy h2v2 upsampling.
+// wrote with cv2.imwrite (v1_keyframes_facetrack.py:166) — libjpeg's defaults: ISLOW inverse DCT, fancy upsampling (h2v2 for
+// the 4:2:0 files both writers produce by default; h2v1 for 4:2:2 and none for 4:4:4, the layouts their sampling options add).
 // Pixel-identical to both libraries. Per batch of files (any mix of sizes):
 //
-//   unstuff_kernel  one CTA per file: entropy-coded segment with FF 00 -> FF, as a flat bit stream
+//   unstuff_kernel  one CTA per file: entropy-coded segment with FF 00 -> FF (and RSTn markers dropped, their positions
+//                   recorded), as a flat bit stream
 //   huffman_kernel  one CTA per file: Huffman decoding in parallel by SELF-SYNCHRONISATION. The stream is cut into
 //                   1024-bit subsequences, one per thread. Only the first thread knows its decoder state (bit position,
 //                   block-in-MCU, zigzag index); the others start blind at their subsequence's first bit, and because
@@ -13,6 +15,7 @@
 //                   recorded state is the true one. A prefix sum of the blocks completed per subsequence gives every thread
 //                   its output position and a last pass decodes again, this time writing coefficients. Windows of 1024
 //                   subsequences are processed in order by the same CTA, carrying the exact state from one to the next.
+//   huffman_rst_kernel  files with restart intervals only: every interval starts in a known state, one thread each
 //   dc_kernel       one CTA per file: DC differences -> DC values (prefix sum per component, T.81 F.2.2.1) on a dense
 //                   int16-per-block array
 //   idct_kernel     dequantise + ISLOW inverse DCT, 4 threads per block -> sample planes
@@ -46,7 +49,10 @@ struct DecTabSet {                         // Huffman tables of one file: [0] lu
 
 struct DecImage {
     int32_t h, w, ncomp;
+    int32_t hs, vs;                        // luma blocks per MCU across / down: 2x2 (4:2:0), 2x1 (4:2:2), 1x1 (4:4:4, one component)
     int32_t mcux, mcuy, bpm, blocks;
+    int32_t restart;                       // restart interval in MCUs, 0 = none: the file is decoded interval by interval
+    int32_t rst_off;                       // first entry of this file in the interval-start array (restart > 0)
     int32_t tabset;                        // index into the table-set array
     int32_t qt;                            // index into the quantisation-table array (2 x 64 uint16 per entry)
     int32_t yw, yh, cw, ch;                // padded plane sizes
@@ -57,6 +63,22 @@ struct DecImage {
     int64_t plane_off;                     // Y plane inside the plane buffer; Cb follows, then Cr
     int64_t rgb_off, gray_off;             // output positions (bytes), -1 = not wanted
 };
+
+// Geometry of a file: MCU grid, blocks per MCU (luma blocks, then Cb, Cr), padded plane sizes.
+V5_HOSTDEV void dec_geometry(DecImage &im, int h, int w, int ncomp, int hs, int vs)
+{
+    im.h = h; im.w = w; im.ncomp = ncomp;
+    im.hs = ncomp == 3 ? hs : 1;
+    im.vs = ncomp == 3 ? vs : 1;
+    im.mcux = (w + 8 * im.hs - 1) / (8 * im.hs);
+    im.mcuy = (h + 8 * im.vs - 1) / (8 * im.vs);
+    im.bpm = ncomp == 3 ? im.hs * im.vs + 2 : 1;
+    im.blocks = im.mcux * im.mcuy * im.bpm;
+    im.yw = im.mcux * 8 * im.hs;
+    im.yh = im.mcuy * 8 * im.vs;
+    im.cw = ncomp == 3 ? im.mcux * 8 : 0;
+    im.ch = ncomp == 3 ? im.mcuy * 8 : 0;
+}
 
 struct SubState {                          // decoder state between two symbols
     uint32_t p;                            // bit position in the unstuffed stream
@@ -168,7 +190,7 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
     while (p < limit) {
-        const int comp = (bpm == 6 && c >= 4) ? 1 : 0;
+        const int comp = (bpm > 1 && c >= bpm - 2) ? 1 : 0;              // an MCU ends with its Cb and Cr block
         const bool is_dc = z == 0;
         const DecTable &tab = is_dc ? T.dc[comp] : T.ac[comp];
         const uint32_t win = stream.window(p);
@@ -194,6 +216,45 @@ V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, 
     s.c = (uint16_t)c;
     s.z = (uint16_t)z;
     return done;
+}
+
+// Files with restart intervals (DRI): every interval starts byte-aligned, right after its RSTn marker, with the DC predictors
+// at zero — its decoder state is known without any synchronisation, so one thread decodes one interval from start to end
+// (huffman_rst_kernel). `nblocks` blocks from bit position p; coef / dc point at the interval's first block and receive the
+// AC coefficients and the DC VALUES (predictions undone on the fly). Returns the blocks decoded before `limit` was reached
+// (== nblocks for a well-formed interval).
+template <class Src>
+V5_HOSTDEV int decode_interval(const Src &stream, uint32_t p, uint32_t limit, const DecTabSet &T, int bpm, int nblocks, int16_t *coef, int16_t *dc)
+{
+    int pred[3] = {0, 0, 0};
+    int c = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const int ci = (bpm > 1 && c >= bpm - 2) ? c - (bpm - 2) + 1 : 0, comp = ci ? 1 : 0;
+        int z = 0;
+        while (z < 64) {
+            if (p >= limit) return b;
+            const bool is_dc = z == 0;
+            const uint32_t win = stream.window(p);
+            const uint32_t act = huff_action(is_dc ? T.dc[comp] : T.ac[comp], win);
+            const int len = (int)(act & 31u), sz = (int)((act >> 8) & 15u), zinc = (int)((act >> 16) & 127u), total = (int)(act >> 24);
+            const int pos = z + zinc - 1;
+            int v = 0;
+            if (sz) {
+                v = (int)((win << len) >> (32 - sz));
+                v = v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v;
+            }
+            if (is_dc) {
+                pred[ci] += v;
+                dc[b] = (int16_t)pred[ci];
+            } else if (sz && pos < 64) {
+                coef[(int64_t)b * 64 + pos] = (int16_t)v;
+            }
+            z += zinc;
+            p += (uint32_t)total;
+        }
+        c = c + 1 == bpm ? 0 : c + 1;
+    }
+    return nblocks;
 }
 
 // ------------------------------------------------------------------------------------ window logic of huffman_kernel
@@ -319,14 +380,15 @@ V5_HOSTDEV void dc_apply_mcu(int16_t *mcu_dc, int bpm, int &py, int &pcb, int &p
         mcu_dc[0] = (int16_t)py;
         return;
     }
-    for (int i = 0; i < 4; i++) {
+    const int ny = bpm - 2;
+    for (int i = 0; i < ny; i++) {
         py += mcu_dc[i];
         mcu_dc[i] = (int16_t)py;
     }
-    pcb += mcu_dc[4];
-    mcu_dc[4] = (int16_t)pcb;
-    pcr += mcu_dc[5];
-    mcu_dc[5] = (int16_t)pcr;
+    pcb += mcu_dc[ny];
+    mcu_dc[ny] = (int16_t)pcb;
+    pcr += mcu_dc[ny + 1];
+    mcu_dc[ny + 1] = (int16_t)pcr;
 }
 
 // ------------------------------------------------------------------------------------------- inverse DCT of a block
@@ -372,19 +434,26 @@ V5_HOSTDEV int64_t block_dest(const DecImage &im, int g, int &pitch, int &comp)
         const int my = g / im.mcux, mx = g - my * im.mcux;
         return (int64_t)(8 * my) * im.yw + 8 * mx;
     }
-    const int m = g / 6, i = g - 6 * m;
+    const int m = g / im.bpm, i = g - im.bpm * m, ny = im.bpm - 2;
     const int my = m / im.mcux, mx = m - my * im.mcux;
-    if (i < 4) {
+    if (i < ny) {                                                         // luma blocks of an MCU: row-major, hs across
+        const int br = im.hs == 2 ? i >> 1 : i, bc = im.hs == 2 ? i & 1 : 0;       // (vs == 2 implies hs == 2 here)
         pitch = im.yw;
         comp = 0;
-        return (int64_t)(16 * my + 8 * (i >> 1)) * im.yw + 16 * mx + 8 * (i & 1);
+        return (int64_t)(8 * (im.vs * my + br)) * im.yw + 8 * (im.hs * mx + bc);
     }
     pitch = im.cw;
-    comp = i - 3;
-    return (int64_t)im.yw * im.yh + (int64_t)(i - 4) * im.cw * im.ch + (int64_t)(8 * my) * im.cw + 8 * mx;
+    comp = i - ny + 1;
+    return (int64_t)im.yw * im.yh + (int64_t)(i - ny) * im.cw * im.ch + (int64_t)(8 * my) * im.cw + 8 * mx;
 }
 
 // ------------------------------------------------------------------------------------------ upsample + colour (A.7/A.8)
+// Chroma for a pixel, as libjpeg's upsamplers produce it with do_fancy_upsampling (jdsample.c):
+//   4:2:0  h2v2 "triangle" filter: 3/4 nearer + 1/4 further row, then the same along the row, biases 8 / 7, >> 4   (A.7)
+//   4:2:2  h2v1: 3/4 nearer + 1/4 further sample along the row, biases 1 / 2, >> 2; rows map one to one
+//   4:4:4  the sample itself
+// At the first / last column the missing neighbour is the sample itself (libjpeg's special cases reduce to exactly that), and
+// planes no wider than two samples are replicated without any filtering.
 V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int y, uint8_t out[3])
 {
     const uint8_t *yp = planes, *cbp = planes + (int64_t)im.yw * im.yh, *crp = cbp + (int64_t)im.cw * im.ch;
@@ -393,24 +462,31 @@ V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int 
         out[0] = out[1] = out[2] = (uint8_t)yy;
         return;
     }
-    const int hc = (im.h + 1) >> 1, wc = (im.w + 1) >> 1, cw = im.cw;
-    const int r = y >> 1, cx = x >> 1;
-    int nb = (y & 1) ? r + 1 : r - 1;
-    nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
+    const int hs = im.hs, vs = im.vs;
+    const int hc = (im.h + vs - 1) / vs, wc = (im.w + hs - 1) / hs, cw = im.cw;
+    const int r = vs == 2 ? y >> 1 : y, cx = hs == 2 ? x >> 1 : x;
     int cb, cr;
-    if (wc <= 2) {
+    if (hs == 1 || wc <= 2) {
         cb = cbp[(int64_t)r * cw + cx];
         cr = crp[(int64_t)r * cw + cx];
     } else {
         int nx = (x & 1) ? cx + 1 : cx - 1;
         nx = nx < 0 ? 0 : (nx > wc - 1 ? wc - 1 : nx);
-        const int bias = (x & 1) ? 7 : 8;
-        int s0 = 3 * cbp[(int64_t)r * cw + cx] + cbp[(int64_t)nb * cw + cx];
-        int s1 = 3 * cbp[(int64_t)r * cw + nx] + cbp[(int64_t)nb * cw + nx];
-        cb = (3 * s0 + s1 + bias) >> 4;
-        s0 = 3 * crp[(int64_t)r * cw + cx] + crp[(int64_t)nb * cw + cx];
-        s1 = 3 * crp[(int64_t)r * cw + nx] + crp[(int64_t)nb * cw + nx];
-        cr = (3 * s0 + s1 + bias) >> 4;
+        if (vs == 2) {
+            int nb = (y & 1) ? r + 1 : r - 1;
+            nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
+            const int bias = (x & 1) ? 7 : 8;
+            int s0 = 3 * cbp[(int64_t)r * cw + cx] + cbp[(int64_t)nb * cw + cx];
+            int s1 = 3 * cbp[(int64_t)r * cw + nx] + cbp[(int64_t)nb * cw + nx];
+            cb = (3 * s0 + s1 + bias) >> 4;
+            s0 = 3 * crp[(int64_t)r * cw + cx] + crp[(int64_t)nb * cw + cx];
+            s1 = 3 * crp[(int64_t)r * cw + nx] + crp[(int64_t)nb * cw + nx];
+            cr = (3 * s0 + s1 + bias) >> 4;
+        } else {
+            const int bias = (x & 1) ? 2 : 1;
+            cb = (3 * cbp[(int64_t)r * cw + cx] + cbp[(int64_t)r * cw + nx] + bias) >> 2;
+            cr = (3 * crp[(int64_t)r * cw + cx] + crp[(int64_t)r * cw + nx] + bias) >> 2;
+        }
     }
     const int cbd = cb - 128, crd = cr - 128;
     out[0] = (uint8_t)v5::clamp255(yy + ((91881 * crd + 32768) >> 16));
@@ -419,8 +495,8 @@ V5_HOSTDEV void pixel_rgb(const DecImage &im, const uint8_t *planes, int x, int 
 }
 
 // Eight consecutive pixels x0 .. x0+7 (x0 a multiple of 8) of row y: same arithmetic as pixel_rgb with the loads shared —
-// two 32-bit words of luma and, per chroma component and row, one aligned word plus the two neighbours beside it.
-// out: 24 bytes R G B R G B ...; pixels at or beyond the image width are left untouched.
+// two 32-bit words of luma and, per chroma component and row, one aligned word plus the two neighbours beside it (two words
+// and no neighbours for 4:4:4). out: 24 bytes R G B R G B ...; pixels at or beyond the image width are left untouched.
 V5_HOSTDEV uint32_t load_u32(const uint8_t *p)
 {
 #ifdef __CUDA_ARCH__
@@ -440,37 +516,62 @@ V5_HOSTDEV void pixels8_rgb(const DecImage &im, const uint8_t *planes, int x0, i
         return;
     }
     const uint8_t *cbp = planes + (int64_t)im.yw * im.yh, *crp = cbp + (int64_t)im.cw * im.ch;
-    const int hc = (im.h + 1) >> 1, wc = (im.w + 1) >> 1, cw = im.cw;
-    const int r = y >> 1, cx0 = x0 >> 1;                                  // cx0 is a multiple of 4
-    int nb = (y & 1) ? r + 1 : r - 1;
-    nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
-    const uint8_t *rows[4] = {cbp + (int64_t)r * cw, cbp + (int64_t)nb * cw, crp + (int64_t)r * cw, crp + (int64_t)nb * cw};
-    const int cl = cx0 > 0 ? cx0 - 1 : 0, cr_ = cx0 + 4 < wc ? cx0 + 4 : wc - 1;   // neighbours beside the word, clamped
-    int s[2][6];                                                          // 3 * cur + neighbour row at chroma columns cx0-1 .. cx0+4
+    const int hs = im.hs, vs = im.vs, cw = im.cw;
+    const int hc = (im.h + vs - 1) / vs, wc = (im.w + hs - 1) / hs;
+    const int r = vs == 2 ? y >> 1 : y;
+    int cbv[8], crv[8];                                                  // chroma of the eight pixels
+    if (hs == 1) {                                                        // 4:4:4: plane rows are padded to a multiple of 8
+        const uint8_t *pb = cbp + (int64_t)r * cw + x0, *pr = crp + (int64_t)r * cw + x0;
+        const uint32_t b[2] = {load_u32(pb), load_u32(pb + 4)}, c[2] = {load_u32(pr), load_u32(pr + 4)};
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-        const uint32_t wr = load_u32(rows[2 * c] + cx0), wn = load_u32(rows[2 * c + 1] + cx0);
-        s[c][0] = 3 * rows[2 * c][cl] + rows[2 * c + 1][cl];
-        s[c][5] = 3 * rows[2 * c][cr_] + rows[2 * c + 1][cr_];
+        for (int k = 0; k < 8; k++) {
+            cbv[k] = (int)((b[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            crv[k] = (int)((c[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        }
+    } else {
+        const int cx0 = x0 >> 1;                                          // a multiple of 4
+        int nb = r;
+        if (vs == 2) {
+            nb = (y & 1) ? r + 1 : r - 1;
+            nb = nb < 0 ? 0 : (nb > hc - 1 ? hc - 1 : nb);
+        }
+        const uint8_t *rows[4] = {cbp + (int64_t)r * cw, cbp + (int64_t)nb * cw, crp + (int64_t)r * cw, crp + (int64_t)nb * cw};
+        if (wc <= 2) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int col = cx0 + j < wc ? j : wc - 1 - cx0;                    // columns past the last one repeat it (col >= 0: cx0 < wc)
-            s[c][1 + j] = 3 * (int)((wr >> (8 * col)) & 0xffu) + (int)((wn >> (8 * col)) & 0xffu);
+            for (int k = 0; k < 8; k++) {
+                cbv[k] = rows[0][cx0 + (k >> 1)];
+                crv[k] = rows[2][cx0 + (k >> 1)];
+            }
+        } else {
+            const int cl = cx0 > 0 ? cx0 - 1 : 0, cr_ = cx0 + 4 < wc ? cx0 + 4 : wc - 1;   // neighbours beside the word, clamped
+            // s: chroma columns cx0-1 .. cx0+4 after the vertical step — 3 * nearer + further row (4:2:0), or the row itself (4:2:2)
+            const int wn = vs == 2 ? 1 : 0, wcur = vs == 2 ? 3 : 1;
+            int s[2][6];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t wr = load_u32(rows[2 * c] + cx0), wnb = load_u32(rows[2 * c + 1] + cx0);
+                s[c][0] = wcur * rows[2 * c][cl] + wn * rows[2 * c + 1][cl];
+                s[c][5] = wcur * rows[2 * c][cr_] + wn * rows[2 * c + 1][cr_];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int col = cx0 + j < wc ? j : wc - 1 - cx0;            // columns past the last one repeat it (col >= 0: cx0 < wc)
+                    s[c][1 + j] = wcur * (int)((wr >> (8 * col)) & 0xffu) + wn * (int)((wnb >> (8 * col)) & 0xffu);
+                }
+            }
+            const int sh = vs == 2 ? 4 : 2;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int j = 1 + (k >> 1), jn = (k & 1) ? j + 1 : j - 1;
+                const int bias = vs == 2 ? ((k & 1) ? 7 : 8) : ((k & 1) ? 2 : 1);
+                cbv[k] = (3 * s[0][j] + s[0][jn] + bias) >> sh;
+                crv[k] = (3 * s[1][j] + s[1][jn] + bias) >> sh;
+            }
         }
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         if (k >= nvalid) break;
-        const int j = 1 + (k >> 1), jn = (k & 1) ? j + 1 : j - 1, bias = (k & 1) ? 7 : 8;
-        int cb, cr;
-        if (wc <= 2) {
-            cb = rows[0][cx0 + (k >> 1)];
-            cr = rows[2][cx0 + (k >> 1)];
-        } else {
-            cb = (3 * s[0][j] + s[0][jn] + bias) >> 4;
-            cr = (3 * s[1][j] + s[1][jn] + bias) >> 4;
-        }
-        const int yy = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xffu), cbd = cb - 128, crd = cr - 128;
+        const int yy = (int)((yw[k >> 2] >> (8 * (k & 3))) & 0xffu), cbd = cbv[k] - 128, crd = crv[k] - 128;
         out[3 * k] = (uint8_t)v5::clamp255(yy + ((91881 * crd + 32768) >> 16));
         out[3 * k + 1] = (uint8_t)v5::clamp255(yy + ((-22554 * cbd - 46802 * crd + 32768) >> 16));
         out[3 * k + 2] = (uint8_t)v5::clamp255(yy + ((116130 * cbd + 32768) >> 16));
@@ -512,35 +613,55 @@ __device__ __forceinline__ uint32_t dec_cta_scan(uint32_t v, uint32_t *warp_sums
 }
 
 // FF 00 -> FF. stream_bits[img] = 8 x kept bytes. The stream buffer is zero-initialised and padded by the host side.
+// Files with restart intervals: the RSTn markers (FF D0..D7) are dropped as well, and the position where interval k begins
+// in the unstuffed stream goes to rst_starts[im.rst_off + k] (entry 0 stays 0).
 __global__ void __launch_bounds__(1024) unstuff_kernel(const DecImage *images, const uint8_t *files, uint8_t *streams,
-                                                       uint32_t *stream_bits)
+                                                       uint32_t *stream_bits, uint32_t *rst_starts)
 {
     __shared__ uint32_t warp_sums[33];
     const DecImage im = images[blockIdx.x];
     const uint8_t *src = files + im.scan_off;
     uint8_t *dst = streams + im.stream_off;
-    uint32_t running = 0;
+    const int mcus = im.mcux * im.mcuy;
+    const uint32_t n_int = im.restart > 0 ? (uint32_t)((mcus + im.restart - 1) / im.restart) : 0u;
+    uint32_t running = 0, markers = 0;
     for (int64_t base = 0; base < im.scan_len; base += 4 * 1024) {
         const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
-        uint8_t b[5];
-        uint32_t keep = 0, cnt = 0;
+        uint8_t b[6];                                                     // the byte before this thread's four, and the one after
+        uint32_t keep = 0, cnt = 0, mark = 0, nmark = 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < 6; k++) {
             const int64_t i = i0 - 1 + k;
             b[k] = (i >= 0 && i < im.scan_len) ? src[i] : 0;
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (i0 + k < im.scan_len && !(b[k + 1] == 0x00 && b[k] == 0xFF)) {
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k >= im.scan_len) continue;
+            const bool stuffed = b[k + 1] == 0x00 && b[k] == 0xFF;
+            const bool rst_ff = n_int && b[k + 1] == 0xFF && b[k + 2] >= 0xD0 && b[k + 2] <= 0xD7;       // first byte of a marker
+            const bool rst_dn = n_int && b[k] == 0xFF && b[k + 1] >= 0xD0 && b[k + 1] <= 0xD7;           // its second byte
+            if (!stuffed && !rst_ff && !rst_dn) {
                 keep |= 1u << k;
                 cnt++;
             }
+            if (rst_dn) {
+                mark |= 1u << k;
+                nmark++;
+            }
+        }
         uint32_t sum;
         uint32_t o = running + dec_cta_scan(cnt, warp_sums, &sum);
+        uint32_t msum = 0, m = 0;
+        if (n_int) m = markers + dec_cta_scan(nmark, warp_sums, &msum);   // uniform branch: n_int is per file
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < 4; k++) {
             if (keep & (1u << k)) dst[o++] = b[k + 1];
+            if (mark & (1u << k)) {                                       // the interval after this marker starts at output byte o
+                if (++m < n_int) rst_starts[im.rst_off + m] = o;
+            }
+        }
         running += sum;
+        markers += msum;
     }
     if (threadIdx.x == 0) stream_bits[blockIdx.x] = running * 8u;
 }
@@ -563,6 +684,10 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
     HuffSmem &S = *reinterpret_cast<HuffSmem *>(huff_smem_raw);
     const int t = (int)threadIdx.x;
     const DecImage im = images[blockIdx.x];
+    if (im.restart > 0) {                                                 // decoded interval by interval (huffman_rst_kernel)
+        if (t == 0) status[blockIdx.x] = 0;
+        return;
+    }
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&tabsets[im.tabset]);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
@@ -645,7 +770,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_sync_kernel(const 
     J.coef = nullptr;
     J.dc = nullptr;
     const uint32_t windows = window_count(J.nsub), parts = part_count(J.nsub, gridDim.x);
-    if (blockIdx.x >= parts || windows == 0) return;
+    if (blockIdx.x >= parts || windows == 0 || im.restart > 0) return;
     const uint32_t w_first = part_first(blockIdx.x, parts, windows), w_end = part_first(blockIdx.x + 1, parts, windows);
     SubInfo *sub_info = sub_info_all + im.sub_off;
     {
@@ -701,6 +826,10 @@ __global__ void __launch_bounds__(1024) huffman_fixup_kernel(const DecImage *ima
     __shared__ uint32_t warp_sums[33];
     __shared__ SubState started_from[32];
     const DecImage im = images[blockIdx.x];
+    if (im.restart > 0) {                                                 // decoded interval by interval (huffman_rst_kernel)
+        if (threadIdx.x == 0) status[blockIdx.x] = 0;
+        return;
+    }
     const uint8_t *stream = streams + im.stream_off;
     const uint32_t total_bits = stream_bits[blockIdx.x], nsub = (total_bits + SUB_BITS - 1) / SUB_BITS;
     const uint32_t windows = window_count(nsub), parts = part_count(nsub, max_parts);
@@ -756,7 +885,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_write_kernel(const
     J.coef = coef + im.coef_off * 64;
     J.dc = dc + im.coef_off;
     const uint32_t w0 = blockIdx.x * (uint32_t)HUFF_NT;
-    if (w0 >= J.nsub) return;
+    if (w0 >= J.nsub || im.restart > 0) return;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&tabsets[im.tabset]);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
@@ -768,11 +897,41 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_write_kernel(const
     huff_write_sub(t, J, S.T, w0, sub_info_all + im.sub_off, sub_block0_all + im.sub_off);
 }
 
+// Files with restart intervals: one thread per interval, reading the stream in place. grid = (ceil(max intervals / 128), files).
+// Runs after the synchronising kernels (which skip these files and set their status to 0); a short interval flags the file.
+__global__ void __launch_bounds__(128) huffman_rst_kernel(const DecImage *images, const DecTabSet *tabsets, const uint8_t *streams,
+                                                          const uint32_t *stream_bits, const uint32_t *rst_starts, int16_t *coef,
+                                                          int16_t *dc, int32_t *status)
+{
+    const DecImage im = images[blockIdx.y];
+    if (im.restart <= 0) return;
+    const int mcus = im.mcux * im.mcuy, n_int = (mcus + im.restart - 1) / im.restart;
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= n_int) return;
+    const uint32_t total_bits = stream_bits[blockIdx.y];
+    const uint32_t *starts = rst_starts + im.rst_off;
+    const uint32_t p0 = k == 0 ? 0u : starts[k] * 8u;
+    if (k > 0 && starts[k] == 0) {                                        // fewer markers in the data than the header promises
+        status[blockIdx.y] = -1;
+        return;
+    }
+    uint32_t limit = total_bits;
+    if (k + 1 < n_int && starts[k + 1] != 0 && starts[k + 1] * 8u < limit) limit = starts[k + 1] * 8u;
+    const int first_mcu = k * im.restart, n_mcu = mcus - first_mcu < im.restart ? mcus - first_mcu : im.restart;
+    const int64_t block0 = im.coef_off + (int64_t)first_mcu * im.bpm;
+    ByteStream bs;
+    bs.data = streams + im.stream_off;
+    const int done = decode_interval(bs, p0, limit, tabsets[im.tabset], im.bpm, n_mcu * im.bpm, coef + block0 * 64, dc + block0);
+    if (done != n_mcu * im.bpm) status[blockIdx.y] = -1;
+}
+
 // DC differences -> values. One CTA per file; thread t owns MCU chunk_base + t, three CTA scans per chunk of 1024 MCUs.
+// (files with restart intervals already hold values: huffman_rst_kernel)
 __global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_t *dc)
 {
     __shared__ uint32_t warp_sums[33];
     const DecImage im = images[blockIdx.x];
+    if (im.restart > 0) return;
     int16_t *base = dc + im.coef_off;
     const int mcus = im.mcux * im.mcuy;
     int run[3] = {0, 0, 0};
@@ -783,9 +942,10 @@ __global__ void __launch_bounds__(1024) dc_kernel(const DecImage *images, int16_
         if (m < mcus) {
             if (im.bpm == 1) d[0] = mc[0];
             else {
-                d[0] = mc[0] + mc[1] + mc[2] + mc[3];
-                d[1] = mc[4];
-                d[2] = mc[5];
+                const int ny = im.bpm - 2;
+                for (int i = 0; i < ny; i++) d[0] += mc[i];
+                d[1] = mc[ny];
+                d[2] = mc[ny + 1];
             }
         }
         int pred[3];

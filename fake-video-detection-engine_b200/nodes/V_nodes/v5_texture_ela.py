@@ -16,7 +16,7 @@ What runs on the B200 instead of Pillow/OpenCV/NumPy:
     on request, the scratch file ``temp_ela_{i}.jpg`` (:66-67) through ``v5ela_jpeg_encode_host`` — the files equal the
     reference's byte for byte.
   There is no CPU fallback for any of it: a missing library or GPU — or a crop outside the GPU decoder's set (not a JPEG,
-  progressive, 4:4:4, restart markers: nothing V1 writes) — surfaces as that face's error, like any other analysis failure
+  progressive, CMYK, 12-bit: nothing V1 writes) — surfaces as that face's error, like any other analysis failure
   (reference :140-144). Reading and writing the files with Pillow/OpenCV instead is an explicit choice of the caller
   (``v5_gpu_codec = False``), never something the node decides on its own.
 Optional state keys (defaults = the reference's literals): ``v5_quality`` 90, ``v5_max_faces`` 3, ``v5_device`` 0,

@@ -164,9 +164,10 @@ V5ELA_API int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, i
  * Decoder: what the reference reads with `Image.open(crop_path).convert('RGB')` (v5_texture_ela.py:64) and
  * `cv2.imread(crop_path, cv2.IMREAD_GRAYSCALE)` (v5…:83) — the crops V1 wrote with cv2.imwrite (v1_keyframes_facetrack.py:166).
  * Pixel-identical to libjpeg's defaults (ISLOW inverse DCT, fancy upsampling). Supported: 8-bit baseline Huffman files with
- * one component or three components sampled 2x2,1x1,1x1 (4:2:0), one scan, any Huffman / quantisation tables, no restart
- * interval — everything PIL's and OpenCV's writers produce by default; anything else returns V5ELA_ERR_UNSUPPORTED and
- * v5ela_last_error names the file.
+ * one component, or three components with the luma sampled 2x2 (4:2:0), 2x1 (4:2:2) or 1x1 (4:4:4) against 1x1 chroma; one
+ * scan; any Huffman / quantisation tables; with or without restart intervals — everything PIL's and OpenCV's writers produce
+ * by default (4:2:0, no restarts) plus what their sampling and restart options add. Anything else (progressive, other
+ * sampling factors, CMYK, 12-bit, arithmetic coding) returns V5ELA_ERR_UNSUPPORTED and v5ela_last_error names the file.
  *   files_host / lens : n complete JPEG files in HOST memory (they come from disk); sizes may differ from file to file.
  *             Files that all live in page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied
  *             to the device asynchronously from where they are — keep them alive until the stream has been synchronised;
@@ -174,7 +175,8 @@ V5ELA_API int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, i
  *   d_rgb   : optional DEVICE buffer; file i is decoded to RGB (HWC; a one-component file is replicated) at byte offset
  *             rgb_offsets[i], or tightly packed in file order when rgb_offsets is NULL.
  *   d_gray  : optional DEVICE buffer; the luma plane alone (what IMREAD_GRAYSCALE returns), offsets likewise.
- *   d_status: optional DEVICE array of n ints: 0, or -1 when the entropy-coded data of that file ended early.
+ *   d_status: optional DEVICE array of n ints: 0, or -1 when the entropy-coded data of that file ended early (or a restart
+ *             marker is missing).
  * Header parsing and the staging copy happen on the calling thread; the decode itself is asynchronous on `cuda_stream`.
  * The compressed bytes are uploaded on an internal stream as soon as the call is made (so the upload of one batch overlaps
  * the kernels of the previous one): the files must be complete in host memory at that moment.

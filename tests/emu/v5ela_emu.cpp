@@ -21,7 +21,10 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
     memset(S, 0xA5, sizeof(v5::Smem));                       // poison: uninitialised reads must not matter
     std::vector<v5::ThreadAcc> acc(v5::NT);
     const int total = n * p.n_strips * p.n_segs;
-    for (int work = 0; work < total; work++) v5::process_work_item(*S, p, work, acc.data());
+    for (int work = 0; work < total; work++) {
+        if (v5::fast_path_ok(p)) v5::process_work_item<true>(*S, p, work, acc.data());       // the choice the C ABI makes
+        else v5::process_work_item<false>(*S, p, work, acc.data());
+    }
     for (int i = 0; i < n; i++) v5::finalize_record(records[i]);
     free(S);
     return 0;

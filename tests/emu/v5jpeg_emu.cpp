@@ -89,6 +89,41 @@ extern "C" int64_t v5jemu_encode(const uint8_t *img, int h, int w, int channels,
 }
 
 // -> 0, or the parse error; rounds_out (optional): the largest number of synchronisation rounds any window needed
+// dc_kernel, idct_kernel, colour_kernel: everything after the entropy decoding
+static int emu_finish(const DecImage &im, const FileInfo &F, std::vector<int16_t> &coef, std::vector<int16_t> &dcv, bool apply_dc,
+                      uint8_t *rgb_out, uint8_t *gray_out, int16_t *coef_out)
+{
+    int py = 0, pcb = 0, pcr = 0;
+    if (apply_dc)                                                           // dc_kernel (files without restart intervals)
+        for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&dcv[(size_t)mcu * im.bpm], im.bpm, py, pcb, pcr);
+    for (int g = 0; g < im.blocks; g++) coef[(size_t)g * 64] = dcv[(size_t)g];     // what idct_kernel does while staging a block
+    if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
+    std::vector<uint8_t> planes((size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch);
+    for (int g = 0; g < im.blocks; g++) {
+        int pitch, comp;
+        const int64_t off = block_dest(im, g, pitch, comp);
+        alignas(16) int16_t nat[64], ws[64];
+        for (int k = 0; k < 64; k++) nat[kZigzag[k]] = coef[(size_t)g * 64 + k];       // the kernel scatters while staging
+        alignas(16) uint16_t qt[64];
+        memcpy(qt, F.qt[comp ? 1 : 0], sizeof(qt));
+        for (int j = 0; j < 4; j++) idct_cols(nat, qt, j, ws);
+        for (int j = 0; j < 4; j++) idct_rows(ws, j, planes.data() + off, pitch);
+    }
+    for (int y = 0; y < im.h; y++)
+        for (int x0 = 0; x0 < im.w; x0 += 8) {
+            uint8_t o[24], single[3];
+            pixels8_rgb(im, planes.data(), x0, y, o);                       // what the kernel runs
+            for (int k = 0; k < 8 && x0 + k < im.w; k++) {
+                const int x = x0 + k;
+                if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
+                pixel_rgb(im, planes.data(), x, y, single);                 // the one-pixel statement of the same arithmetic
+                if (memcmp(single, o + 3 * k, 3)) return -4;
+                if (rgb_out) memcpy(rgb_out + ((size_t)y * im.w + x) * 3, o + 3 * k, 3);
+            }
+        }
+    return 0;
+}
+
 extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out, uint8_t *gray_out, int16_t *coef_out, int *rounds_out)
 {
     FileInfo *F = new FileInfo();
@@ -96,17 +131,18 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     if (rc) { delete F; return rc; }
     DecImage im;
     memset(&im, 0, sizeof(im));
-    im.h = F->h; im.w = F->w; im.ncomp = F->ncomp;
-    const int m = F->ncomp == 3 ? 16 : 8;
-    im.mcux = (F->w + m - 1) / m; im.mcuy = (F->h + m - 1) / m;
-    im.bpm = F->ncomp == 3 ? 6 : 1;
-    im.blocks = im.mcux * im.mcuy * im.bpm;
-    im.yw = im.mcux * m; im.yh = im.mcuy * m;
-    im.cw = F->ncomp == 3 ? im.yw / 2 : 0; im.ch = F->ncomp == 3 ? im.yh / 2 : 0;
+    dec_geometry(im, F->h, F->w, F->ncomp, F->hs, F->vs);
     std::vector<uint8_t> stream;
+    std::vector<uint32_t> rst_starts(1, 0u);                                // unstuff_kernel: where every restart interval begins
     for (size_t i = 0; i < F->scan_len; i++) {
         const uint8_t b = data[F->scan_off + i];
-        if (b == 0 && i > 0 && data[F->scan_off + i - 1] == 0xFF) continue;
+        const uint8_t prev = i > 0 ? data[F->scan_off + i - 1] : 0, next = i + 1 < F->scan_len ? data[F->scan_off + i + 1] : 0;
+        if (b == 0 && prev == 0xFF) continue;
+        if (F->restart && b == 0xFF && next >= 0xD0 && next <= 0xD7) continue;
+        if (F->restart && prev == 0xFF && b >= 0xD0 && b <= 0xD7) {
+            rst_starts.push_back((uint32_t)stream.size());
+            continue;
+        }
         stream.push_back(b);
     }
     const uint32_t total_bits = (uint32_t)stream.size() * 8;
@@ -130,6 +166,25 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
 #ifndef V5J_EMU_PARTS
 #define V5J_EMU_PARTS 0
 #endif
+    if (F->restart > 0) {
+        // ---- huffman_rst_kernel: one thread per restart interval, DC values written directly
+        const int mcus = im.mcux * im.mcuy, n_int = (mcus + F->restart - 1) / F->restart;
+        bool ok = (int)rst_starts.size() >= n_int;
+        ByteStream bs;
+        bs.data = stream.data();
+        for (int k = n_int; k-- > 0 && ok;) {                               // any order: the intervals are independent threads
+            const uint32_t p0 = rst_starts[(size_t)k] * 8u;
+            uint32_t limit = total_bits;
+            if (k + 1 < n_int && rst_starts[(size_t)k + 1] * 8u < limit) limit = rst_starts[(size_t)k + 1] * 8u;
+            const int first_mcu = k * F->restart, n_mcu = mcus - first_mcu < F->restart ? mcus - first_mcu : F->restart;
+            const int64_t block0 = (int64_t)first_mcu * im.bpm;
+            ok = decode_interval(bs, p0, limit, *T, im.bpm, n_mcu * im.bpm, coef.data() + block0 * 64, dcv.data() + block0) == n_mcu * im.bpm;
+        }
+        if (rounds_out) *rounds_out = 0;
+        const int rc2 = emu_finish(im, *F, coef, dcv, false, rgb_out, gray_out, coef_out);
+        delete T; delete F;
+        return rc2 ? rc2 : (ok ? 0 : -3);
+    }
 #if V5J_EMU_PARTS == 0
     // ---- huffman_kernel: one CTA per file, windows in order, coefficients written window by window
     HuffWindow *W = new HuffWindow();
@@ -226,35 +281,9 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     const bool ok = total_blocks >= (uint32_t)im.blocks;
 #endif
     if (rounds_out) *rounds_out = max_rounds;
-    int py = 0, pcb = 0, pcr = 0;
-    for (int mcu = 0; mcu < im.mcux * im.mcuy; mcu++) dc_apply_mcu(&dcv[(size_t)mcu * im.bpm], im.bpm, py, pcb, pcr);
-    for (int g = 0; g < im.blocks; g++) coef[(size_t)g * 64] = dcv[(size_t)g];     // what idct_kernel does while staging a block
-    if (coef_out) memcpy(coef_out, coef.data(), coef.size() * 2);
-    std::vector<uint8_t> planes((size_t)im.yw * im.yh + 2 * (size_t)im.cw * im.ch);
-    for (int g = 0; g < im.blocks; g++) {
-        int pitch, comp;
-        const int64_t off = block_dest(im, g, pitch, comp);
-        alignas(16) int16_t nat[64], ws[64];
-        for (int k = 0; k < 64; k++) nat[kZigzag[k]] = coef[(size_t)g * 64 + k];       // the kernel scatters while staging
-        alignas(16) uint16_t qt[64];
-        memcpy(qt, F->qt[comp ? 1 : 0], sizeof(qt));
-        for (int j = 0; j < 4; j++) idct_cols(nat, qt, j, ws);
-        for (int j = 0; j < 4; j++) idct_rows(ws, j, planes.data() + off, pitch);
-    }
-    for (int y = 0; y < im.h; y++)
-        for (int x0 = 0; x0 < im.w; x0 += 8) {
-            uint8_t o[24], single[3];
-            pixels8_rgb(im, planes.data(), x0, y, o);                       // what the kernel runs
-            for (int k = 0; k < 8 && x0 + k < im.w; k++) {
-                const int x = x0 + k;
-                if (gray_out) gray_out[(size_t)y * im.w + x] = planes[(size_t)y * im.yw + x];
-                pixel_rgb(im, planes.data(), x, y, single);                 // the one-pixel statement of the same arithmetic
-                if (memcmp(single, o + 3 * k, 3)) return -4;
-                if (rgb_out) memcpy(rgb_out + ((size_t)y * im.w + x) * 3, o + 3 * k, 3);
-            }
-        }
+    const int rc2 = emu_finish(im, *F, coef, dcv, true, rgb_out, gray_out, coef_out);
     delete W; delete T; delete F;
-    return ok ? 0 : -3;
+    return rc2 ? rc2 : (ok ? 0 : -3);
 }
 
 extern "C" int v5jemu_info(const uint8_t *data, int64_t len, int *h, int *w, int *ncomp)

@@ -74,7 +74,9 @@ def emu_decode(lib, data):
         raise ValueError(rc)
     rgb = np.zeros((h.value, w.value, 3), np.uint8)
     gray = np.zeros((h.value, w.value), np.uint8)
-    coef = np.zeros((c_oracle.jpeg_blocks(h.value, w.value, c.value), 64), np.int16)
+    hs, vs, _ = c_oracle.jpeg_layout(data)
+    mcus = ((h.value + 8 * vs - 1) // (8 * vs)) * ((w.value + 8 * hs - 1) // (8 * hs))
+    coef = np.zeros((mcus * (hs * vs + 2 if c.value == 3 else 1), 64), np.int16)
     rounds = ctypes.c_int()
     rc = lib.v5jemu_decode(_u8(buf), len(data), _u8(rgb), _u8(gray), coef.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)),
                            ctypes.byref(rounds))
@@ -130,14 +132,61 @@ def test_decoder_custom_tables_and_noise(emu):
         assert np.array_equal(out["rgb"], np.asarray(Image.open(buf).convert("RGB"))), kw
 
 
+@pytest.mark.parametrize("subsampling", [0, 1], ids=["444", "422"])
+def test_decoder_other_chroma_layouts(emu, subsampling):
+    """4:4:4 and 4:2:2 files (PIL subsampling=0 / 1): coefficients as the oracle's, pixels as Pillow's and OpenCV's."""
+    rng = np.random.default_rng(40 + subsampling)
+    sizes = [(1, 1), (7, 9), (8, 16), (16, 17), (33, 3), (2, 5), (40, 71), (64, 80), (90, 133), (5, 260)]
+    for i, (h, w) in enumerate(sizes):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if i % 2 else golden_frame({"spec": ["gen", i, 3], "h": h, "w": w})
+        for q in (95, 60):
+            buf = io.BytesIO()
+            Image.fromarray(rgb).save(buf, "JPEG", quality=q, subsampling=subsampling)
+            data = buf.getvalue()
+            out = emu_decode(emu, data)
+            ref = c_oracle.jpeg_decode(data, want_coef=True)
+            assert np.array_equal(out["coef"], ref["coef"]), (h, w, q)
+            assert np.array_equal(out["rgb"], np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))), (h, w, q)
+            assert np.array_equal(out["gray"], cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)), (h, w, q)
+
+
+def test_decoder_restart_intervals(emu):
+    """Files with restart markers (cv2 IMWRITE_JPEG_RST_INTERVAL, PIL restart_marker_blocks / _rows): every interval is decoded
+    from its own known state; all three chroma layouts and one-component files; intervals of 1 MCU up to longer than the file."""
+    rng = np.random.default_rng(77)
+    for i, (h, w) in enumerate([(40, 48), (1, 1), (17, 130), (64, 64), (100, 37), (33, 260)]):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if i % 2 else golden_frame({"spec": ["gen", i, 4], "h": h, "w": w})
+        for ri in (1, 3, 7, 1000):
+            ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, ri])
+            data = enc.tobytes()
+            out = emu_decode(emu, data)
+            ref = c_oracle.jpeg_decode(data, want_coef=True)
+            assert np.array_equal(out["coef"], ref["coef"]), (h, w, ri)
+            assert np.array_equal(out["rgb"][..., ::-1], cv2.imdecode(enc, cv2.IMREAD_COLOR)), (h, w, ri)
+            assert np.array_equal(out["gray"], cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE)), (h, w, ri)
+        for ss in (0, 1, 2):
+            buf = io.BytesIO()
+            Image.fromarray(rgb).save(buf, "JPEG", quality=75, subsampling=ss, restart_marker_blocks=2 + ss)
+            out = emu_decode(emu, buf.getvalue())
+            assert np.array_equal(out["rgb"], np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB"))), (h, w, ss)
+        ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(rgb[..., 1]), [cv2.IMWRITE_JPEG_RST_INTERVAL, 4])
+        assert np.array_equal(emu_decode(emu, enc.tobytes())["gray"], cv2.imdecode(enc, cv2.IMREAD_GRAYSCALE))
+    # a marker that has gone missing: refused, not decoded into something else
+    ok, enc = cv2.imencode(".jpg", golden_frame({"spec": ["gen", 1, 2], "h": 64, "w": 64}), [cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    data = enc.tobytes()
+    k = data.index(b"\xff\xd3", data.index(b"\xff\xda"))
+    with pytest.raises(ValueError):
+        emu_decode(emu, data[:k] + data[k + 2:])
+
+
 def test_unsupported_files_are_refused(emu):
     rgb = golden_frame({"spec": ["gen", 1, 2], "h": 40, "w": 40})
-    for kw in ({"subsampling": 0}, {"progressive": True}):
+    for kw in ({"progressive": True},):
         buf = io.BytesIO()
         Image.fromarray(rgb).save(buf, "JPEG", quality=80, **kw)
         with pytest.raises(ValueError):
             emu_decode(emu, buf.getvalue())
-    ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3])
+    ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411])
     with pytest.raises(ValueError):
         emu_decode(emu, enc.tobytes())
 
@@ -209,11 +258,11 @@ def test_parser_refuses_what_the_kernels_do_not_implement(emu):
     Image.fromarray(np.dstack([rgb, rgb[..., 0]]), "CMYK").save(cmyk, "JPEG", quality=85)
     with pytest.raises(ValueError):
         emu_decode(emu, cmyk.getvalue())
-    for kw in ({"subsampling": 1}, {"subsampling": 0}):                  # 4:2:2, 4:4:4
-        b2 = io.BytesIO()
-        Image.fromarray(rgb).save(b2, "JPEG", quality=85, **kw)
+    for factor in (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440):   # 4x1 and 1x2 luma sampling
+        ok, enc = cv2.imencode(".jpg", rgb, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, factor])
+        assert ok
         with pytest.raises(ValueError):
-            emu_decode(emu, b2.getvalue())
+            emu_decode(emu, enc.tobytes())
     for bad in (b"", b"\xff\xd8", data[:20], b"\x89PNG\r\n\x1a\n" + bytes(32), data[:i + 4]):
         with pytest.raises(ValueError):
             emu_decode(emu, bad)

@@ -32,13 +32,13 @@ def emu(request):
     lib.v5emu_analyze.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_void_p, u8p, ctypes.c_int]
 
-    def run(frames, q, seg=0):
+    def run(frames, q, seg=0, want_residual=True):
         frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
         recs = np.zeros(n, RECORD_DTYPE)
-        res = np.zeros((n, h, w, 3), np.uint8)
+        res = np.zeros((n, h, w, 3), np.uint8) if want_residual else None
         rc = lib.v5emu_analyze(frames.ctypes.data_as(u8p), n, h, w, h * w * 3, w * 3, q,
-                               recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p), seg)
+                               recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p) if want_residual else None, seg)
         assert rc == 0
         return recs, res
 
@@ -61,6 +61,22 @@ def test_emulated_kernel_vs_oracle(emu, hw, seg):
             recs, res = emu(frame[None], q, seg)
             assert np.array_equal(res[0], o["residual"])
             assert recs[0].tobytes() == o["record"].tobytes()
+
+
+@pytest.mark.parametrize("hw", [(1, 16), (16, 16), (17, 32), (40, 48), (33, 496), (100, 1008), (272, 512), (9, 976)])
+@pytest.mark.parametrize("seg", [0, 2])
+def test_emulated_fast_instantiation_vs_oracle(emu, hw, seg):
+    """Statistics-only calls on widths that are a multiple of 16 take the kernel instantiation without the horizontal edge
+    predicates (csrc/v5ela_host.h fast_path_ok); same records as the oracle and as the general instantiation."""
+    h, w = hw
+    rng = np.random.default_rng(h * 11 + w)
+    for q in (90, 40):
+        for frame in (gen_frame(5, h, w, 2), rng.integers(0, 256, (h, w, 3), dtype=np.uint8)):
+            o = c_oracle.analyze_frame(frame, q)
+            recs, _ = emu(frame[None], q, seg, want_residual=False)
+            assert recs[0].tobytes() == o["record"].tobytes()
+            general, _ = emu(frame[None], q, seg)
+            assert general[0].tobytes() == recs[0].tobytes()
 
 
 def test_emulated_kernel_vs_reference_goldens(emu):

@@ -134,13 +134,14 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // Byte-lane selector constants of the residual stage. As literals ptxas rematerialises each one with a UMOV in front of
 // (almost) every use — 3 % of the kernel's issue slots; as a table in constant memory four of them arrive with one
 // uniform 128-bit load (LDCU.128). Index = 4 * family + byte lane.
-enum { SEL_ONE = 0, SEL_THREE = 4, SEL_FOUR = 8, SEL_HALF = 12, SEL_LAP = 16 };   // SEL_HALF: 0x8000 (rounding of the colour conversion)
+enum { SEL_ONE = 0, SEL_THREE = 4, SEL_FOUR = 8, SEL_HALF = 12, SEL_TRI = 13, SEL_LAP = 16 };   // SEL_HALF: 0x8000 (rounding of the colour
+                                                                                     // conversion); SEL_TRI: the two triangle kernels
 #ifndef V5_CONST_SEL
 #define V5_CONST_SEL 1
 #endif
 #if defined(__CUDACC__) && V5_CONST_SEL
 static __constant__ uint32_t kSelTab[20] = {1u,       1u << 8,    1u << 16,    1u << 24,  3u,     3u << 8, 3u << 16, 3u << 24, 4u, 4u << 8,
-                                            4u << 16, 4u << 24,   0x8000u,     0u,        0u,      0u,
+                                            4u << 16, 4u << 24,   0x8000u,     0x03090103u, 0x01030309u, 0u,
                                             0x01fc01u, 0x01fc0100u, 0xfc010000u, 0x000001fcu};
 #endif
 #if defined(__CUDA_ARCH__) && V5_CONST_SEL
@@ -149,7 +150,7 @@ V5_DEV uint32_t sel_const(int i) { return kSelTab[i]; }
 V5_HOSTDEV constexpr uint32_t sel_const(int i)
 {
     return i < 12 ? (i < 4 ? 1u : (i < 8 ? 3u : 4u)) << (8 * (i & 3))
-                  : (i < 16 ? (i == 12 ? 0x8000u : 0u)
+                  : (i < 16 ? (i == 12 ? 0x8000u : (i == 13 ? 0x03090103u : (i == 14 ? 0x01030309u : 0u)))
                             : (i == 16 ? 0x01fc01u : (i == 17 ? 0x01fc0100u : (i == 18 ? 0xfc010000u : 0x000001fcu))));
 }
 #endif
@@ -601,9 +602,10 @@ struct BlockTask {
     bool active;
 };
 
-// FAST (here and below): the width is a multiple of 16 and no residual map is wanted — every 8-pixel unit and every block
-// of a strip lies inside the image horizontally, so the per-unit edge predicates and the residual store compile away. The
-// host picks the instantiation (fast_path_ok); both are the same arithmetic.
+// FAST (here and below): the width is a multiple of 16, the frames are 16-byte aligned and no residual map is wanted — every
+// 8-pixel unit and every block of a strip lies inside the image horizontally and every band arrives by bulk copy alone, so
+// the per-unit edge predicates, the residual store and the fall-back loads compile away. The host picks the instantiation
+// (fast_path_ok); both are the same arithmetic.
 template <bool FAST>
 V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, int r, bool want_y)
 {
@@ -758,6 +760,34 @@ V5_DEV void upsample8(const uint8_t *lc, const uint8_t *ln, int gcx0, int wc1, b
     }
 }
 
+// The same filter for the width-multiple-of-16 instantiation (Wc is a multiple of 8 and >= 8: always "fancy", the right image
+// edge can only fall right after a unit). Both filter steps are folded into ONE dot product per output sample: with
+// W = bytes [c_j, n_j, c_j+1, n_j+1] (c: nearer chroma row, n: further one),
+//   out[2j]   = (3 (3 c_j + n_j) + (3 c_j-1 + n_j-1) + 8) >> 4 = (W_j-1 . [3, 1, 9, 3] + 8) >> 4
+//   out[2j+1] = (3 (3 c_j + n_j) + (3 c_j+1 + n_j+1) + 7) >> 4 = (W_j   . [9, 3, 3, 1] + 7) >> 4
+// i.e. 9 PRMT + 8 dp4a + 8 shifts per component instead of 12 dp4a + 8 multiply-adds + 8 adds + 8 shifts.
+V5_DEV void upsample8_fast(const uint8_t *lc, const uint8_t *ln, bool left_edge, bool right_edge, int out[8])
+{
+    const uint32_t c0 = *reinterpret_cast<const uint32_t *>(lc - 4), n0 = *reinterpret_cast<const uint32_t *>(ln - 4);
+    const uint32_t c1 = *reinterpret_cast<const uint32_t *>(lc), n1 = *reinterpret_cast<const uint32_t *>(ln);
+    const uint32_t c2 = *reinterpret_cast<const uint32_t *>(lc + 4), n2 = *reinterpret_cast<const uint32_t *>(ln + 4);
+    // columns -1 .. 2 and 1 .. 4 as words; at an image edge the missing neighbour is the edge column itself
+    const uint32_t cs = left_edge ? prmt(c1, 0u, 0x2100u) : prmt(c0, c1, 0x6543u), ns = left_edge ? prmt(n1, 0u, 0x2100u) : prmt(n0, n1, 0x6543u);
+    const uint32_t ce = right_edge ? prmt(c1, 0u, 0x3321u) : prmt(c1, c2, 0x4321u), ne = right_edge ? prmt(n1, 0u, 0x3321u) : prmt(n1, n2, 0x4321u);
+    uint32_t w[5];
+    w[0] = prmt(cs, ns, 0x5140u);                               // columns -1, 0
+    w[1] = prmt(c1, n1, 0x5140u);                               // 0, 1
+    w[2] = prmt(c1, n1, 0x6251u);                               // 1, 2
+    w[3] = prmt(c1, n1, 0x7362u);                               // 2, 3
+    w[4] = prmt(ce, ne, 0x7362u);                               // 3, 4
+    const uint32_t ke = sel_const(SEL_TRI), ko = sel_const(SEL_TRI + 1);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out[2 * j] = dp4a_us(w[j], ke, 8 - 2048) >> 4;
+        out[2 * j + 1] = dp4a_us(w[j + 1], ko, 7 - 2048) >> 4;
+    }
+}
+
 // 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
 template <bool FAST>
 V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
@@ -776,8 +806,13 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const int ccol = col >> 1, gcx0 = gx0 >> 1;
     const bool fancy = wc1 > 1;
     int cb[8], cr[8];
-    upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
-    upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    if (FAST) {
+        upsample8_fast(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cb);
+        upsample8_fast(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cr);
+    } else {
+        upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
+        upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    }
 
     // ---- reconstruct (A.8), residual (A.9), histogram
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
@@ -864,7 +899,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     if (y == p.h - 1) ld = p.h > 1 ? l - 1 : l;
     const uint8_t *yc = &S.yorig[ring16(r, l)][col];
     const uint8_t *yu = &S.yorig[ring16(r, lu)][col], *yd2 = &S.yorig[ring16(r, ld)][col];
-    const int wide = p.w > 1;
+    const int wide = FAST || p.w > 1;
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
     {
         // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per

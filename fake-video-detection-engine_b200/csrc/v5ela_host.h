@@ -71,13 +71,14 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
 }
 
 // Which instantiation of the fused kernel a call takes (v5ela_device.cuh, FAST): widths that are a multiple of the MCU
-// width (1280, 1920, 3840, ...) without a residual map — the statistics-only keyframe batches the benchmark drives.
+// width (1280, 1920, 3840, ...), 16-byte aligned, without a residual map — the statistics-only keyframe batches the
+// benchmark drives.
 inline bool fast_path_ok(const KParams &p)
 {
 #ifdef V5_NO_FAST_PATH
     return false;
 #else
-    return p.w % 16 == 0 && p.residual == nullptr;
+    return p.w % 16 == 0 && p.residual == nullptr && p.vec_ok;
 #endif
 }
 

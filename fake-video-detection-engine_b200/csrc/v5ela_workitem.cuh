@@ -125,8 +125,9 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 
     // Bands r0-1 and r1 only contribute decoded chroma / original luma to the rows next to them.
     const int r_first = g.r0 > 0 ? g.r0 - 1 : 0;
-    const bool bulk = use_bulk(p, g);
-    const bool rest = load_rest_needed(p, g, bulk);
+    // FAST: 16-byte aligned frames whose strips are whole multiples of 48 bytes — the bulk copies cover every band completely
+    const bool bulk = FAST || use_bulk(p, g);
+    const bool rest = !FAST && load_rest_needed(p, g, bulk);
     V5_FOR_THREADS(if (bulk) stage_prefetch(tid, S, p, g, r_first))
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;

@@ -23,7 +23,7 @@ static_assert(sizeof(v5::Smem) <= (227 * 1024) / v5::MIN_CTAS - 1024, "MIN_CTAS 
 
 namespace v5 {
 
-template <bool FAST>
+template <bool FAST, bool TEXHIST>
 __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_co
         __syncthreads();
         const int work = (int)S.next_work;
         if (work >= total_work) break;
-        process_work_item<FAST>(S, p, work, acc_store);          // ends with a CTA barrier: next_work may be rewritten
+        process_work_item<FAST, TEXHIST>(S, p, work, acc_store);          // ends with a CTA barrier: next_work may be rewritten
     }
 }
 
@@ -178,9 +178,11 @@ int v5ela_create(int device, v5ela_handle **out)
     h->sm_count = prop.multiProcessorCount;
     v5::quant_tables(h->quality, h->luma, h->chroma);
     DeviceGuard guard(device);
-    if (cudaFuncSetAttribute(v5::ela_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(v5::ela_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(v5::Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(v5::ela_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(v5::ela_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(v5::Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(v5::ela_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(v5::Smem)) != cudaSuccess) {
         delete h;
         return V5ELA_ERR_CUDA;
@@ -247,6 +249,12 @@ int v5ela_get_quant_tables(const v5ela_handle *h, uint16_t luma_host[64], uint16
 int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width, int64_t frame_stride_bytes,
                   int64_t row_stride_bytes, void *d_records, uint8_t *d_residual, void *cuda_stream)
 {
+    return v5ela_analyze_ex(h, d_rgb, n, height, width, frame_stride_bytes, row_stride_bytes, d_records, d_residual, nullptr, cuda_stream);
+}
+
+int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width, int64_t frame_stride_bytes,
+                     int64_t row_stride_bytes, void *d_records, uint8_t *d_residual, uint32_t *d_tex_hist, void *cuda_stream)
+{
     if (!h) return V5ELA_ERR_INVALID;
     if (n == 0) return V5ELA_OK;
     v5::KParams p;
@@ -254,6 +262,7 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
                         static_cast<v5ela_record *>(d_records), d_residual, h->quality, h->seg_rows,
                         2 * h->sm_count * h->ctas_per_sm) != 0)
         return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: bad pointer, size or stride%s");
+    p.tex_hist = d_tex_hist;
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const long long total = (long long)n * p.n_strips * p.n_segs;
@@ -262,12 +271,14 @@ int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int 
     p.ticket = h->d_ticket;
     V5_CUDA(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), st));
     V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
+    if (d_tex_hist) V5_CUDA(h, cudaMemsetAsync(d_tex_hist, 0, sizeof(uint32_t) * 256 * (size_t)n, st));
     const int max_ctas = h->sm_count * h->ctas_per_sm;
     const int grid = total < max_ctas ? (int)total : max_ctas;
     const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
     if (prof) V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used], st));
-    if (v5::fast_path_ok(p)) v5::ela_fused_kernel<true><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
-    else v5::ela_fused_kernel<false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    if (p.tex_hist) v5::ela_fused_kernel<false, true><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    else if (v5::fast_path_ok(p)) v5::ela_fused_kernel<true, false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
+    else v5::ela_fused_kernel<false, false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
     V5_CUDA(h, cudaGetLastError());
     if (prof) {
         V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used + 1], st));

@@ -66,6 +66,7 @@ struct KParams {
     int64_t row_stride;
     v5ela_record *records;
     uint8_t *residual;          // optional
+    uint32_t *tex_hist;         // optional: n x 256 counters of min(|Laplacian|, 255)
     int n, h, w;
     int mw, mh;                 // MCU columns / rows of the padded frame
     int n_strips, n_segs;       // work decomposition: strips x vertical segments per frame
@@ -306,6 +307,7 @@ struct alignas(16) Smem {
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
     uint8_t cdec[2][16][C_PITCH];       // decoded Cb/Cr; band r chroma line j at [8*(r&1) + j]
     uint32_t hist[3][256];
+    uint32_t tex_hist[256];             // histogram of min(|Laplacian|, 255); only the TEXHIST instantiation touches it
     unsigned long long tex_sumabs, tex_sumsq;
     unsigned long long full_bar[2];     // mbarriers: "band has landed in rgb[b]"
     uint32_t tex_maxabs;
@@ -789,7 +791,9 @@ V5_DEV void upsample8_fast(const uint8_t *lc, const uint8_t *ln, bool left_edge,
 }
 
 // 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
-template <bool FAST>
+// TEXHIST: the optional tex_hist[256] output of the record table is wanted — one more shared-memory
+// increment per pixel; an instantiation of its own so that calls without it pay nothing.
+template <bool FAST, bool TEXHIST>
 V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
 {
     const int y = 16 * r + l;                                   // global pixel row
@@ -930,6 +934,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
                 sabs += (uint32_t)lap;
                 ssq += (uint32_t)(lap * lap);
                 mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
+                if (TEXHIST) smem_inc(&S.tex_hist[lap < 255 ? lap : 255]);
             }
         }
         if (!FAST && edge >= 0) {
@@ -940,6 +945,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
             sabs += (uint32_t)lap;
             ssq += (uint32_t)(lap * lap);
             mx = (uint32_t)lap > mx ? (uint32_t)lap : mx;
+            if (TEXHIST) smem_inc(&S.tex_hist[lap < 255 ? lap : 255]);
         }
     }
     acc.tex_sumabs += sabs;
@@ -948,7 +954,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
 }
 
 // Iteration r finishes pixel rows 16r-1 .. 16r+14 (clipped to the segment and the image).
-template <bool FAST>
+template <bool FAST, bool TEXHIST>
 V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r)
 {
     const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
@@ -958,7 +964,7 @@ V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, Thr
         const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
         if (y < ylo || y >= yhi || (!FAST && 16 * g.m0 + 8 * ox >= p.w)) continue;
-        residual_unit<FAST>(S, p, g, acc, r, l, ox);
+        residual_unit<FAST, TEXHIST>(S, p, g, acc, r, l, ox);
     }
 }
 

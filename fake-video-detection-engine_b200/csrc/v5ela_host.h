@@ -78,7 +78,7 @@ inline bool fast_path_ok(const KParams &p)
 #ifdef V5_NO_FAST_PATH
     return false;
 #else
-    return p.w % 16 == 0 && p.residual == nullptr && p.vec_ok;
+    return p.w % 16 == 0 && p.residual == nullptr && p.tex_hist == nullptr && p.vec_ok;
 #endif
 }
 

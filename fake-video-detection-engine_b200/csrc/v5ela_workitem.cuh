@@ -69,12 +69,17 @@ V5_DEV void flush_partials(int tid, Smem &S, ThreadAcc &acc)
         atomicMax(&S.tex_maxabs, mx);
     }
 }
-V5_DEV void flush_global(int tid, Smem &S, v5ela_record *rec)
+V5_DEV void flush_global(int tid, Smem &S, v5ela_record *rec, uint32_t *tex_hist)
 {
     for (int i = tid; i < 3 * 256; i += NT) {
         const uint32_t c = (&S.hist[0][0])[i];
         if (c) atomicAdd(&rec->ela_hist[0][0] + i, c);
     }
+    if (tex_hist)
+        for (int i = tid; i < 256; i += NT) {
+            const uint32_t c = S.tex_hist[i];
+            if (c) atomicAdd(tex_hist + i, c);
+        }
     if (tid == 0) {
         atomicAdd(reinterpret_cast<unsigned long long *>(&rec->tex_sumabs), S.tex_sumabs);
         atomicAdd(reinterpret_cast<unsigned long long *>(&rec->tex_sumsq), S.tex_sumsq);
@@ -88,9 +93,11 @@ inline void flush_partials(int, Smem &S, ThreadAcc &acc)
     S.tex_sumabs += acc.tex_sumabs;
     if (acc.tex_maxabs > S.tex_maxabs) S.tex_maxabs = acc.tex_maxabs;
 }
-inline void flush_global(int tid, Smem &S, v5ela_record *rec)
+inline void flush_global(int tid, Smem &S, v5ela_record *rec, uint32_t *tex_hist)
 {
     for (int i = tid; i < 3 * 256; i += NT) (&rec->ela_hist[0][0])[i] += (&S.hist[0][0])[i];
+    if (tex_hist)
+        for (int i = tid; i < 256; i += NT) tex_hist[i] += S.tex_hist[i];
     if (tid == 0) {
         rec->tex_sumabs += S.tex_sumabs;
         rec->tex_sumsq += S.tex_sumsq;
@@ -99,7 +106,7 @@ inline void flush_global(int tid, Smem &S, v5ela_record *rec)
 }
 #endif
 
-template <bool FAST>
+template <bool FAST, bool TEXHIST>
 V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *acc_store)
 {
     Geo g;
@@ -108,6 +115,8 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 
     V5_FOR_THREADS({
         for (int i = tid; i < 3 * 256; i += NT) (&S.hist[0][0])[i] = 0;
+        if (TEXHIST)
+            for (int i = tid; i < 256; i += NT) S.tex_hist[i] = 0;
         for (int i = tid; i < 2 * 64; i += NT) {
             const QuantTab &q = p.q[i >> 6];
             const int k = i & 63;
@@ -163,11 +172,11 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             }
             V5_FOR_THREADS((void)0)
         }
-        V5_FOR_THREADS(stage_residual<FAST>(tid, S, p, g, acc, r))
+        V5_FOR_THREADS(stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
     }
 
     V5_FOR_THREADS(flush_partials(tid, S, acc))
-    V5_FOR_THREADS(flush_global(tid, S, p.records + frame))
+    V5_FOR_THREADS(flush_global(tid, S, p.records + frame, TEXHIST ? p.tex_hist + (int64_t)frame * 256 : nullptr))
 }
 
 }  // namespace v5

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("V5ELA_LIB") or os.path.join(_HERE, "libv5ela.so")
 # Every symbol include/v5ela.h declares; tests assert the built library exports exactly these.
 EXPORTS = (
     "v5ela_abi_version", "v5ela_record_bytes", "v5ela_status_string", "v5ela_create", "v5ela_destroy",
-    "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze",
+    "v5ela_last_error", "v5ela_set_quality", "v5ela_get_quality", "v5ela_get_quant_tables", "v5ela_analyze", "v5ela_analyze_ex",
     "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
     "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host", "v5ela_jpeg_bound", "v5ela_jpeg_encode",
     "v5ela_jpeg_encode_host", "v5ela_jpeg_info", "v5ela_jpeg_info_batch", "v5ela_jpeg_decode", "v5ela_jpeg_decode_host",
@@ -54,6 +54,7 @@ def load() -> ctypes.CDLL:
     lib.v5ela_get_quality.argtypes = [vp]
     lib.v5ela_get_quant_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16)]
     lib.v5ela_analyze.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
+    lib.v5ela_analyze_ex.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp]
     lib.v5ela_enhance.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.v5ela_reduce_records.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
@@ -117,9 +118,13 @@ class Handle:
         return lu.reshape(8, 8), ch.reshape(8, 8)
 
     def analyze(self, d_rgb: int, n: int, h: int, w: int, frame_stride: int, row_stride: int, d_records: int,
-                d_residual: int | None, stream: int | None):
-        self._check(self._lib.v5ela_analyze(self._h, d_rgb, n, h, w, frame_stride, row_stride, d_records,
-                                            d_residual or None, stream or None))
+                d_residual: int | None, stream: int | None, d_tex_hist: int | None = None):
+        if d_tex_hist:
+            self._check(self._lib.v5ela_analyze_ex(self._h, d_rgb, n, h, w, frame_stride, row_stride, d_records,
+                                                   d_residual or None, d_tex_hist, stream or None))
+        else:
+            self._check(self._lib.v5ela_analyze(self._h, d_rgb, n, h, w, frame_stride, row_stride, d_records,
+                                                d_residual or None, stream or None))
 
     def enhance(self, d_residual: int, d_records: int, n: int, h: int, w: int, d_enhanced: int, stream: int | None):
         self._check(self._lib.v5ela_enhance(self._h, d_residual, d_records, n, h, w, d_enhanced, stream or None))

@@ -25,13 +25,14 @@ def get_handle(device_index: int) -> "_abi.Handle":
 
 
 def analyze_batch(frames, quality: int = 90, want_residual: bool = False, want_enhanced: bool = False,
-                  records_out=None, residual_out=None, handle=None):
+                  records_out=None, residual_out=None, handle=None, want_tex_hist: bool = False):
     """Run the fused ELA + texture kernel over a batch of RGB frames.
 
     frames : torch.uint8 CUDA tensor, shape (N, H, W, 3), innermost two dims dense (row/frame strides may be padded).
     Returns a dict: ``records`` uint8 (N, 3144) on the same device (view with ``records.as_records`` on the host),
     and, when asked, ``residual`` (= the reference's ``diff``, v5_texture_ela.py:70) and ``enhanced``
-    (= ``ImageEnhance.Brightness(diff).enhance(scale)``, v5…:78), both uint8 (N, H, W, 3).
+    (= ``ImageEnhance.Brightness(diff).enhance(scale)``, v5…:78), both uint8 (N, H, W, 3); with ``want_tex_hist`` also
+    ``tex_hist`` int32 (N, 256), the histogram of min(|Laplacian of the luma|, 255) (optional field).
     Asynchronous on torch's current stream.
     """
     import torch
@@ -54,6 +55,9 @@ def analyze_batch(frames, quality: int = 90, want_residual: bool = False, want_e
     residual = None
     if want_residual or want_enhanced:
         residual = residual_out if residual_out is not None else torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    tex_hist = torch.zeros((n, 256), dtype=torch.int32, device=dev) if want_tex_hist else None
+    if tex_hist is not None:
+        out["tex_hist"] = tex_hist
     if n == 0 or h == 0 or w == 0:
         if residual is not None:
             out["residual"] = residual
@@ -62,7 +66,8 @@ def analyze_batch(frames, quality: int = 90, want_residual: bool = False, want_e
         return out
     stream = torch.cuda.current_stream(dev).cuda_stream
     hd.analyze(frames.data_ptr(), n, h, w, frames.stride(0), frames.stride(1), records.data_ptr(),
-               residual.data_ptr() if residual is not None else None, stream)
+               residual.data_ptr() if residual is not None else None, stream,
+               tex_hist.data_ptr() if tex_hist is not None else None)
     if residual is not None:
         out["residual"] = residual
     if want_enhanced:

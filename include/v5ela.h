@@ -100,6 +100,17 @@ V5ELA_API int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int he
                   void *d_records, uint8_t *d_residual, void *cuda_stream);
 
 /*
+ * The same call with the record table's optional texture histogram (`tex_hist[256]`):
+ *   d_tex_hist : optional (may be NULL): n x 256 uint32, overwritten with
+ *                np.bincount(np.minimum(np.abs(cv2.Laplacian(Y, cv2.CV_16S, ksize=1)), 255), minlength=256)
+ *                of each frame's luma (the Laplacian behind tex_sumabs / tex_sumsq / tex_maxabs).
+ * Asking for it selects a kernel instantiation with one more shared-memory increment per pixel; NULL is v5ela_analyze.
+ */
+V5ELA_API int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width,
+                     int64_t frame_stride_bytes, int64_t row_stride_bytes,
+                     void *d_records, uint8_t *d_residual, uint32_t *d_tex_hist, void *cuda_stream);
+
+/*
  * Brightness enhancement of the residual map: `ImageEnhance.Brightness(diff).enhance(255.0 / max_diff)`
  * (v5_texture_ela.py:74-78) == u8(trunc(f32(x) * f32(scale))) clipped, with max_diff read per frame from the records
  * produced by v5ela_analyze on the same stream (0 -> 1 fix applied). d_enhanced may alias d_residual.

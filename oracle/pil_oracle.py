@@ -87,6 +87,14 @@ def texture_stats(rgb: np.ndarray):
     return int(a.sum()), int((lap * lap).sum()), int(a.max())
 
 
+def texture_hist(rgb: np.ndarray):
+    """§8a optional field tex_hist[256]: bincount(min(|cv2.Laplacian(Y, CV_16S, ksize=1)|, 255))."""
+    import cv2
+
+    lap = cv2.Laplacian(luma(rgb), cv2.CV_16S, ksize=1).astype(np.int64)
+    return np.bincount(np.minimum(np.abs(lap), 255).ravel(), minlength=256).astype(np.uint32)
+
+
 def record(rgb: np.ndarray, quality: int = 90, with_residual: bool = False):
     """Full V5F v1 record for one frame, as a 0-d structured array (same bytes as the C-ABI record)."""
     d, _, _ = ela_residual(rgb, quality)

@@ -12,18 +12,21 @@
 #include "v5ela_host.h"
 
 extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t frame_stride, int64_t row_stride,
-                             int quality, v5ela_record *records, uint8_t *residual, int seg_rows)
+                             int quality, v5ela_record *records, uint8_t *residual, int seg_rows, uint32_t *tex_hist)
 {
     v5::KParams p;
     if (v5::fill_params(p, rgb, n, h, w, frame_stride, row_stride, records, residual, quality, seg_rows) != 0) return -1;
+    p.tex_hist = tex_hist;
     memset(records, 0, sizeof(v5ela_record) * (size_t)n);
+    if (tex_hist) memset(tex_hist, 0, sizeof(uint32_t) * 256 * (size_t)n);
     v5::Smem *S = (v5::Smem *)aligned_alloc(16, sizeof(v5::Smem));
     memset(S, 0xA5, sizeof(v5::Smem));                       // poison: uninitialised reads must not matter
     std::vector<v5::ThreadAcc> acc(v5::NT);
     const int total = n * p.n_strips * p.n_segs;
     for (int work = 0; work < total; work++) {
-        if (v5::fast_path_ok(p)) v5::process_work_item<true>(*S, p, work, acc.data());       // the choice the C ABI makes
-        else v5::process_work_item<false>(*S, p, work, acc.data());
+        if (p.tex_hist) v5::process_work_item<false, true>(*S, p, work, acc.data());         // the choice the C ABI makes
+        else if (v5::fast_path_ok(p)) v5::process_work_item<true, false>(*S, p, work, acc.data());
+        else v5::process_work_item<false, false>(*S, p, work, acc.data());
     }
     for (int i = 0; i < n; i++) v5::finalize_record(records[i]);
     free(S);

@@ -296,3 +296,27 @@ def test_two_host_threads_with_their_own_handles():
     for th in threads:
         th.join()
     assert errors == []
+
+
+def test_texture_histogram_optional_output():
+    """tex_hist[256] (SURVEY.md §8a, optional): per frame bincount(min(|cv2.Laplacian(Y)|, 255)) through v5ela_analyze_ex;
+    records identical to the call without it (which takes another kernel instantiation); ragged sizes, full size, a batch."""
+    import torch
+    from oracle import pil_oracle
+    from v5ela import analyze_batch
+    from v5ela.synth import gen_frame
+
+    rng = np.random.default_rng(9)
+    for h, w in [(1, 1), (9, 1), (17, 33), (64, 64), (270, 481), (1080, 1920)]:
+        frames = np.stack([gen_frame(0, h, w, 4), rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
+                           np.where(rng.integers(0, 2, (h, w, 1)) > 0, 255, 0).astype(np.uint8).repeat(3, axis=2)])
+        t = torch.from_numpy(frames).cuda()
+        out = analyze_batch(t, want_tex_hist=True)
+        plain = analyze_batch(t)
+        with_res = analyze_batch(t, want_tex_hist=True, want_residual=True)
+        th = out["tex_hist"].cpu().numpy().view(np.uint32)
+        for i in range(3):
+            assert np.array_equal(th[i], pil_oracle.texture_hist(frames[i])), (h, w, i)
+        assert int(th.sum()) == 3 * h * w
+        assert torch.equal(out["records"], plain["records"]) and torch.equal(with_res["records"], plain["records"])
+        assert torch.equal(with_res["tex_hist"], out["tex_hist"])

@@ -30,15 +30,16 @@ def emu(request):
     lib = ctypes.CDLL(so)
     u8p = ctypes.POINTER(ctypes.c_uint8)
     lib.v5emu_analyze.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
-                                  ctypes.c_int, ctypes.c_void_p, u8p, ctypes.c_int]
+                                  ctypes.c_int, ctypes.c_void_p, u8p, ctypes.c_int, ctypes.c_void_p]
 
-    def run(frames, q, seg=0, want_residual=True):
+    def run(frames, q, seg=0, want_residual=True, tex_hist=None):
         frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
         recs = np.zeros(n, RECORD_DTYPE)
         res = np.zeros((n, h, w, 3), np.uint8) if want_residual else None
         rc = lib.v5emu_analyze(frames.ctypes.data_as(u8p), n, h, w, h * w * 3, w * 3, q,
-                               recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p) if want_residual else None, seg)
+                               recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p) if want_residual else None, seg,
+                               tex_hist.ctypes.data_as(ctypes.c_void_p) if tex_hist is not None else None)
         assert rc == 0
         return recs, res
 
@@ -77,6 +78,27 @@ def test_emulated_fast_instantiation_vs_oracle(emu, hw, seg):
             assert recs[0].tobytes() == o["record"].tobytes()
             general, _ = emu(frame[None], q, seg)
             assert general[0].tobytes() == recs[0].tobytes()
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (1, 7), (9, 1), (16, 16), (17, 33), (40, 48), (33, 497), (100, 1000)])
+def test_emulated_texture_histogram(emu, hw):
+    """The optional tex_hist[256] output against OpenCV's Laplacian of Pillow's luma; the record and the
+    residual map of the same call stay what they are without it."""
+    from oracle import pil_oracle
+
+    h, w = hw
+    rng = np.random.default_rng(h * 13 + w)
+    for frame in (gen_frame(2, h, w, 3), rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
+                  np.where(rng.integers(0, 2, (h, w, 1)) > 0, 255, 0).astype(np.uint8).repeat(3, axis=2)):   # saturates the last bin
+        for want_residual in (False, True):
+            th = np.full((1, 256), 0xA5A5A5A5, np.uint32)
+            recs, res = emu(frame[None], 90, 0, want_residual=want_residual, tex_hist=th)
+            assert np.array_equal(th[0], pil_oracle.texture_hist(frame))
+            assert int(th[0].sum()) == h * w
+            o = c_oracle.analyze_frame(frame, 90)
+            assert recs[0].tobytes() == o["record"].tobytes()
+            if want_residual:
+                assert np.array_equal(res[0], o["residual"])
 
 
 def test_emulated_kernel_vs_reference_goldens(emu):

@@ -397,8 +397,10 @@ def run_native_arm(args):
                          "traffic": load_ncu_traffic(), "kernel": "v5::ela_fused_kernel", "kernel_ms": kernel_ms,
                          "kernel_launches_timed": int(fused_n), "bytes_per_launch": n_local * BYTES_PER_FRAME,
                          "peak_source": peak_src,
-                         "note": "integer-issue bound, not HBM bound: ~138 exact int32 thread-instructions per pixel "
-                                 "(DESIGN.md 4.4); int_issue = ncu figures of the committed profile",
+                         "note": "integer-issue bound, not HBM bound: ~%d exact int32 thread-instructions per pixel "
+                                 "(DESIGN.md 4.4); int_issue = ncu figures of the committed profile"
+                                 % round(32 * ((load_issue_stats() or {}).get("warp_instructions_per_pixel") or 3.83)),
+                         "kernel_instantiation": "ela_fused_kernel<FAST=true, TEXHIST=false> (width % 16 == 0, records only)",
                          "int_issue": load_issue_stats()},
         }
         if files_leg is not None:

@@ -2,6 +2,9 @@
 usage: python profiles/ncu_by_function.py <rep.ncu-rep> <libv5ela.so> [pixels_per_launch]"""
 import bisect, collections, csv, io, os, re, subprocess, sys, tempfile
 
+# which instantiation of the fused kernel the capture holds (mangled-name fragment): <FAST=1, TEXHIST=0> by default
+KERNEL = os.environ.get("V5_NCU_KERNEL", "ela_fused_kernelILb1ELb0")
+
 def line_map(so):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
@@ -10,7 +13,7 @@ def line_map(so):
     m, cur, infn = {}, None, False
     for ln in dis.splitlines():
         if ln.startswith(".text."):
-            infn = "ela_fused" in ln
+            infn = KERNEL in ln
         if not infn:
             continue
         mm = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)

@@ -1,6 +1,9 @@
 """Executed warp-instructions per source line (ncu source page joined with nvdisasm line info).
 usage: python profiles/ncu_by_line.py rep so file.cuh first_line last_line"""
 import collections, csv, io, os, re, subprocess, sys
+
+# which instantiation of the fused kernel the capture holds (mangled-name fragment): <FAST=1, TEXHIST=0> by default
+KERNEL = os.environ.get("V5_NCU_KERNEL", "ela_fused_kernelILb1ELb0")
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from ncu_by_function import line_map
 

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_co
     if (threadIdx.x == 0) {
         mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[0]), 1);
         mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[1]), 1);
+        mbar_init(reinterpret_cast<uint64_t *>(&S.done_bar), NT);
         mbar_init_fence();
     }
     __syncthreads();

@@ -233,6 +233,10 @@ V5_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+V5_DEV void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 V5_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -251,6 +255,7 @@ inline void mbar_init_fence() {}
 inline void async_proxy_fence() {}
 inline void mbar_expect_tx(uint64_t *, uint32_t) {}
 inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+inline void mbar_arrive(uint64_t *) {}
 inline void mbar_wait(uint64_t *, uint32_t) {}
 #endif
 
@@ -310,6 +315,8 @@ struct alignas(16) Smem {
     uint32_t tex_hist[256];             // histogram of min(|Laplacian|, 255); only the TEXHIST instantiation touches it
     unsigned long long tex_sumabs, tex_sumsq;
     unsigned long long full_bar[2];     // mbarriers: "band has landed in rgb[b]"
+    unsigned long long done_bar;        // mbarrier (count NT): "every thread has finished the residual stage of the band before"
+    unsigned long long pad2_;
     uint32_t tex_maxabs;
     uint32_t next_work;                 // ticket drawn by thread 0 for the CTA's next work item
     uint32_t pad_[2];
@@ -329,7 +336,7 @@ struct ThreadAcc {              // per-thread state that lives across barriers (
     unsigned long long tex_sumsq;
     uint32_t tex_sumabs;
     uint32_t tex_maxabs;
-    uint32_t phase;             // bit b: parity of the next wait on full_bar[b] (persists across work items)
+    uint32_t phase;             // bit b: parity of the next wait on full_bar[b], bit 2: on done_bar (persist across work items)
     int col[16];                // block stage: two columns between the two halves of the column sub-stage
 };
 
@@ -486,14 +493,26 @@ V5_DEV void convert8x2(const uint8_t *la, const uint8_t *lb, U2 &y0, U2 &y1, uin
     }
 }
 
-V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int r)
+// `defer`: the residual stage of band r-1 ended with an arrive on done_bar instead of a CTA barrier (split barrier: a thread
+// that is done early starts converting while others still read the shared buffers this stage overwrites — the luma ring lines
+// of band r-2, the carried RGB line, and, through the bulk copy of band r+1, the other RGB buffer). Everything up to a
+// unit's stores only reads band r and computes, so the wait for the stragglers sits in front of the first store.
+V5_DEV void convert_wait_done(int tid, Smem &S, const KParams &p, const Geo &g, int r, ThreadAcc &acc, bool prefetch_next)
+{
+    mbar_wait(reinterpret_cast<uint64_t *>(&S.done_bar), (acc.phase >> 2) & 1u);
+    acc.phase ^= 4u;
+    if (prefetch_next) stage_prefetch(tid, S, p, g, r + 1);
+}
+
+V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int r, ThreadAcc &acc, bool defer, bool prefetch_next)
 {
     // Chroma line j of this band averages frame rows (2jc, min(2jc+1, H-1)) with jc = min(8r+j, He/2-1): below the
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
     const int last_cline = ((p.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
     const int last_line = p.h - 1 - 16 * r;                     // local index of the last real pixel line
     const uint8_t(*src)[RGB_PITCH] = S.rgb[rb(r)];
-    if (RGB_BUFS == 2)
+    bool waiting = defer;
+    if (RGB_BUFS == 2 && !waiting)
         for (int i = tid; i < RGB_PITCH / 16; i += NT)          // keep line 15 for the next iteration's residual stage
             reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
     for (int u = tid; u < 8 * 2 * BAND_MCUS; u += NT) {          // unit = 2 lines x 8 px
@@ -510,10 +529,23 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
             U2 d0, d1;
             convert8x2<false, true>(&src[2 * jc][24 * ox], &src[lb][24 * ox], d0, d1, cb, cr);   // rare path
         }
+        if (waiting) {
+            convert_wait_done(tid, S, p, g, r, acc, prefetch_next);
+            waiting = false;
+            if (RGB_BUFS == 2)
+                for (int i = tid; i < RGB_PITCH / 16; i += NT)
+                    reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
+        }
         *reinterpret_cast<U2 *>(&S.yorig[ring16(r, 2 * li)][8 * ox]) = y0;
         *reinterpret_cast<U2 *>(&S.yorig[ring16(r, 2 * li + 1)][8 * ox]) = y1;
         *reinterpret_cast<uint32_t *>(&S.cenc[0][li][4 * ox]) = cb;
         *reinterpret_cast<uint32_t *>(&S.cenc[1][li][4 * ox]) = cr;
+    }
+    if (waiting) {                                              // a thread without any unit to store still owes the wait
+        convert_wait_done(tid, S, p, g, r, acc, prefetch_next);
+        if (RGB_BUFS == 2)
+            for (int i = tid; i < RGB_PITCH / 16; i += NT)
+                reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
     }
 }
 

@@ -31,7 +31,15 @@ namespace v5 {
         __VA_ARGS__;                         \
     }                                        \
     __syncthreads();
+#define V5_FOR_THREADS_NOSYNC(...)           \
+    {                                        \
+        const int tid = (int)threadIdx.x;    \
+        ThreadAcc &acc = acc_store[0];       \
+        (void)acc;                           \
+        __VA_ARGS__;                         \
+    }
 #else
+#define V5_FOR_THREADS_NOSYNC(...) V5_FOR_THREADS(__VA_ARGS__)
 #define V5_BLOCK_TASK(t)
 #define V5_GET_TASK(t) const BlockTask t = block_task_of<FAST>(tid, S, p, g, r, want_y, round)
 #define V5_FOR_WARP(...)                     \
@@ -138,26 +146,35 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     const bool bulk = FAST || use_bulk(p, g);
     const bool rest = !FAST && load_rest_needed(p, g, bulk);
     V5_FOR_THREADS(if (bulk) stage_prefetch(tid, S, p, g, r_first))
+    // Split barrier between the residual stage of one band and the conversion of the next (stage_convert): arrive there,
+    // wait in front of the first store here. Only in the bulk-copy-only instantiation with two RGB buffers.
+#ifndef V5_SPLIT_BARRIER
+#define V5_SPLIT_BARRIER 0
+#endif
+    constexpr bool SPLIT = FAST && RGB_BUFS == 2 && V5_SPLIT_BARRIER;
+    bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;
         const bool want_y = r >= g.r0 && r < g.r1;
+        const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
         if (!has_band && 16 * r - 1 >= p.h) break;          // nothing left below the image
         if (has_band) {
             // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
             // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
-            const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
             if (rest) {                                     // ragged right edge / unaligned frames only
                 V5_FOR_THREADS(stage_load_rest(tid, S, p, g, r, bulk))
             }
             // every thread waits for the bulk copy itself, so no CTA barrier is needed before the conversion
             V5_FOR_THREADS({
-                if (RGB_BUFS == 2 && bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
+                const bool defer = SPLIT && pending;         // the other RGB buffer may still be read: prefetch after the wait
+                if (!defer && RGB_BUFS == 2 && bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
                 if (bulk) {
                     mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[rb(r)]), (acc.phase >> rb(r)) & 1u);
                     acc.phase ^= 1u << rb(r);
                 }
-                stage_convert(tid, S, p, g, r);
+                stage_convert(tid, S, p, g, r, acc, defer, defer && bulk && next_band);
             })
+            pending = false;
             // single staging buffer: band r has been consumed by every warp (barrier above), fetch band r+1 over it now
             if (RGB_BUFS == 1 && bulk && next_band) {
                 V5_FOR_WARP(stage_prefetch(tid, S, p, g, r + 1))
@@ -172,7 +189,15 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             }
             V5_FOR_THREADS((void)0)
         }
-        V5_FOR_THREADS(stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
+        if (SPLIT && next_band) {
+            V5_FOR_THREADS_NOSYNC({
+                stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r);
+                mbar_arrive(reinterpret_cast<uint64_t *>(&S.done_bar));
+            })
+            pending = true;
+        } else {
+            V5_FOR_THREADS(stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
+        }
     }
 
     V5_FOR_THREADS(flush_partials(tid, S, acc))

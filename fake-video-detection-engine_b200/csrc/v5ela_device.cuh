@@ -135,15 +135,16 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // Byte-lane selector constants of the residual stage. As literals ptxas rematerialises each one with a UMOV in front of
 // (almost) every use — 3 % of the kernel's issue slots; as a table in constant memory four of them arrive with one
 // uniform 128-bit load (LDCU.128). Index = 4 * family + byte lane.
-enum { SEL_ONE = 0, SEL_THREE = 4, SEL_FOUR = 8, SEL_HALF = 12, SEL_TRI = 13, SEL_LAP = 16 };   // SEL_HALF: 0x8000 (rounding of the colour
+enum { SEL_ONE = 0, SEL_THREE = 4, SEL_FOUR = 8, SEL_HALF = 12, SEL_LAP = 16, SEL_TRI = 20 };   // SEL_HALF: 0x8000 (rounding of the colour
                                                                                      // conversion); SEL_TRI: the two triangle kernels
 #ifndef V5_CONST_SEL
 #define V5_CONST_SEL 1
 #endif
 #if defined(__CUDACC__) && V5_CONST_SEL
-static __constant__ uint32_t kSelTab[20] = {1u,       1u << 8,    1u << 16,    1u << 24,  3u,     3u << 8, 3u << 16, 3u << 24, 4u, 4u << 8,
-                                            4u << 16, 4u << 24,   0x8000u,     0x03090103u, 0x01030309u, 0u,
-                                            0x01fc01u, 0x01fc0100u, 0xfc010000u, 0x000001fcu};
+static __constant__ uint32_t kSelTab[24] = {1u,       1u << 8,    1u << 16,    1u << 24,  3u,     3u << 8, 3u << 16, 3u << 24, 4u, 4u << 8,
+                                            4u << 16, 4u << 24,   0x8000u,     0u,        0u,      0u,
+                                            0x01fc01u, 0x01fc0100u, 0xfc010000u, 0x000001fcu,
+                                            0x03090103u, 0x01030309u, 0x09030301u, 0x03010903u};
 #endif
 #if defined(__CUDA_ARCH__) && V5_CONST_SEL
 V5_DEV uint32_t sel_const(int i) { return kSelTab[i]; }
@@ -151,8 +152,13 @@ V5_DEV uint32_t sel_const(int i) { return kSelTab[i]; }
 V5_HOSTDEV constexpr uint32_t sel_const(int i)
 {
     return i < 12 ? (i < 4 ? 1u : (i < 8 ? 3u : 4u)) << (8 * (i & 3))
-                  : (i < 16 ? (i == 12 ? 0x8000u : (i == 13 ? 0x03090103u : (i == 14 ? 0x01030309u : 0u)))
-                            : (i == 16 ? 0x01fc01u : (i == 17 ? 0x01fc0100u : (i == 18 ? 0xfc010000u : 0x000001fcu))));
+                  : (i < 16 ? (i == 12 ? 0x8000u : 0u)
+                            : (i == 16 ? 0x01fc01u
+                                       : (i == 17 ? 0x01fc0100u
+                                                  : (i == 18 ? 0xfc010000u
+                                                             : (i == 19 ? 0x000001fcu
+                                                                        : (i == 20 ? 0x03090103u
+                                                                                   : (i == 21 ? 0x01030309u : (i == 22 ? 0x09030301u : 0x03010903u))))))));
 }
 #endif
 
@@ -822,33 +828,16 @@ V5_DEV void upsample8_fast(const uint8_t *lc, const uint8_t *ln, bool left_edge,
     }
 }
 
-// 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
 // TEXHIST: the optional tex_hist[256] output of the record table is wanted — one more shared-memory
 // increment per pixel; an instantiation of its own so that calls without it pay nothing.
+// Second half of a unit: given the upsampled chroma (minus 128) of its 8 pixels, reconstruct, residual, histogram, Laplacian.
 template <bool FAST, bool TEXHIST>
-V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
+V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox, const int *cb, const int *cr)
 {
     const int y = 16 * r + l;                                   // global pixel row
     const int gx0 = 16 * g.m0 + 8 * ox;                         // global pixel column of this unit
     const int col = 16 + 8 * ox;                                // band smem column
     const int nvalid = p.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8; FAST: >= 8)
-
-    // ---- chroma upsample (A.7)
-    const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = ((p.w + 1) >> 1) - 1;
-    const int crow = y >> 1;
-    int nrow = (y & 1) ? crow + 1 : crow - 1;
-    nrow = nrow < 0 ? 0 : (nrow > hc1 ? hc1 : nrow);
-    const int lcur = ring8(r, crow - 8 * r), lnb = ring8(r, nrow - 8 * r);
-    const int ccol = col >> 1, gcx0 = gx0 >> 1;
-    const bool fancy = wc1 > 1;
-    int cb[8], cr[8];
-    if (FAST) {
-        upsample8_fast(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cb);
-        upsample8_fast(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cr);
-    } else {
-        upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
-        upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
-    }
 
     // ---- reconstruct (A.8), residual (A.9), histogram
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
@@ -983,6 +972,97 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     acc.tex_sumabs += sabs;
     acc.tex_sumsq += ssq;
     acc.tex_maxabs = mx;
+}
+
+// 8 pixels of one output row: ox = 8-pixel column index inside the strip, l = band-relative line in [-1, 14].
+template <bool FAST, bool TEXHIST>
+V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int l, int ox)
+{
+    const int y = 16 * r + l;                                   // global pixel row
+    const int gx0 = 16 * g.m0 + 8 * ox;                         // global pixel column of this unit
+    const int col = 16 + 8 * ox;                                // band smem column
+
+    // ---- chroma upsample (A.7)
+    const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = ((p.w + 1) >> 1) - 1;
+    const int crow = y >> 1;
+    int nrow = (y & 1) ? crow + 1 : crow - 1;
+    nrow = nrow < 0 ? 0 : (nrow > hc1 ? hc1 : nrow);
+    const int lcur = ring8(r, crow - 8 * r), lnb = ring8(r, nrow - 8 * r);
+    const int ccol = col >> 1, gcx0 = gx0 >> 1;
+    const bool fancy = wc1 > 1;
+    int cb[8], cr[8];
+    if (FAST) {
+        upsample8_fast(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cb);
+        upsample8_fast(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0 == 0, gcx0 + 4 > wc1, cr);
+    } else {
+        upsample8(&S.cdec[0][lcur][ccol], &S.cdec[0][lnb][ccol], gcx0, wc1, fancy, cb);
+        upsample8(&S.cdec[1][lcur][ccol], &S.cdec[1][lnb][ccol], gcx0, wc1, fancy, cr);
+    }
+
+    residual_row<FAST, TEXHIST>(S, p, g, acc, r, l, ox, cb, cr);
+}
+
+// Two rows per unit (width-multiple-of-16 instantiation, -DV5_PAIR_ROWS=1). Band iteration r finishes rows 16r-1 .. 16r+14:
+// eight pairs (2i+1, 2i+2) of an odd row and the even row below it. Both rows of a pair filter the SAME two decoded chroma
+// rows a = i and b = i+1 — the odd row with a nearer, the even row with b nearer — so the interleaved byte pairs
+// W = [a_j, b_j, a_j+1, b_j+1] are built once and only the dot-product coefficients swap ([3,1,9,3] / [9,3,3,1] for the odd
+// row, [1,3,3,9] / [3,9,1,3] for the even one); the column arithmetic is shared as well.
+// pi = pair index 0..7 (lines l = 2pi-1 and 2pi); v0 / v1: the row lies inside the segment and the image.
+V5_DEV void chroma_pairs(const uint8_t *la, const uint8_t *lb, bool left_edge, bool right_edge, uint32_t w[5])
+{
+    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(la - 4), b0 = *reinterpret_cast<const uint32_t *>(lb - 4);
+    const uint32_t a1 = *reinterpret_cast<const uint32_t *>(la), b1 = *reinterpret_cast<const uint32_t *>(lb);
+    const uint32_t a2 = *reinterpret_cast<const uint32_t *>(la + 4), b2 = *reinterpret_cast<const uint32_t *>(lb + 4);
+    const uint32_t as = left_edge ? prmt(a1, 0u, 0x2100u) : prmt(a0, a1, 0x6543u), bs = left_edge ? prmt(b1, 0u, 0x2100u) : prmt(b0, b1, 0x6543u);
+    const uint32_t ae = right_edge ? prmt(a1, 0u, 0x3321u) : prmt(a1, a2, 0x4321u), be = right_edge ? prmt(b1, 0u, 0x3321u) : prmt(b1, b2, 0x4321u);
+    w[0] = prmt(as, bs, 0x5140u);
+    w[1] = prmt(a1, b1, 0x5140u);
+    w[2] = prmt(a1, b1, 0x6251u);
+    w[3] = prmt(a1, b1, 0x7362u);
+    w[4] = prmt(ae, be, 0x7362u);
+}
+
+template <bool TEXHIST>
+V5_DEV void residual_pair(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int pi, int ox, bool v0, bool v1)
+{
+    const int col = 16 + 8 * ox, ccol = col >> 1, gcx0 = (16 * g.m0 + 8 * ox) >> 1;
+    const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = (p.w >> 1) - 1;
+    int ja = pi - 1, jb = pi;                                   // chroma lines of this band: a nearer for the odd row, b for the even one
+    if (8 * r + ja < 0) ja = jb;                                // row 0: the line above does not exist, libjpeg repeats line 0
+    if (8 * r + jb > hc1) jb = ja;                              // last row of an even-height image: the line below repeats the last
+    const bool le = gcx0 == 0, re = gcx0 + 4 > wc1;
+    uint32_t wb[5], wr[5];
+    chroma_pairs(&S.cdec[0][ring8(r, ja)][ccol], &S.cdec[0][ring8(r, jb)][ccol], le, re, wb);
+    chroma_pairs(&S.cdec[1][ring8(r, ja)][ccol], &S.cdec[1][ring8(r, jb)][ccol], le, re, wr);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        if (!(h ? v1 : v0)) continue;
+        const uint32_t ke = sel_const(SEL_TRI + 2 * h), ko = sel_const(SEL_TRI + 2 * h + 1);
+        int cb[8], cr[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            cb[2 * j] = dp4a_us(wb[j], ke, 8 - 2048) >> 4;
+            cb[2 * j + 1] = dp4a_us(wb[j + 1], ko, 7 - 2048) >> 4;
+            cr[2 * j] = dp4a_us(wr[j], ke, 8 - 2048) >> 4;
+            cr[2 * j + 1] = dp4a_us(wr[j + 1], ko, 7 - 2048) >> 4;
+        }
+        residual_row<true, TEXHIST>(S, p, g, acc, r, 2 * pi - 1 + h, ox, cb, cr);
+    }
+}
+
+template <bool TEXHIST>
+V5_DEV void stage_residual_pairs(int tid, Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r)
+{
+    const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
+    const uint32_t inv = 65536u / (uint32_t)n8 + 1u;            // exact u / n8 for u < 8 * 60
+    const int ylo = 16 * g.r0, yhi = 16 * g.r1 < p.h ? 16 * g.r1 : p.h;
+    for (int u = tid; u < 8 * n8; u += NT) {
+        const int pi = (int)(((uint32_t)u * inv) >> 16), ox = u - pi * n8;
+        const int y0 = 16 * r + 2 * pi - 1;
+        const bool v0 = y0 >= ylo && y0 < yhi, v1 = y0 + 1 >= ylo && y0 + 1 < yhi;
+        if (!v0 && !v1) continue;
+        residual_pair<TEXHIST>(S, p, g, acc, r, pi, ox, v0, v1);
+    }
 }
 
 // Iteration r finishes pixel rows 16r-1 .. 16r+14 (clipped to the segment and the image).

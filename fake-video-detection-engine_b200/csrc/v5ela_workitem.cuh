@@ -152,6 +152,10 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 #define V5_SPLIT_BARRIER 0
 #endif
     constexpr bool SPLIT = FAST && RGB_BUFS == 2 && V5_SPLIT_BARRIER;
+#ifndef V5_PAIR_ROWS
+#define V5_PAIR_ROWS 0
+#endif
+    constexpr bool PAIRS = FAST && V5_PAIR_ROWS;             // two rows per residual unit (stage_residual_pairs)
     bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet
     for (int r = r_first; r <= g.r1; r++) {
         const bool has_band = r < p.mh;
@@ -191,12 +195,13 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
         }
         if (SPLIT && next_band) {
             V5_FOR_THREADS_NOSYNC({
-                stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r);
+                if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r);
+                else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r);
                 mbar_arrive(reinterpret_cast<uint64_t *>(&S.done_bar));
             })
             pending = true;
         } else {
-            V5_FOR_THREADS(stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
+            V5_FOR_THREADS(if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r); else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
         }
     }
 

@@ -16,16 +16,19 @@ from v5ela.synth import gen_frame
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module", params=["2cta", "3cta"])
+@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_pairs"])
 def emu(request):
-    """The default layout (2 CTAs/SM, double-buffered RGB) and the -DV5_MIN_CTAS=3 single-buffer layout."""
+    """The default layout (2 CTAs/SM, double-buffered RGB), the -DV5_MIN_CTAS=3 single-buffer layout, and the default layout
+    with the two compile-time variants of the width-multiple-of-16 instantiation switched on (two rows per residual unit,
+    split barrier)."""
     variant = request.param
     so = os.path.join(HERE, "emu", f"libv5ela_emu_{variant}.so")
     src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
     csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}",
+        extra = ["-DV5_PAIR_ROWS=1", "-DV5_SPLIT_BARRIER=1"] if variant.endswith("pairs") else []
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}", *extra,
                                "-I", os.path.join(ROOT, "include"), "-I", csrc, src, "-o", so])
     lib = ctypes.CDLL(so)
     u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -64,8 +67,9 @@ def test_emulated_kernel_vs_oracle(emu, hw, seg):
             assert recs[0].tobytes() == o["record"].tobytes()
 
 
-@pytest.mark.parametrize("hw", [(1, 16), (16, 16), (17, 32), (40, 48), (33, 496), (100, 1008), (272, 512), (9, 976)])
-@pytest.mark.parametrize("seg", [0, 2])
+@pytest.mark.parametrize("hw", [(1, 16), (2, 16), (15, 32), (16, 16), (17, 32), (31, 16), (32, 48), (33, 496), (40, 48), (100, 1008),
+                                (272, 512), (9, 976)])
+@pytest.mark.parametrize("seg", [0, 1, 2])
 def test_emulated_fast_instantiation_vs_oracle(emu, hw, seg):
     """Statistics-only calls on widths that are a multiple of 16 take the kernel instantiation without the horizontal edge
     predicates (csrc/v5ela_host.h fast_path_ok); same records as the oracle and as the general instantiation."""

@@ -1034,7 +1034,12 @@ V5_DEV void residual_pair(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     uint32_t wb[5], wr[5];
     chroma_pairs(&S.cdec[0][ring8(r, ja)][ccol], &S.cdec[0][ring8(r, jb)][ccol], le, re, wb);
     chroma_pairs(&S.cdec[1][ring8(r, ja)][ccol], &S.cdec[1][ring8(r, jb)][ccol], le, re, wr);
+    // rolled: one copy of the row code (the kernel is sensitive to the size of its hot loops); -DV5_PAIR_UNROLL=1 unrolls
+#if defined(V5_PAIR_UNROLL) && V5_PAIR_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int h = 0; h < 2; h++) {
         if (!(h ? v1 : v0)) continue;
         const uint32_t ke = sel_const(SEL_TRI + 2 * h), ko = sel_const(SEL_TRI + 2 * h + 1);

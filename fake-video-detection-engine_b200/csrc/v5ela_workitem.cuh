@@ -147,13 +147,14 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     const bool rest = !FAST && load_rest_needed(p, g, bulk);
     V5_FOR_THREADS(if (bulk) stage_prefetch(tid, S, p, g, r_first))
     // Split barrier between the residual stage of one band and the conversion of the next (stage_convert): arrive there,
-    // wait in front of the first store here. Only in the bulk-copy-only instantiation with two RGB buffers.
+    // wait in front of the first store here. Only in the bulk-copy-only instantiation with two RGB buffers. Measured 3 %
+    // SLOWER than the plain CTA barrier (profiles/r01/variants.txt) and therefore off: a compile-time variant.
 #ifndef V5_SPLIT_BARRIER
 #define V5_SPLIT_BARRIER 0
 #endif
     constexpr bool SPLIT = FAST && RGB_BUFS == 2 && V5_SPLIT_BARRIER;
 #ifndef V5_PAIR_ROWS
-#define V5_PAIR_ROWS 0
+#define V5_PAIR_ROWS 1
 #endif
     constexpr bool PAIRS = FAST && V5_PAIR_ROWS;             // two rows per residual unit (stage_residual_pairs)
     bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet

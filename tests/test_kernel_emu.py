@@ -16,18 +16,18 @@ from v5ela.synth import gen_frame
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_pairs"])
+@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_rows_split"])
 def emu(request):
     """The default layout (2 CTAs/SM, double-buffered RGB), the -DV5_MIN_CTAS=3 single-buffer layout, and the default layout
-    with the two compile-time variants of the width-multiple-of-16 instantiation switched on (two rows per residual unit,
-    split barrier)."""
+    with the two compile-time variants of the width-multiple-of-16 instantiation flipped (one row per residual unit instead
+    of two, split barrier on)."""
     variant = request.param
     so = os.path.join(HERE, "emu", f"libv5ela_emu_{variant}.so")
     src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
     csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        extra = ["-DV5_PAIR_ROWS=1", "-DV5_SPLIT_BARRIER=1"] if variant.endswith("pairs") else []
+        extra = ["-DV5_PAIR_ROWS=0", "-DV5_SPLIT_BARRIER=1"] if variant.endswith("rows_split") else []
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}", *extra,
                                "-I", os.path.join(ROOT, "include"), "-I", csrc, src, "-o", so])
     lib = ctypes.CDLL(so)

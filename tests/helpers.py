@@ -60,3 +60,34 @@ def record_matches_golden(rec, case) -> list:
     if sha(rec.tobytes()) != case["record_sha"]:
         bad.append("record_bytes")
     return bad
+
+
+def layout_golden_files():
+    """[(case, label, file bytes, golden entry)] of tests/golden/layouts_golden.json: the files are written again with the
+    generator's own code (tests/golden/make_layouts_golden.py) and must hash to what it recorded."""
+    import hashlib
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_layouts_golden", os.path.join(GOLDEN, "make_layouts_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    out = []
+    for case in load_json("layouts_golden.json")["cases"]:
+        rgb = golden_frame(case)
+        assert sha(rgb) == case["in_sha"]
+        written = dict(gen.layout_files(rgb, case["q"]))
+        for entry in case["files"]:
+            data = written[entry["label"]]
+            assert (len(data), hashlib.sha256(data).hexdigest()[:16]) == (entry["file_len"], entry["file_sha"]), (case["spec"], entry["label"])
+            out.append((case, entry["label"], data, entry))
+    return out
+
+
+def check_layout_goldens(decode):
+    """decode(list of file bytes) -> list of dict(rgb, gray); every file of layouts_golden.json must decode to the recorded pixels."""
+    items = layout_golden_files()
+    outs = decode([data for _, _, data, _ in items])
+    assert len(outs) == len(items) == 100
+    for (case, label, _, entry), o in zip(items, outs):
+        assert sha(o["rgb"]) == entry["dec_rgb_sha"], (case["spec"], case["h"], case["w"], label)
+        assert sha(o["gray"]) == entry["dec_y_sha"], (case["spec"], case["h"], case["w"], label)

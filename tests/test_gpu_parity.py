@@ -320,3 +320,16 @@ def test_texture_histogram_optional_output():
         assert int(th.sum()) == 3 * h * w
         assert torch.equal(out["records"], plain["records"]) and torch.equal(with_res["records"], plain["records"])
         assert torch.equal(with_res["tex_hist"], out["tex_hist"])
+
+
+def test_texture_histogram_goldens():
+    """tests/golden/layouts_golden.json: tex_hist recorded from OpenCV's Laplacian of Pillow's luma, through v5ela_analyze_ex."""
+    import torch
+    from helpers import golden_frame, load_json, sha
+    from v5ela import analyze_batch
+
+    for case in load_json("layouts_golden.json")["cases"]:
+        t = torch.from_numpy(golden_frame(case)[None]).cuda()
+        th = analyze_batch(t, want_tex_hist=True)["tex_hist"].cpu().numpy().view(np.uint32)[0]
+        assert sha(np.ascontiguousarray(th)) == case["tex_hist_sha"], (case["spec"], case["h"], case["w"])
+        assert int(th[255]) == case["tex_hist_last"]

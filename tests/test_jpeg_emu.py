@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 from PIL import Image
 
-from helpers import HERE, golden_frame, load_json, sha
+from helpers import check_layout_goldens, HERE, golden_frame, load_json, sha
 from oracle import c_oracle
 
 ROOT = os.path.dirname(HERE)
@@ -177,6 +177,10 @@ def test_decoder_restart_intervals(emu):
     k = data.index(b"\xff\xd3", data.index(b"\xff\xda"))
     with pytest.raises(ValueError):
         emu_decode(emu, data[:k] + data[k + 2:])
+
+
+def test_layout_goldens(emu):
+    check_layout_goldens(lambda blobs: [emu_decode(emu, b) for b in blobs])
 
 
 def test_unsupported_files_are_refused(emu):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 from PIL import Image
 
-from helpers import GOLDEN, golden_frame, load_json, sha
+from helpers import check_layout_goldens, GOLDEN, golden_frame, load_json, sha
 from oracle import c_oracle
 
 JPEG = load_json("jpeg_golden.json")
@@ -115,6 +115,12 @@ def test_decoder_takes_the_other_chroma_layouts_and_restart_intervals():
             out = c_oracle.jpeg_decode(data, want_coef=True)
             assert np.array_equal(out["rgb"], np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))), (h, w, q, ss)
             assert np.array_equal(out["gray"], cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)), (h, w, q, ss)
+
+
+def test_layout_goldens():
+    """tests/golden/layouts_golden.json: 100 files in the layouts the decoder row was widened to (4:4:4 / 4:2:2 / 4:2:0 with
+    restart intervals, one component with restarts), pixels as recorded from Pillow / OpenCV."""
+    check_layout_goldens(lambda blobs: [c_oracle.jpeg_decode(b) for b in blobs])
 
 
 def test_unsupported_flavours_are_reported():

@@ -105,6 +105,15 @@ def test_emulated_texture_histogram(emu, hw):
                 assert np.array_equal(res[0], o["residual"])
 
 
+def test_emulated_texture_histogram_goldens(emu):
+    """tests/golden/layouts_golden.json: tex_hist recorded from OpenCV's Laplacian of Pillow's luma."""
+    for case in load_json("layouts_golden.json")["cases"]:
+        th = np.zeros((1, 256), np.uint32)
+        emu(golden_frame(case)[None], 90, 0, want_residual=False, tex_hist=th)
+        assert sha(th[0]) == case["tex_hist_sha"] and [int(v) for v in th[0][:8]] == case["tex_hist_head"]
+        assert int(th[0][255]) == case["tex_hist_last"]
+
+
 def test_emulated_kernel_vs_reference_goldens(emu):
     cases = [c for c in load_json("frames_golden.json")["cases"] if c["h"] * c["w"] <= 64 * 96]
     assert len(cases) > 20

@@ -13,39 +13,15 @@
 #include <vector>
 
 #include "v5ela.h"
-#include "v5ela_host.h"
-#include "v5ela_workitem.cuh"
+#include "v5ela_launch.cuh"
 #include "v5ela_fft.cuh"
 
 static_assert(sizeof(v5ela_record) == 3144, "V5F v1 record layout");
-static_assert(sizeof(v5::KParams) <= 4096, "kernel parameters must fit the 4 KB parameter bank");
-static_assert(sizeof(v5::Smem) <= (227 * 1024) / v5::MIN_CTAS - 1024, "MIN_CTAS CTAs per SM must fit in shared memory");
 
 namespace v5 {
 
-template <bool FAST, bool TEXHIST>
-__global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    ThreadAcc acc_store[1];
-    acc_store[0].phase = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[0]), 1);
-        mbar_init(reinterpret_cast<uint64_t *>(&S.full_bar[1]), 1);
-        mbar_init(reinterpret_cast<uint64_t *>(&S.done_bar), NT);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    // Work items are drawn from a global ticket counter: no tail of idle CTAs whatever the batch size / CTA count ratio.
-    for (;;) {
-        if (threadIdx.x == 0) S.next_work = atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const int work = (int)S.next_work;
-        if (work >= total_work) break;
-        process_work_item<FAST, TEXHIST>(S, p, work, acc_store);          // ends with a CTA barrier: next_work may be rewritten
-    }
-}
+cudaError_t fused_prepare_smem() { return fused_prepare(); }
+int fused_launch_smem(v5_fused_args &a) { return fused_launch(a); }
 
 // One warp per (frame, channel): ela_sum = sum b*hist[b], ela_sumsq = sum b^2*hist[b], ela_max = highest non-empty bin.
 __global__ void __launch_bounds__(96) ela_finalize_kernel(v5ela_record *recs, int n)
@@ -179,19 +155,25 @@ int v5ela_create(int device, v5ela_handle **out)
     h->sm_count = prop.multiProcessorCount;
     v5::quant_tables(h->quality, h->luma, h->chroma);
     DeviceGuard guard(device);
-    if (cudaFuncSetAttribute(v5::ela_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(v5::Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(v5::ela_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(v5::Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(v5::ela_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(v5::Smem)) != cudaSuccess) {
+    if (v5::fused_prepare_smem() != cudaSuccess || v5m::fused_prepare_mma() != cudaSuccess) {
         delete h;
         return V5ELA_ERR_CUDA;
+    }
+    {   // per-lane operand fragments of the tensor-core block stage: 32 x 128 bytes, fixed for the life of the handle
+        alignas(16) unsigned char lc[32 * 128];
+        if (!v5m::lane_consts_host(lc) || cudaMalloc(&h->d_lane_consts, sizeof(lc)) != cudaSuccess ||
+            cudaMemcpy(h->d_lane_consts, lc, sizeof(lc), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(h->d_lane_consts);
+            delete h;
+            return V5ELA_ERR_CUDA;
+        }
     }
     const char *env = getenv("V5ELA_SEG_ROWS");
     if (env) h->seg_rows = atoi(env);
     env = getenv("V5ELA_CTAS_PER_SM");                        // tuning knob: launch fewer persistent CTAs than fit
     if (env && atoi(env) >= 1 && atoi(env) <= v5::MIN_CTAS) h->ctas_per_sm = atoi(env);
+    env = getenv("V5ELA_BLOCK_STAGE");                        // "mma" / "smem": default block stage of new handles (A/B runs)
+    if (env) h->block_stage = !strcmp(env, "mma") ? V5ELA_BLOCKS_MMA : (!strcmp(env, "smem") ? V5ELA_BLOCKS_SMEM : h->block_stage);
     env = getenv("V5ELA_HOST_CHUNK");
     if (env) h->host_chunk_frames = atoi(env);
     *out = h;
@@ -214,6 +196,7 @@ int v5ela_destroy(v5ela_handle *h)
     cudaFree(h->d_enh);
     cudaFree(h->d_rec);
     cudaFree(h->d_ticket);
+    cudaFree(h->d_lane_consts);
     cudaFree(h->tw_w);
     cudaFree(h->tw_h);
     cudaFree(h->d_g);
@@ -258,33 +241,37 @@ int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, i
 {
     if (!h) return V5ELA_ERR_INVALID;
     if (n == 0) return V5ELA_OK;
-    v5::KParams p;
-    if (v5::fill_params(p, d_rgb, n, height, width, frame_stride_bytes, row_stride_bytes,
-                        static_cast<v5ela_record *>(d_records), d_residual, h->quality, h->seg_rows,
-                        2 * h->sm_count * h->ctas_per_sm) != 0)
-        return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: bad pointer, size or stride%s");
-    p.tex_hist = d_tex_hist;
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    const long long total = (long long)n * p.n_strips * p.n_segs;
-    if (total > 0x7fffffffLL) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: batch too large%s");
     if (!h->d_ticket) V5_CUDA(h, cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
-    p.ticket = h->d_ticket;
-    V5_CUDA(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), st));
-    V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
-    if (d_tex_hist) V5_CUDA(h, cudaMemsetAsync(d_tex_hist, 0, sizeof(uint32_t) * 256 * (size_t)n, st));
-    const int max_ctas = h->sm_count * h->ctas_per_sm;
-    const int grid = total < max_ctas ? (int)total : max_ctas;
     const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
-    if (prof) V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used], st));
-    if (p.tex_hist) v5::ela_fused_kernel<false, true><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
-    else if (v5::fast_path_ok(p)) v5::ela_fused_kernel<true, false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
-    else v5::ela_fused_kernel<false, false><<<grid, v5::NT, sizeof(v5::Smem), st>>>(p, (int)total);
-    V5_CUDA(h, cudaGetLastError());
-    if (prof) {
-        V5_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used + 1], st));
-        h->prof_used += 2;
+    v5_fused_args a;
+    memset(&a, 0, sizeof(a));
+    a.rgb = d_rgb; a.n = n; a.h = height; a.w = width;
+    a.frame_stride = frame_stride_bytes; a.row_stride = row_stride_bytes;
+    a.records = static_cast<v5ela_record *>(d_records);
+    a.residual = d_residual; a.tex_hist = d_tex_hist;
+    a.quality = h->quality; a.seg_rows = h->seg_rows;
+    a.target_items = 2 * h->sm_count * h->ctas_per_sm;
+    a.max_ctas = h->sm_count * h->ctas_per_sm;
+    a.ticket = h->d_ticket; a.lane_consts = h->d_lane_consts;
+    a.stream = st;
+    if (prof) { a.ev_start = h->prof_events[h->prof_used]; a.ev_stop = h->prof_events[h->prof_used + 1]; }
+    const bool use_mma = h->block_stage == V5ELA_BLOCKS_MMA;
+    a.check_only = 1;                                           // validate before anything is written
+    int rc = use_mma ? v5m::fused_launch_mma(a) : v5::fused_launch_smem(a);
+    if (rc == 0) {
+        V5_CUDA(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), st));
+        V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
+        if (d_tex_hist) V5_CUDA(h, cudaMemsetAsync(d_tex_hist, 0, sizeof(uint32_t) * 256 * (size_t)n, st));
+        a.check_only = 0;
+        rc = use_mma ? v5m::fused_launch_mma(a) : v5::fused_launch_smem(a);
     }
+    if (rc == -1) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: bad pointer, size or stride%s");
+    if (rc == -2) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze: batch too large%s");
+    if (rc > 0) return fail(h, V5ELA_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    h->last_inst = a.inst;
+    if (prof) h->prof_used += 2;
     v5::ela_finalize_kernel<<<n, 96, 0, st>>>(static_cast<v5ela_record *>(d_records), n);
     V5_CUDA(h, cudaGetLastError());
     h->launches += 2;
@@ -528,5 +515,17 @@ int v5ela_profile_read(v5ela_handle *h, double *fused_ms_sum, int64_t *fused_lau
 }
 
 int64_t v5ela_launch_count(const v5ela_handle *h) { return h ? h->launches : 0; }
+
+int v5ela_last_instantiation(const v5ela_handle *h) { return h ? h->last_inst : V5ELA_ERR_INVALID; }
+
+int v5ela_set_block_stage(v5ela_handle *h, int mode)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (mode != V5ELA_BLOCKS_SMEM && mode != V5ELA_BLOCKS_MMA) return fail(h, V5ELA_ERR_INVALID, "block stage must be V5ELA_BLOCKS_SMEM or V5ELA_BLOCKS_MMA%s");
+    h->block_stage = mode;
+    return V5ELA_OK;
+}
+
+int v5ela_get_block_stage(const v5ela_handle *h) { return h ? h->block_stage : V5ELA_ERR_INVALID; }
 
 }  // extern "C"

@@ -30,7 +30,14 @@
 #define V5_HOSTDEV inline
 #endif
 
-namespace v5 {
+// The library carries the device code twice, as two translation units with different block stages (V5_MMA_BLOCKS): v5ela.cu builds
+// it in namespace v5 (shared-memory transposes, also what the codec kernels take their DCT passes from), v5ela_mma.cu in namespace
+// v5m (tensor-core form). V5_NS names the namespace of the current build.
+#ifndef V5_NS
+#define V5_NS v5
+#endif
+
+namespace V5_NS {
 
 // ----------------------------------------------------------------------------------------------- geometry constants
 #ifndef V5_NT
@@ -42,14 +49,25 @@ namespace v5 {
 #ifndef V5_MIN_CTAS
 #define V5_MIN_CTAS 2
 #endif
+// Block stage (8x8 round trip): 1 = int8 limb-split tensor-core form (v5ela_dctmma.cuh, kernel v11), 0 = the v2..v10 form
+// (4 threads per block, two shared-memory transposes) kept as a compile-time variant for A/B runs.
+#ifndef V5_MMA_BLOCKS
+#define V5_MMA_BLOCKS 0
+#endif
+#ifndef V5_MMA_NP
+#define V5_MMA_NP 1                         // pairs of blocks in flight per warp (1, 2, 4 measured: profiles/r02/variants.txt)
+#endif
 constexpr int NT = V5_NT;                   // threads per CTA
 constexpr int TW_MAX = V5_TW_MAX;           // strip width, MCUs (16 px)
 constexpr int MIN_CTAS = V5_MIN_CTAS;       // resident CTAs per SM the kernel is built for
 constexpr int BAND_MCUS = TW_MAX + 2;       // + halo MCU column each side
 constexpr int BAND_PX = BAND_MCUS * 16;     // 512
 constexpr int RGB_PITCH = BAND_PX * 3;      // 1536 bytes per band line
-constexpr int Y_PITCH = BAND_PX;            // 512
-constexpr int C_PITCH = BAND_PX / 2;        // 256
+// Plane pitches. The tensor-core block stage reads 4 pixels of 8 consecutive lines per quarter warp: 16 bytes of padding per line
+// put those lines into different banks (pitch / 4 = 4 mod 32) — conflict-free 32-bit loads and 16-bit stores.
+constexpr int PLANE_PAD = V5_MMA_BLOCKS ? 16 : 0;
+constexpr int Y_PITCH = BAND_PX + PLANE_PAD;        // 512 (+16)
+constexpr int C_PITCH = BAND_PX / 2 + PLANE_PAD;    // 256 (+16)
 
 // Exact division constants for one quantisation table entry T (divisor d = 8T), see make_quant():
 //   q_biased = umulhi(c + (c >> 31) + bias, recip);  dequantised = q_biased * t - unbias
@@ -59,6 +77,8 @@ struct QuantTab {
     int32_t t[64];
     int32_t unbias[64];
 };
+
+namespace mma { struct LaneConsts; }
 
 struct KParams {
     const uint8_t *rgb;
@@ -71,6 +91,7 @@ struct KParams {
     int mw, mh;                 // MCU columns / rows of the padded frame
     int n_strips, n_segs;       // work decomposition: strips x vertical segments per frame
     unsigned int *ticket;       // work-item counter (zeroed before every launch): CTAs draw items dynamically
+    const mma::LaneConsts *lane_consts;   // 32 entries (v5ela_dctmma.cuh), device memory owned by the handle
     int vec_ok;                 // 1: every band line start is 16-byte aligned in global memory (128-bit loads)
     int resid_vec_ok;           // 1: residual rows are 16-byte aligned (3*W % 16 == 0 and base aligned): 128-bit stores
     QuantTab q[2];              // [0] luma, [1] chroma — lives in the kernel parameter constant bank
@@ -293,6 +314,18 @@ V5_DEV uint32_t pack4(int a, int b, int c, int d)
 // ------------------------------------------------------------------------------------------------- shared memory
 struct alignas(16) QEntry { uint32_t recip; int32_t bias, t, unbias; };   // one LDS.128 per coefficient
 
+#ifndef __CUDA_ARCH__
+// host compilations only (used by the g++ build, tests/emu): 16-bit hand-offs of the block stage that did not fit 16 bits, counted (tests assert 0)
+inline long long &range_violations()
+{
+    static long long n = 0;
+    return n;
+}
+#endif
+}  // namespace V5_NS
+#include "v5ela_dctmma.cuh"
+namespace V5_NS {
+
 // Two shared-memory layouts, chosen by the number of resident CTAs the kernel is built for:
 //   RGB_BUFS == 2 (2 CTAs/SM): double-buffered RGB band (TMA runs a whole iteration ahead), original pixels for the
 //                  residual stage come from shared memory, 32-line luma ring.
@@ -308,11 +341,22 @@ constexpr int RINGD = V5_RINGD;         // ydec ring lines (16 + 1 carried); a p
                                         // ring index is computed per 8-pixel unit
 
 struct alignas(16) Smem {
-    QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per CTA
+    QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per work item (tensor-core
+                                        // block stage: in mma::qswz_pos order, unbias minus the limb offset)
+#if V5_MMA_BLOCKS
+#ifdef __CUDA_ARCH__
+    U4 lane[8][32];                     // per-lane operand fragments of the four passes (mma::LaneConsts), 128-bit word j of lane l
+                                        // at [j][l]: a warp's load of one word is 512 contiguous bytes, conflict-free
+#else
+    mma::LaneConsts lane[32];
+#endif
+#endif
     uint8_t rgb[RGB_BUFS][16][RGB_PITCH];   // band r in rgb[rb(r)]; with two buffers the other one receives band r+1
     uint8_t rgb_carry[RGB_BUFS == 2 ? 2 : 1][RGB_BUFS == 2 ? RGB_PITCH : 16];   // line 15 of band r (two-buffer layout only)
+#if !V5_MMA_BLOCKS
     uint32_t tscratch[NT / 32][8 * 36]; // block stage: per warp, 8 blocks x (64 int16 + pad): both transpositions;
                                         // 36-word block stride = conflict-free scattered stores and 128-bit loads
+#endif
     uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
     uint8_t ydec[RINGD][Y_PITCH];       // luma after the JPEG round trip; band r line l at [(16r + l) mod RINGD]
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
@@ -343,7 +387,9 @@ struct ThreadAcc {              // per-thread state that lives across barriers (
     uint32_t tex_sumabs;
     uint32_t tex_maxabs;
     uint32_t phase;             // bit b: parity of the next wait on full_bar[b], bit 2: on done_bar (persist across work items)
+#if !V5_MMA_BLOCKS
     int col[16];                // block stage: two columns between the two halves of the column sub-stage
+#endif
 };
 
 V5_DEV int rb(int r) { return RGB_BUFS == 2 ? (r & 1) : 0; }           // RGB buffer / mbarrier of band r
@@ -631,6 +677,18 @@ V5_DEV void idct8(int *v)
     v[4 * S] = (t0 - t3 - u0) >> n;
 }
 
+// int16 pairs in a word (also used by the codec kernels, v5jpeg_*.cuh)
+V5_DEV uint32_t pack_s16(int lo, int hi)
+{
+#ifndef __CUDACC__
+    if (lo < -32768 || lo > 32767 || hi < -32768 || hi > 32767) range_violations()++;
+#endif
+    return prmt((uint32_t)lo, (uint32_t)hi, 0x5410u);
+}
+V5_DEV int s16_lo(uint32_t w) { return (int)prmt(w, 0u, 0x9910u); }         // sign-extend the low half: one PRMT
+V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
+
+#if !V5_MMA_BLOCKS
 // The block stage. Four threads share one 8x8 block; thread j owns rows 2j,2j+1 in the row passes and columns 2j,2j+1
 // in the column passes. The two transpositions go through a per-warp shared-memory scratch as int16 pairs (ranges:
 // |fDCT row output| <= 4096, |IDCT column output| <= 21047 by Parseval + quantisation error), laid out so
@@ -692,9 +750,6 @@ V5_DEV BlockTask block_task_of(int tid, Smem &S, const KParams &p, const Geo &g,
 
 V5_DEV int blocks_in_band(const Geo &g, bool want_y) { return (want_y ? 4 * (g.m1 - g.m0) : 0) + 2 * g.band_mcus; }
 
-V5_DEV uint32_t pack_s16(int lo, int hi) { return prmt((uint32_t)lo, (uint32_t)hi, 0x5410u); }
-V5_DEV int s16_lo(uint32_t w) { return (int)prmt(w, 0u, 0x9910u); }         // sign-extend the low half: one PRMT
-V5_DEV int s16_hi(uint32_t w) { return (int)w >> 16; }
 
 // sub-stage 1: forward row pass of rows 2j, 2j+1 -> tscratch (column-major pairs)
 V5_DEV void blocks_rows_fwd(int tid, Smem &S, const BlockTask &t)
@@ -768,6 +823,74 @@ V5_DEV void blocks_rows_inv(int tid, Smem &S, const BlockTask &t)
     *reinterpret_cast<U2 *>(t.out + (2 * j) * t.pitch) = U2{pack4sat(a[0], a[1], a[2], a[3]), pack4sat(a[4], a[5], a[6], a[7])};
     *reinterpret_cast<U2 *>(t.out + (2 * j + 1) * t.pitch) = U2{pack4sat(b[0], b[1], b[2], b[3]), pack4sat(b[4], b[5], b[6], b[7])};
 }
+
+#else   // V5_MMA_BLOCKS
+// The block stage, tensor-core form (v5ela_dctmma.cuh): a warp takes NP pairs of horizontally adjacent blocks through the four
+// passes in registers. A band's blocks come in four sections — luma block rows 0 and 1 (strip width / 16 pairs each), Cb and Cr
+// (ceil(band MCUs / 2) pairs each, the halo columns included) — and a section's pairs are dealt to the warps NP at a time, so the
+// per-pair set-up is one add. Blocks [act_lo, act_hi) of a section are stored; the others (libjpeg's dummy blocks right of the
+// image, chroma halo columns outside it, the odd block of the last chroma pair) are computed on whatever the plane holds and
+// dropped. FAST: the width is a multiple of 16, so every luma block of a strip is inside the image.
+constexpr int MMA_NP = V5_MMA_NP;
+
+template <int PITCH, bool ALL_ACTIVE>
+V5_DEV void blocks_section(int tid, const mma::LaneConsts *K, const uint8_t *in, uint8_t *out, const QEntry *q, int npairs, int act_lo,
+                           int act_hi)
+{
+    const int warp = tid >> 5;
+    for (int k0 = warp * MMA_NP; k0 < npairs; k0 += (NT / 32) * MMA_NP) {
+        mma::PairTask t[MMA_NP];
+#pragma unroll
+        for (int j = 0; j < MMA_NP; j++) {
+            const int k = k0 + j < npairs ? k0 + j : npairs - 1;        // a group's tail repeats the last pair without storing it
+            t[j].in = in + 16 * k;
+            t[j].out = out + 16 * k;
+            t[j].q = q;
+            t[j].ipitch = t[j].opitch = PITCH;
+            t[j].left = k0 + j < npairs && (ALL_ACTIVE || (2 * k >= act_lo && 2 * k < act_hi));
+            t[j].right = k0 + j < npairs && (ALL_ACTIVE || (2 * k + 1 >= act_lo && 2 * k + 1 < act_hi));
+        }
+#ifdef __CUDA_ARCH__
+        mma::dct_pairs<MMA_NP>(t, *K, tid & 31);
+#else
+        for (int j = 0; j < MMA_NP; j++)
+            if (t[j].left || t[j].right) mma::dct_pair_emu(t[j], K);
+#endif
+    }
+}
+
+// every warp calls it once per band (emulator: once per warp, tid = 32 * warp)
+template <bool FAST>
+V5_DEV void stage_blocks_mma(int tid, Smem &S, const KParams &p, const Geo &g, int r, bool want_y)
+{
+    const int tw = g.m1 - g.m0;
+#ifdef __CUDA_ARCH__
+    mma::LaneConsts Kreg;                                               // eight LDS.128, once per band
+#pragma unroll
+    for (int j = 0; j < 8; j++) reinterpret_cast<U4 *>(&Kreg)[j] = S.lane[j][tid & 31];
+    const mma::LaneConsts *K = &Kreg;
+#else
+    const mma::LaneConsts *K = S.lane;                                 // the emulator works on all 32 lanes at once
+#endif
+    if (want_y) {
+        int hi = 2 * tw;
+        if (!FAST) {
+            const int inside = (p.w - 16 * g.m0 + 7) >> 3;             // luma blocks of this strip that hold image columns
+            hi = inside < hi ? inside : hi;
+        }
+#pragma unroll 1
+        for (int br = 0; br < 2; br++) {
+            if (16 * r + 8 * br >= p.h) break;                         // block rows below the image: dummy data, never visible
+            blocks_section<Y_PITCH, FAST>(tid, K, &S.yorig[ring16(r, 8 * br)][16], &S.ydec[ringd(r, 8 * br)][16], S.qtab[0], tw, 0, hi);
+        }
+    }
+    const int lo = g.m0 == 0 ? 1 : 0;                                  // halo MCU columns outside the image are not real blocks
+    const int hi = g.band_mcus < p.mw - g.m0 + 1 ? g.band_mcus : p.mw - g.m0 + 1;
+#pragma unroll 1
+    for (int comp = 0; comp < 2; comp++)
+        blocks_section<C_PITCH, false>(tid, K, &S.cenc[comp][0][0], &S.cdec[comp][ring8(r, 0)][0], S.qtab[1], (g.band_mcus + 1) >> 1, lo, hi);
+}
+#endif  // V5_MMA_BLOCKS
 
 // ------------------------------------------------------------------- stage: upsample, reconstruct, residual, Laplacian
 // Horizontal+vertical fancy upsample (A.7) of one chroma component for 8 output pixels of one line.
@@ -1105,4 +1228,4 @@ V5_DEV void make_geo(const KParams &p, int work, Geo &g, int &frame)
     g.resid = p.residual ? p.residual + (int64_t)frame * p.h * p.w * 3 : nullptr;
 }
 
-}  // namespace v5
+}  // namespace V5_NS

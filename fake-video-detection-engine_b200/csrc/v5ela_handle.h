@@ -9,6 +9,7 @@
 
 #include "v5ela.h"
 #include "v5ela_device.cuh"
+#include "v5ela_fused_args.h"
 
 struct v5ela_handle {
     int device = 0;
@@ -17,6 +18,7 @@ struct v5ela_handle {
     int seg_rows = 0;                      // 0 = default
     int ctas_per_sm = v5::MIN_CTAS;
     int64_t launches = 0;
+    int last_inst = -1;                    // V5ELA_INST_* of the most recent fused-kernel launch
     cudaStream_t own_stream = nullptr;     // v5ela_analyze_host with a NULL stream
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;   // chunk pipeline of v5ela_analyze_host
     cudaEvent_t ev_fork = nullptr, ev_join_copy = nullptr, ev_join_work = nullptr;
@@ -28,6 +30,8 @@ struct v5ela_handle {
     uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
     void *d_rec = nullptr;
     unsigned int *d_ticket = nullptr;
+    void *d_lane_consts = nullptr;         // 32 x mma::LaneConsts: operand fragments of the tensor-core block stage (v5ela_dctmma.cuh)
+    int block_stage = V5ELA_BLOCKS_DEFAULT; // which build of the fused kernel analyze launches (v5ela_set_block_stage)
     size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
     // spectrum path (v5ela_fft.cuh): twiddle tables for the last (width, height), DFT workspace
     double2 *tw_w = nullptr, *tw_h = nullptr;

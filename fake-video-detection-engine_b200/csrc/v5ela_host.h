@@ -5,7 +5,7 @@
 
 #include "v5ela_device.cuh"
 
-namespace v5 {
+namespace V5_NS {
 
 // JPEG Annex K.1 / K.2 base tables in natural (row-major) order, scaled like libjpeg's jpeg_set_quality with
 // force_baseline — what `Image.save(..., 'JPEG', quality=q)` uses (v5_texture_ela.py:67).
@@ -100,4 +100,4 @@ inline void finalize_record(v5ela_record &r)
     }
 }
 
-}  // namespace v5
+}  // namespace V5_NS

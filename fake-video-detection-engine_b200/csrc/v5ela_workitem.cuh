@@ -7,7 +7,7 @@
 #pragma once
 #include "v5ela_device.cuh"
 
-namespace v5 {
+namespace V5_NS {
 
 // V5_FOR_WARP(body): same, but the ordering point is only warp-wide (device: __syncwarp()).
 // V5_BLOCK_TASK / V5_GET_TASK: the block-stage task of a thread is computed once per round on the device and once per
@@ -28,6 +28,7 @@ namespace v5 {
         const int tid = (int)threadIdx.x;    \
         ThreadAcc &acc = acc_store[0];       \
         (void)acc;                           \
+        (void)tid;                           \
         __VA_ARGS__;                         \
     }                                        \
     __syncthreads();
@@ -38,7 +39,19 @@ namespace v5 {
         (void)acc;                           \
         __VA_ARGS__;                         \
     }
+// V5_FOR_EACH_WARP(body): warp-collective work (the tensor-core block stage). Device: every thread runs `body`; emulator: `body`
+// runs once per warp with tid = 32 * warp and does the whole warp's work. Ends with a CTA barrier.
+#define V5_FOR_EACH_WARP(...)                \
+    {                                        \
+        const int tid = (int)threadIdx.x;    \
+        __VA_ARGS__;                         \
+    }                                        \
+    __syncthreads();
 #else
+#define V5_FOR_EACH_WARP(...)                        \
+    for (int tid = 0; tid < NT; tid += 32) {         \
+        __VA_ARGS__;                                 \
+    }
 #define V5_FOR_THREADS_NOSYNC(...) V5_FOR_THREADS(__VA_ARGS__)
 #define V5_BLOCK_TASK(t)
 #define V5_GET_TASK(t) const BlockTask t = block_task_of<FAST>(tid, S, p, g, r, want_y, round)
@@ -128,8 +141,20 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
         for (int i = tid; i < 2 * 64; i += NT) {
             const QuantTab &q = p.q[i >> 6];
             const int k = i & 63;
+#if V5_MMA_BLOCKS
+            S.qtab[i >> 6][mma::qswz_pos(k)] = mma::qswz_entry(q.recip[k], q.bias[k], q.t[k], q.unbias[k]);
+#else
             S.qtab[i >> 6][k] = QEntry{q.recip[k], q.bias[k], q.t[k], q.unbias[k]};
+#endif
         }
+#if V5_MMA_BLOCKS
+#ifdef __CUDA_ARCH__
+        for (int i = tid; i < 32 * 8; i += NT) S.lane[i & 7][i >> 3] = reinterpret_cast<const U4 *>(p.lane_consts)[i];   // word i & 7 of lane i >> 3
+#else
+        for (int i = tid; i < 32 * (int)(sizeof(mma::LaneConsts) / 16); i += NT)
+            reinterpret_cast<U4 *>(S.lane)[i] = reinterpret_cast<const U4 *>(p.lane_consts)[i];
+#endif
+#endif
         if (tid == 0) {
             S.tex_sumabs = 0;
             S.tex_sumsq = 0;
@@ -184,6 +209,9 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
             if (RGB_BUFS == 1 && bulk && next_band) {
                 V5_FOR_WARP(stage_prefetch(tid, S, p, g, r + 1))
             }
+#if V5_MMA_BLOCKS
+            V5_FOR_EACH_WARP(stage_blocks_mma<FAST>(tid, S, p, g, r, want_y))
+#else
             const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
             for (int round = 0; round < rounds; round++) {
                 V5_BLOCK_TASK(t)
@@ -193,6 +221,7 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
                 V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_inv(tid, S, t))
             }
             V5_FOR_THREADS((void)0)
+#endif
         }
         if (SPLIT && next_band) {
             V5_FOR_THREADS_NOSYNC({
@@ -210,4 +239,4 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     V5_FOR_THREADS(flush_global(tid, S, p.records + frame, TEXHIST ? p.tex_hist + (int64_t)frame * 256 : nullptr))
 }
 
-}  // namespace v5
+}  // namespace V5_NS

@@ -12,16 +12,17 @@ What runs on the B200 instead of Pillow/OpenCV/NumPy:
   * the error-level analysis (:66-78) through ``v5ela_analyze_host`` — bit-exact;
   * the FFT log-magnitude image (:84-88) through ``v5ela_spectrum_host`` (within one grey level of NumPy; identical on
     every golden crop);
-  * JPEG-encoding the artefacts ``ela_{i}.jpg`` (:80-81, quality 75), ``fft_{i}.jpg`` (:90-91, quality 95, one component) and,
-    on request, the scratch file ``temp_ela_{i}.jpg`` (:66-67) through ``v5ela_jpeg_encode_host`` — the files equal the
-    reference's byte for byte.
+  * JPEG-encoding the three files the reference leaves in ``ela_analysis/`` — the scratch file ``temp_ela_{i}.jpg`` (:66-67,
+    quality 90), ``ela_{i}.jpg`` (:80-81, quality 75) and ``fft_{i}.jpg`` (:90-91, quality 95, one component) — through
+    ``v5ela_jpeg_encode_host``; the files equal the reference's byte for byte.
   There is no CPU fallback for any of it: a missing library or GPU — or a crop outside the GPU decoder's set (not a JPEG,
   progressive, CMYK, 12-bit: nothing V1 writes) — surfaces as that face's error, like any other analysis failure
   (reference :140-144). Reading and writing the files with Pillow/OpenCV instead is an explicit choice of the caller
   (``v5_gpu_codec = False``), never something the node decides on its own.
 Optional state keys (defaults = the reference's literals): ``v5_quality`` 90, ``v5_max_faces`` 3, ``v5_device`` 0,
   ``v5_gpu_fft`` True (False: the reference's NumPy spectrum), ``v5_gpu_codec`` True (False: Pillow/OpenCV read and write the
-  files), ``v5_keep_temp_jpeg`` False (the reference's scratch file, which nothing reads, is written only on request). The
+  files), ``v5_keep_temp_jpeg`` True (the reference always leaves its scratch file behind, :66-67; nothing reads it, so a
+  caller that does not want it may switch it off). The
   V5F v1 statistics of every analysed face are attached as ``ela_features`` to ``texture_ela_details`` entries and
   ``V5_debug.json`` (lr_node reads only ``avg_score``).
 Host side, unchanged: the OpenAI call.
@@ -100,7 +101,7 @@ def _gpu_artefacts(crop_path, rank, ela_dir, state):
     device = int(state.get("v5_device", 0))
     gpu_codec = bool(state.get("v5_gpu_codec", True))
     rgb, gray = _read_crop(crop_path, device, gpu_codec)
-    if state.get("v5_keep_temp_jpeg", False):
+    if state.get("v5_keep_temp_jpeg", True):
         _write_jpeg(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), rgb, quality, device, gpu_codec)
 
     records, _, enhanced = v5host.analyze_frames_host(rgb[None], quality=quality, want_enhanced=True, device=device)

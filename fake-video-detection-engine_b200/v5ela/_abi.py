@@ -15,7 +15,10 @@ EXPORTS = (
     "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
     "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host", "v5ela_jpeg_bound", "v5ela_jpeg_encode",
     "v5ela_jpeg_encode_host", "v5ela_jpeg_info", "v5ela_jpeg_info_batch", "v5ela_jpeg_decode", "v5ela_jpeg_decode_host",
+    "v5ela_last_instantiation", "v5ela_set_block_stage", "v5ela_get_block_stage",
 )
+BLOCK_STAGES = {"smem": 0, "mma": 1}
+INSTANTIATIONS = {0: "general", 1: "fast", 2: "texhist", -1: None}
 
 
 class V5ElaError(RuntimeError):
@@ -70,6 +73,9 @@ def load() -> ctypes.CDLL:
     lib.v5ela_jpeg_decode_host.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.v5ela_profile_enable.argtypes = [vp, i32]
     lib.v5ela_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
+    lib.v5ela_last_instantiation.argtypes = [vp]
+    lib.v5ela_set_block_stage.argtypes = [vp, i32]
+    lib.v5ela_get_block_stage.argtypes = [vp]
     lib.v5ela_launch_count.restype = i64
     lib.v5ela_launch_count.argtypes = [vp]
     for name in EXPORTS:
@@ -172,6 +178,21 @@ class Handle:
         ms, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
         self._check(self._lib.v5ela_profile_read(self._h, ctypes.byref(ms), ctypes.byref(cnt), 1 if reset else 0))
         return ms.value, cnt.value
+
+    @property
+    def last_instantiation(self):
+        """'general' | 'fast' | 'texhist' — the fused-kernel instantiation the last analyze call launched (None before any)."""
+        return INSTANTIATIONS[int(self._lib.v5ela_last_instantiation(self._h))]
+
+    @property
+    def block_stage(self) -> str:
+        """'smem' | 'mma' — which build of the fused kernel's 8x8 block stage this handle launches (include/v5ela.h)."""
+        v = int(self._lib.v5ela_get_block_stage(self._h))
+        return {n: k for k, n in BLOCK_STAGES.items()}[v]
+
+    @block_stage.setter
+    def block_stage(self, name: str):
+        self._check(self._lib.v5ela_set_block_stage(self._h, BLOCK_STAGES[name]))
 
     @property
     def launch_count(self) -> int:

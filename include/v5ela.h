@@ -211,6 +211,31 @@ V5ELA_API int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *file
 V5ELA_API int v5ela_profile_enable(v5ela_handle *h, int enable);
 V5ELA_API int v5ela_profile_read(v5ela_handle *h, double *fused_ms_sum, int64_t *fused_launches, int reset);
 
+/*
+ * Which instantiation of the fused kernel the most recent v5ela_analyze / v5ela_analyze_ex call on this handle launched
+ * (same arithmetic, different edge handling — csrc/v5ela_device.cuh): V5ELA_INST_GENERAL any size / stride / outputs,
+ * V5ELA_INST_FAST width % 16 == 0, 16-byte aligned frames, records only (every BASELINE.json config), V5ELA_INST_TEXHIST
+ * general + tex_hist. -1 before the first call. Tests and bench.py use it to prove which code they measured.
+ */
+#define V5ELA_INST_GENERAL 0
+#define V5ELA_INST_FAST 1
+#define V5ELA_INST_TEXHIST 2
+V5ELA_API int v5ela_last_instantiation(const v5ela_handle *h);
+
+/*
+ * The 8x8 block stage of the fused kernel (fDCT -> quantise -> dequantise -> IDCT) exists in two bit-identical builds:
+ *   V5ELA_BLOCKS_SMEM  four threads per block, ISLOW butterflies in registers, two shared-memory transposes (kernel v10);
+ *   V5ELA_BLOCKS_MMA   the four passes as int8 limb-split tensor-core contractions (mma.sync.m16n8k16, SASS IMMA), a warp per pair
+ *                      of blocks, everything in registers (csrc/v5ela_dctmma.cuh): 17 % fewer instructions per pixel.
+ * Which one is faster depends on the frame geometry; V5ELA_BLOCKS_DEFAULT is what a new handle uses. Results do
+ * not depend on the choice.
+ */
+#define V5ELA_BLOCKS_SMEM 0
+#define V5ELA_BLOCKS_MMA 1
+#define V5ELA_BLOCKS_DEFAULT V5ELA_BLOCKS_SMEM
+V5ELA_API int v5ela_set_block_stage(v5ela_handle *h, int mode);
+V5ELA_API int v5ela_get_block_stage(const v5ela_handle *h);
+
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches evidence). */
 V5ELA_API int64_t v5ela_launch_count(const v5ela_handle *h);
 

@@ -28,7 +28,7 @@ def line_map(so):
 def functions(path):
     out = []
     for i, t in enumerate(open(path).read().split("\n"), 1):
-        mm = re.match(r"^(?:V5_DEV|inline|__global__)\s+[\w\s\*&:<>]*?\b(\w+)\(", t)
+        mm = re.match(r"^(?:V5_DEV|V5_HOSTDEV|inline|__global__|__device__ __forceinline__)\s+[\w\s\*&:<>]*?\b(\w+)\(", t)
         if mm:
             out.append((i, mm.group(1)))
     return out
@@ -41,7 +41,7 @@ def main(rep, so, px=None):
     lm = line_map(so)
     base = int(rows[2][ia], 16)
     csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(so))), "csrc")
-    fn = {f: functions(os.path.join(csrc, f)) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh")}
+    fn = {f: functions(os.path.join(csrc, f)) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_dctmma.cuh")}
     ex, sm, ops = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
     tot_e = tot_s = 0
     for r in rows[2:]:

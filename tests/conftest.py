@@ -35,3 +35,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(params=["smem", "mma"])
+def block_stage(request):
+    """Runs a GPU test once per build of the fused kernel's block stage (include/v5ela.h v5ela_set_block_stage): the calling
+    thread's cached handle is switched for the duration of the test."""
+    import torch
+    from v5ela.batch import get_handle
+
+    hd = get_handle(torch.cuda.current_device())
+    old = hd.block_stage
+    hd.block_stage = request.param
+    yield request.param
+    hd.block_stage = old

@@ -17,6 +17,9 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
     v5::KParams p;
     if (v5::fill_params(p, rgb, n, h, w, frame_stride, row_stride, records, residual, quality, seg_rows) != 0) return -1;
     p.tex_hist = tex_hist;
+    static v5::mma::LaneConsts lane_consts[32];
+    if (!v5::mma::make_lane_consts(lane_consts)) return -2;
+    p.lane_consts = lane_consts;
     memset(records, 0, sizeof(v5ela_record) * (size_t)n);
     if (tex_hist) memset(tex_hist, 0, sizeof(uint32_t) * 256 * (size_t)n);
     v5::Smem *S = (v5::Smem *)aligned_alloc(16, sizeof(v5::Smem));
@@ -31,6 +34,12 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
     for (int i = 0; i < n; i++) v5::finalize_record(records[i]);
     free(S);
     return 0;
+}
+
+// 16-bit hand-offs of the block stage (int16 pairs / 8-bit limb pairs) that left their range, since the library was loaded
+extern "C" long long v5emu_range_violations(void)
+{
+    return v5::range_violations();
 }
 
 extern "C" int v5emu_quant_selftest(void)

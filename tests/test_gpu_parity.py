@@ -11,7 +11,7 @@ from oracle import c_oracle, pil_oracle
 from v5ela.records import as_records, features
 from v5ela.synth import gen_batch, gen_batch_torch, gen_frame
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("block_stage")]   # every test under both block-stage builds
 
 FRAMES = load_json("frames_golden.json")
 

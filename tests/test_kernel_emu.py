@@ -16,18 +16,22 @@ from v5ela.synth import gen_frame
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_rows_split"])
+@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_rows_split", "2cta_mma", "2cta_mma_np2", "3cta_mma"])
 def emu(request):
     """The default layout (2 CTAs/SM, double-buffered RGB), the -DV5_MIN_CTAS=3 single-buffer layout, and the default layout
     with the two compile-time variants of the width-multiple-of-16 instantiation flipped (one row per residual unit instead
-    of two, split barrier on)."""
+    of two, split barrier on); "_mma": the tensor-core block stage (csrc/v5ela_dctmma.cuh, the library's second build of the
+    kernel) with the m16n8k16 fragment layout emulated lane by lane, one or two pairs of blocks in flight per warp."""
     variant = request.param
     so = os.path.join(HERE, "emu", f"libv5ela_emu_{variant}.so")
     src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
     csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("v5ela_device.cuh", "v5ela_dctmma.cuh", "v5ela_workitem.cuh", "v5ela_host.h")]
+    deps.append(__file__)
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         extra = ["-DV5_PAIR_ROWS=0", "-DV5_SPLIT_BARRIER=1"] if variant.endswith("rows_split") else []
+        if "_mma" in variant:
+            extra += ["-DV5_MMA_BLOCKS=1", "-DV5_MMA_NP=2" if variant.endswith("np2") else "-DV5_MMA_NP=1"]
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}", *extra,
                                "-I", os.path.join(ROOT, "include"), "-I", csrc, src, "-o", so])
     lib = ctypes.CDLL(so)
@@ -121,3 +125,66 @@ def test_emulated_kernel_vs_reference_goldens(emu):
         recs, res = emu(golden_frame(case)[None], case["q"])
         assert sha(res[0]) == case["resid_sha"]
         assert record_matches_golden(recs[0], case) == []
+
+
+def adversarial_blocks_frame(rng=None):
+    """A frame whose 8x8 blocks drive the intermediates of the round trip to their extremes: for every pair (u, v) the sign
+    pattern of the 2-D basis function (u, v) at full swing (0 / 255) and its negative — these maximise the forward row / column
+    outputs and, at coarse tables, the quantisation error that the inverse column pass amplifies — plus the rounded cosine itself,
+    single-pixel impulses, and all of it again per channel in saturated colours (chroma blocks see the same patterns)."""
+    import math
+
+    blocks = []
+    for u in range(8):
+        for v in range(8):
+            cu = [math.cos((2 * x + 1) * u * math.pi / 16) for x in range(8)]
+            cv = [math.cos((2 * y + 1) * v * math.pi / 16) for y in range(8)]
+            sign = np.array([[255 if cu[x] * cv[y] >= 0 else 0 for x in range(8)] for y in range(8)], np.uint8)
+            cosb = np.array([[int(round(127.5 + 127.5 * cu[x] * cv[y])) for x in range(8)] for y in range(8)], np.uint8)
+            blocks += [sign, 255 - sign, cosb, 255 - cosb]
+    for k in range(8):
+        imp = np.zeros((8, 8), np.uint8)
+        imp[k, 7 - k] = 255
+        blocks += [imp, 255 - imp]
+    n = len(blocks)                                       # 272 luma blocks -> 17 x 16 blocks
+    cols = 16
+    rows = (n + cols - 1) // cols
+    plane = np.zeros((8 * rows, 8 * cols), np.uint8)
+    for i, b in enumerate(blocks):
+        plane[8 * (i // cols):8 * (i // cols) + 8, 8 * (i % cols):8 * (i % cols) + 8] = b
+    gray = np.repeat(plane[..., None], 3, axis=2)
+    # chroma sees 2x2-averaged planes: upscale the patterns by two so that the chroma blocks get the same extremes
+    big = np.kron(plane, np.ones((2, 2), np.uint8))
+    col = np.zeros(big.shape + (3,), np.uint8)
+    col[..., 0] = big                                     # red swings: Cr (and Cb) at full range
+    col[..., 2] = 255 - big
+    return gray, col
+
+
+@pytest.mark.parametrize("q", [1, 2, 25, 50, 90, 100])
+def test_adversarial_ranges_of_the_int16_hand_offs(emu, q):
+    """The block stage hands 16-bit intermediates from pass to pass (shared-memory int16 pairs in one build, 8-bit limb pairs in
+    the tensor-core build): |forward row output| <= 4096, |coefficient| <= 8192 (the exact division's domain), |inverse column
+    output| <= 21047 must hold for blocks built to maximise them, at the coarsest (q=1, T=255) and the finest
+    (q=100, T=1) tables — a silent wrap would be a parity bug. The tensor-core emulation counts every violation; both builds
+    must reproduce Pillow bit for bit."""
+    from oracle import pil_oracle
+
+    for frame in adversarial_blocks_frame():
+        rec, resid = pil_oracle.record(frame, q, with_residual=True)
+        recs, res = emu(frame[None], q, 0)
+        assert np.array_equal(res[0], resid)
+        assert recs[0].tobytes() == rec.tobytes()
+        if frame.shape[1] % 16 == 0:
+            fast, _ = emu(frame[None], q, 0, want_residual=False)
+            assert fast[0].tobytes() == rec.tobytes()
+    emu.lib.v5emu_range_violations.restype = __import__("ctypes").c_longlong
+    assert emu.lib.v5emu_range_violations() == 0
+
+
+def test_no_range_violations_after_the_whole_module(emu):
+    """Runs last: everything this module pushed through the tensor-core emulation stayed inside the limb ranges."""
+    import ctypes
+
+    emu.lib.v5emu_range_violations.restype = ctypes.c_longlong
+    assert emu.lib.v5emu_range_violations() == 0

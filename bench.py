@@ -1,25 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — 1080p keyframes/s of the V5 ELA+texture hot path on N B200s (BASELINE.json metric), one JSON line.
+"""bench.py — keyframes/s of the V5 ELA+texture hot path on N B200s (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # N=1: plain python; N>1: launched under torchrun
-    python bench.py --impl reference [...]                          # the reference's CPU path on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]     # N=1: plain python; N>1: launched under torchrun
+    python bench.py --impl reference [...]                                # the reference's CPU path on the host cores
 
-A step = one pass of the hot path over one batch of 256 synthetic 1920x1080 RGB keyframes per GPU at JPEG q=90
-(BASELINE.json configs[1]; weak scaling: every rank owns its own 256 frames), records-only mode, followed for N>1 by
-the NCCL gather of the per-frame records to rank 0.
-  value     : whole-job frames/s with inputs resident in HBM (CUDA events, max over ranks).
-  e2e       : same metric through the reference-facing C-ABI call with HOST (pinned) buffers — the H2D copy of every
-              frame and the D2H copy of the records are inside the timed region.
-  roofline  : fused kernel only — algorithmic bytes (3*H*W + 3144 per frame) / its CUDA-event duration, against the
-              measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  e2e_from_jpeg_files : (N=1, extra) the same work starting from JPEG files in host memory — GPU decode + analyse.
-  cpu_baseline : the oracle port of the reference's ELA core (Pillow/libjpeg-turbo + NumPy/OpenCV statistics) on all
-              host cores, on a bounded sample of the same frames. Reported, not the target.
+--config selects one of BASELINE.json's five configurations (default 2, the one the metric is quoted on):
+  1  16 x 1280x720, q=90, per GPU (the reference's own CPU-runnable case)                          weak
+  2  256 x 1920x1080, q=90, per GPU                                                                  weak
+  3  1024 x 3840x2160, q=90, sharded over the N GPUs                                                 strong
+  4  64 videos x 32 keyframes of 1080p, whole videos per rank, per-video records gathered by NCCL   strong
+  5  512 x 1080p at q in {75, 85, 90, 95} (four passes per step), sharded over the N GPUs           strong
+A step = one pass of the hot path over the configuration's batch, records-only mode, followed for N>1 by the NCCL gather of the
+per-frame (config 4: per-video) records to rank 0.
+  value     : whole-job frames/s with inputs resident in HBM (CUDA events, max over ranks). The timed region runs at least
+              --min-seconds (default 1 s): `steps` is what was timed (>= the --steps asked for), `timed_region_s` its length.
+  e2e       : the same metric through the reference-facing C-ABI call with HOST (pinned) buffers — the H2D copy of every frame and
+              the D2H copy of the records are inside the timed region; `ceiling_frames_s` = what a bare pinned cudaMemcpyAsync of
+              the same bytes reaches on this rank at the same moment (all ranks copying concurrently), `per_rank_ms` every rank's time.
+  roofline  : fused kernel only — algorithmic bytes (3*H*W + 3144 per frame) / its CUDA-event duration against the measured HBM
+              copy bandwidth in MEASURED_PEAKS.json; `int_issue_frac` = the issue-slot utilisation ncu measured (the resource that
+              binds the kernel), tagged with the hash of the sources it was profiled on.
+  parity    : untimed spot-check of the timed call's records against the C oracle (oracle/ is only ever the checker).
+  e2e_from_jpeg_files : (config 2) the same work starting from JPEG files in host memory — GPU decode + analyse.
+  cpu_baseline : (N=1) the oracle port of the reference's ELA core (Pillow/libjpeg-turbo + NumPy/OpenCV statistics) on all host
+              cores, on a bounded sample of the same frames. Reported, not the target.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -44,24 +55,61 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-METRIC = "1080p_keyframes_per_sec_v5_ela_texture"
 UNIT = "frames/s"
-FRAMES_PER_GPU, H, W, QUALITY = 256, 1080, 1920, 90
 RECORD_BYTES = 3144
-BYTES_PER_FRAME = 3 * H * W + RECORD_BYTES          # algorithmic bytes, SURVEY.md §8d
-HBM_TRAFFIC_NCU = None                              # per-launch dram bytes from profiles/ (filled by load_ncu_traffic)
+
+# name -> (frames, H, W, qualities, scaling, group, description); `frames` is per GPU for weak configurations, total for strong ones
+CONFIGS = {
+    1: dict(frames=16, h=720, w=1280, q=(90,), scaling="weak", group=0, metric="720p_keyframes_per_sec_v5_ela_texture",
+            what="16 synthetic 1280x720 RGB keyframes per GPU, JPEG q=90 — BASELINE.json configs[0]"),
+    2: dict(frames=256, h=1080, w=1920, q=(90,), scaling="weak", group=0, metric="1080p_keyframes_per_sec_v5_ela_texture",
+            what="256 synthetic 1920x1080 RGB keyframes per GPU, JPEG q=90 — BASELINE.json configs[1]"),
+    3: dict(frames=1024, h=2160, w=3840, q=(90,), scaling="strong", group=0, metric="4k_keyframes_per_sec_v5_ela_texture",
+            what="1024 synthetic 3840x2160 RGB keyframes sharded over the GPUs, JPEG q=90 — BASELINE.json configs[2]"),
+    4: dict(frames=2048, h=1080, w=1920, q=(90,), scaling="strong", group=32, metric="1080p_keyframes_per_sec_v5_ela_texture",
+            what="64 synthetic 1080p videos x 32 keyframes (video v frame k = gen_frame(32v+k, seed=v)), whole videos per GPU, per-video "
+                 "records reduced on the device and gathered by NCCL — BASELINE.json configs[3]"),
+    5: dict(frames=512, h=1080, w=1920, q=(75, 85, 90, 95), scaling="strong", group=0, metric="1080p_keyframes_per_sec_v5_ela_texture",
+            what="512 synthetic 1920x1080 RGB keyframes sharded over the GPUs, analysed at JPEG q in {75, 85, 90, 95} (four passes per "
+                 "step; value counts frame-analyses) — BASELINE.json configs[4]"),
+}
 
 
-def workload_config(n_gpus: int) -> dict:
+def local_range(cfg: dict, rank: int, world: int):
+    """[lo, hi) of the configuration's frames this rank owns."""
+    from v5ela.shard import shard_range, shard_videos
+
+    if cfg["scaling"] == "weak":
+        return rank * cfg["frames"], (rank + 1) * cfg["frames"]
+    if cfg["group"]:
+        return shard_videos(cfg["frames"] // cfg["group"], cfg["group"], rank, world)
+    return shard_range(cfg["frames"], rank, world)
+
+
+def workload_config(cid: int, n_gpus: int) -> dict:
+    cfg = CONFIGS[cid]
+    total = cfg["frames"] * (n_gpus if cfg["scaling"] == "weak" else 1)
+    per_gpu_bytes = 3 * cfg["h"] * cfg["w"] * (cfg["frames"] if cfg["scaling"] == "weak" else math.ceil(cfg["frames"] / n_gpus))
     return {
-        "workload": f"{FRAMES_PER_GPU} synthetic {W}x{H} RGB keyframes per GPU (gen_frame, SURVEY App. B), JPEG q={QUALITY}, "
-                    "records-only — BASELINE.json configs[1]",
-        "frames_per_gpu": FRAMES_PER_GPU, "height": H, "width": W, "quality": QUALITY,
-        "global_frames": FRAMES_PER_GPU * n_gpus,
-        "l2": "inputs (1.59 GB per GPU) are larger than the 126 MB L2; no flush needed",
-        "sharding": "by frame, contiguous per rank; one NCCL gather of 3144-byte records to rank 0 per step" if n_gpus > 1
-                    else "single GPU",
+        "workload": cfg["what"] + " (gen_frame, SURVEY App. B), records-only",
+        "baseline_config": cid, "height": cfg["h"], "width": cfg["w"], "quality": list(cfg["q"]) if len(cfg["q"]) > 1 else cfg["q"][0],
+        "global_frames": total, "frame_analyses_per_step": total * len(cfg["q"]), "group_size": cfg["group"],
+        "l2": f"inputs ({per_gpu_bytes / 1e9:.2f} GB per GPU) " + ("are larger than the 126 MB L2; no flush needed" if per_gpu_bytes > 126e6 * 2
+                                                                  else "fit the 126 MB L2: a 256 MB buffer is overwritten between timed steps"),
+        "sharding": ("by frame, contiguous per rank" if not cfg["group"] else "by video, contiguous per rank") +
+                    ("; one NCCL gather of 3144-byte records to rank 0 per step" if n_gpus > 1 else "; single GPU"),
     }
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources the library is built from (what a profile has to match to describe this build)."""
+    h = hashlib.sha256()
+    csrc = os.path.join(PKG, "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference arm
@@ -79,55 +127,62 @@ def _cpu_init(frames):
         pass
 
 
-def _cpu_work(i):
+def _cpu_work(job):
     from oracle import pil_oracle
 
-    rec = pil_oracle.ela_core(_CPU_FRAMES[i % len(_CPU_FRAMES)], QUALITY)
+    i, q = job
+    rec = pil_oracle.ela_core(_CPU_FRAMES[i % len(_CPU_FRAMES)], q)
     return int(rec["ela_sum"][0])
 
 
-def cpu_reference_rate(sample_frames: int, repeats: int = 1, warmup: int = 0):
-    """Frames/s of the reference's CPU ELA core (+ §8a statistics) with one process per host core."""
+def cpu_reference_rate(cid: int, frames_per_step: int, repeats: int = 1, warmup: int = 0, distinct: int = 8):
+    """Frame-analyses/s of the reference's CPU ELA core (+ §8a statistics) with one process per host core."""
     import multiprocessing as mp
 
     from oracle import pil_oracle
     from v5ela.synth import gen_frame
 
+    cfg = CONFIGS[cid]
     cores = os.cpu_count() or 1
-    distinct = [gen_frame(i, H, W, 0) for i in range(min(8, sample_frames))]
+    pics = [gen_frame(i, cfg["h"], cfg["w"], 0) for i in range(min(distinct, frames_per_step))]
+    jobs = [(i, q) for q in cfg["q"] for i in range(frames_per_step)]
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(distinct,)) as pool:
-        pool.map(_cpu_work, range(cores))                       # spin the workers up
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(pics,)) as pool:
+        pool.map(_cpu_work, [(i, cfg["q"][0]) for i in range(cores)])           # spin the workers up
         for _ in range(warmup):
-            pool.map(_cpu_work, range(sample_frames), chunksize=1)
+            pool.map(_cpu_work, jobs, chunksize=1)
         times = []
         for _ in range(max(1, repeats)):
             t0 = time.perf_counter()
-            pool.map(_cpu_work, range(sample_frames), chunksize=1)
+            pool.map(_cpu_work, jobs, chunksize=1)
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return sample_frames * len(times) / total, cores, total / len(times), pil_oracle.versions()
+    return len(jobs) * len(times) / total, cores, total / len(times), pil_oracle.versions()
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 4 * (os.cpu_count() or 1)                          # per step: a few frames per core (~1-2 s per step)
-    fps, cores, step_s, versions = cpu_reference_rate(sample, repeats=args.steps, warmup=min(args.warmup, 1))
+    cfg = CONFIGS[args.config]
+    # one step = the configuration's per-GPU batch, as in the native arm, bounded to ~256 frames of 1080p worth of CPU work
+    budget_px = 256 * 1080 * 1920
+    per_step = max(16, min(cfg["frames"], budget_px // (cfg["h"] * cfg["w"] * len(cfg["q"]))))
+    steps = max(1, min(args.steps, 8))                          # ~2 s of CPU work per step on 16 cores: the arm ends within minutes
+    fps, cores, step_s, versions = cpu_reference_rate(args.config, per_step, repeats=steps, warmup=min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {**workload_config(args.gpus),
-                   "note": "reference arm: the reference's own operations (v5_texture_ela.py:66-73: PIL save q=90 -> open -> "
-                           "ImageChops.difference -> getextrema) + NumPy/OpenCV record statistics, one process per host core; "
-                           "the reference module itself is pure Python over Pillow and is not present on the GPU box",
-                   "libraries": versions},
+        "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args.config, args.gpus),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames of {W}x{H} per step x {args.steps} steps"},
+                         "sample": f"{per_step} frames of {cfg['w']}x{cfg['h']} per step x {len(cfg['q'])} qualities x {steps} steps "
+                                   "(8 distinct gen_frame pictures cycled)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "reference arm: the reference's own operations (v5_texture_ela.py:66-73: PIL save q -> open -> ImageChops.difference -> "
+                "getextrema) + NumPy/OpenCV record statistics, one process per host core; the reference module itself is pure Python "
+                "over Pillow and is not present on the GPU box",
+        "libraries": versions,
     }
     emit(line)
     return 0
@@ -179,23 +234,9 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def load_ncu_traffic():
-    """Per-launch DRAM bytes of the fused kernel from the committed ncu summary (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "fused_kernel_dram.json")
+def load_profile_json(name: str):
     try:
-        with open(path) as f:
-            d = json.load(f)
-        if d.get("frames_per_launch") == FRAMES_PER_GPU and d.get("height") == H and d.get("width") == W:
-            return float(d["dram_bytes_per_launch"])
-        return float(d["dram_bytes_per_frame"]) * FRAMES_PER_GPU
-    except Exception:
-        return None
-
-
-def load_issue_stats():
-    """ncu-measured issue-slot figures of the fused kernel (the resource that actually binds it), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "fused_kernel_issue.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             return json.load(f)
     except Exception:
         return None
@@ -209,6 +250,19 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def set_affinity(local_rank: int) -> dict:
+    """Run (and first-touch the pinned host buffers) on the CPU cores next to this rank's GPU: matters for `e2e` at N > 1."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return {"ok": True, "cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:  # reported, not hidden: the e2e figure at N > 1 depends on it
+        return {"ok": False, "error": repr(e)[:200], "cpus": len(os.sched_getaffinity(0))}
+
+
 # ---------------------------------------------------------------------------------------------------------- GPU arm
 def run_native_arm(args):
     import torch
@@ -216,79 +270,112 @@ def run_native_arm(args):
 
     import v5ela
     from v5ela import _abi
-    from v5ela.batch import analyze_batch, get_handle
+    from v5ela.batch import analyze_batch, get_handle, reduce_records
+    from v5ela.records import as_records, combine
     from v5ela.shard import gather_records
 
+    cid = args.config
+    cfg = CONFIGS[cid]
+    H, W, quals, group = cfg["h"], cfg["w"], cfg["q"], cfg["group"]
+    bytes_per_frame = 3 * H * W + RECORD_BYTES                  # algorithmic bytes, SURVEY.md §8d
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cpu_baseline = None
     if world == 1 and not args.no_cpu:                          # before CUDA is initialised: the pool forks
-        sample = 8 * (os.cpu_count() or 1)
-        fps, cores, _, versions = cpu_reference_rate(sample_frames=sample, repeats=1)
+        sample = max(16, min(8 * (os.cpu_count() or 1), (128 * 1080 * 1920) // (H * W)))
+        fps, cores, _, versions = cpu_reference_rate(cid, sample, repeats=1)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{sample} frames of {W}x{H} (gen_frame), oracle/pil_oracle.ela_core = the reference's "
-                                  "v5_texture_ela.py:66-73 calls + record statistics, one process per core",
+                        "sample": f"{sample} frames of {W}x{H} (gen_frame) x {len(quals)} qualities, oracle/pil_oracle.ela_core = the "
+                                  "reference's v5_texture_ela.py:66-73 calls + record statistics, one process per core",
                         "libraries": versions}
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU implementation (use --impl reference)")
     _abi.load()
-    try:    # run (and first-touch the pinned host buffers) on the CPU cores next to this rank's GPU: matters for `e2e` at N > 1
-        import pynvml
-
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-    except Exception:
-        pass
+    affinity = set_affinity(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
 
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
-    n_gpus = world
-    K, Wm = args.steps, args.warmup
-    n_local, total = FRAMES_PER_GPU, FRAMES_PER_GPU * world
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    lo, hi = local_range(cfg, rank, world)
+    n_local = hi - lo
+    total = cfg["frames"] * (world if cfg["scaling"] == "weak" else 1)
+    total_records = total // group if group else total
 
-    frames = v5ela.gen_batch_torch(rank * n_local, n_local, H, W, seed=0, device=dev)
-    records = torch.empty((n_local, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    if group:                                                   # config 4: video v frame k = gen_frame(32 v + k, seed = v)
+        frames = torch.cat([v5ela.gen_batch_torch(group * v, group, H, W, seed=v, device=dev) for v in range(lo // group, hi // group)]) \
+            if n_local else torch.empty((0, H, W, 3), dtype=torch.uint8, device=dev)
+    else:
+        frames = v5ela.gen_batch_torch(lo, n_local, H, W, seed=0, device=dev)
+    records = torch.empty((len(quals), n_local, RECORD_BYTES), dtype=torch.uint8, device=dev)
     handle = get_handle(local_rank)
+    if args.block_stage:
+        handle.block_stage = args.block_stage
+    small = n_local * 3 * H * W < 2 * 126e6
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+    gathered = [None]
 
     def step():
-        analyze_batch(frames, quality=QUALITY, records_out=records, handle=handle)
-        return gather_records(records, total) if world > 1 else records
+        for qi, q in enumerate(quals):
+            analyze_batch(frames, quality=q, records_out=records[qi], handle=handle)
+            recs = reduce_records(records[qi], group, handle=handle) if group else records[qi]
+            gathered[0] = gather_records(recs, total_records) if world > 1 else recs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(Wm, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
+
+    # ---- step-time estimate -> number of timed steps (at least --steps, at least --min-seconds)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    barrier()
+    est = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    K = max(args.steps, int(math.ceil(args.min_seconds * 1e3 / max(float(est.item()), 1e-3))))
+    K = min(K, 200000 if not small else 4000)                   # L2-sized inputs: one event pair and one flush per step
 
     # ---- device-resident throughput (value) + fused-kernel duration (roofline), clocks sampled during the region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     handle.profile_enable(True)
     handle.profile_read(reset=True)
     launches0 = handle.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    if flush is None:
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    else:                                                       # inputs fit the L2: evict them between timed steps, time each step
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = handle.launch_count - launches0
     fused_ms, fused_n = handle.profile_read(reset=True)
     handle.profile_enable(False)
-    # keep the GPU busy a little longer so that slow nvidia-smi polling still sees the load (local work only: the number
-    # of iterations depends on the wall clock, so no collective may be issued here)
-    t_end = time.perf_counter() + 0.6
-    while time.perf_counter() < t_end:
-        analyze_batch(frames, quality=QUALITY, records_out=records, handle=handle)
+    inst = handle.last_instantiation
+    # keep the GPU busy a little longer so that slow nvidia-smi polling still sees the load (local work only)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end and n_local:
+        analyze_batch(frames, quality=quals[0], records_out=records[0], handle=handle)
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -296,43 +383,90 @@ def run_native_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
-    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory)
-    host_frames = torch.empty((n_local, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    host_frames.copy_(frames)
-    host_records = torch.empty((n_local, RECORD_BYTES), dtype=torch.uint8, pin_memory=True)
+    # ---- untimed parity spot-check of what was just timed, against the C oracle (rank 0)
+    parity = None
+    if rank == 0 and not args.no_parity and n_local:
+        from oracle import c_oracle
+
+        step()
+        torch.cuda.synchronize()
+        ok, checked = True, 0
+        if group:                                               # video 0: device aggregate == combine(oracle records of its frames)
+            host = frames[:group].cpu().numpy()
+            orecs, _ = c_oracle.analyze(host, quals[0])
+            agg = as_records((gathered[0] if world > 1 else reduce_records(records[0], group, handle=handle))[:1])
+            ok = agg[0].tobytes() == combine(orecs).tobytes() and as_records(records[0][:group]).tobytes() == orecs.tobytes()
+            checked = group
+        else:
+            picks = sorted({0, n_local // 3, (2 * n_local) // 3, n_local - 1})[: (2 if H * W > 4e6 else 4)]
+            for qi, q in enumerate(quals):
+                got = as_records(records[qi][picks])
+                for j, i in enumerate(picks):
+                    o = c_oracle.analyze_frame(frames[i].cpu().numpy(), q)
+                    ok = ok and got[j].tobytes() == o["record"].tobytes()
+                    checked += 1
+        parity = {"frames": checked, "vs": "c_oracle", "ok": bool(ok), "instantiation": inst, "block_stage": handle.block_stage}
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory), on a bounded part of the local shard
+    n_e2e = max(1, min(n_local, (4 << 30) // (3 * H * W)))
+    host_frames = torch.empty((n_e2e, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    host_frames.copy_(frames[:n_e2e])
+    host_records = torch.empty((n_e2e, RECORD_BYTES), dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
-    Ke = max(2, min(K, 10))
     stream = torch.cuda.current_stream(dev).cuda_stream
+    handle.set_quality(quals[0])
 
     def e2e_step():
-        handle.analyze_host(host_frames.data_ptr(), n_local, H, W, host_records.data_ptr(), None, None, stream)
+        handle.analyze_host(host_frames.data_ptr(), n_e2e, H, W, host_records.data_ptr(), None, None, stream)
         if world > 1:
-            recs = host_records.to(dev, non_blocking=True)      # records already on the host: gather via device
-            gather_records(recs, total)
+            gather_records(host_records.to(dev, non_blocking=True), n_e2e * world)   # every rank holds n_e2e records
 
     for _ in range(2):
         e2e_step()
+    barrier()
+    e0.record()
+    e2e_step()
+    e1.record()
+    barrier()
+    Ke = max(2, min(50, int(math.ceil(min(args.min_seconds, 1.0) * 1e3 / max(e0.elapsed_time(e1), 1e-3)))))
     barrier()
     e0.record()
     for _ in range(Ke):
         e2e_step()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    e2e_local_ms = e0.elapsed_time(e1)
+    ok_e2e = bool(torch.equal(host_records, records[0][:n_e2e].cpu()))
+    # the ceiling of that path: the same bytes through a bare pinned copy, every rank at the same time
+    dst = torch.empty_like(host_frames, device=dev)
+    dst.copy_(host_frames, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(3):
+        dst.copy_(host_frames, non_blocking=True)
+    e1.record()
+    barrier()
+    h2d_ms = e0.elapsed_time(e1) / 3
+    del dst
+    per_rank = torch.tensor([e2e_local_ms, h2d_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    ok_e2e = bool(torch.equal(host_records, records.cpu()))
+        allr = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(allr, per_rank)
+    else:
+        allr = [per_rank]
+    e2e_ms = max(float(x[0]) for x in allr)
+    h2d_ms_max = max(float(x[1]) for x in allr)
 
     # ---- the same work starting from JPEG FILES in host memory, the form V1 hands keyframes/crops over in
     # (cv2.imwrite default quality 95, v1_keyframes_facetrack.py:112,166): only compressed bytes cross PCIe; the GPU
-    # decodes, analyses, and the records come back. N=1 only (an extra figure, not the headline).
+    # decodes, analyses, and the records come back. Config 2 only.
     files_leg = None
-    if world == 1:
+    if cid == 2 and not args.no_files:
         try:
             from v5ela import jpeg
             from v5ela.batch import analyze_jpeg_files
 
+            os.environ.setdefault("V5ELA_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
             enc, enc_sizes = jpeg.encode_batch(frames, 95)                  # warm-up (workspace allocation), then timed once
             torch.cuda.synchronize()
             del enc, enc_sizes                                              # let the timed call reuse the 1.6 GB output block
@@ -353,23 +487,29 @@ def run_native_arm(args):
                 arena_np[offs[i]:offs[i] + enc_sizes[i]] = enc[i, :enc_sizes[i]]
                 blobs.append(arena_np[offs[i]:offs[i] + int(enc_sizes[i])])
             del enc
-            Kf = max(2, min(K, 5))
+            host_recs_f = torch.empty((n_local, RECORD_BYTES), dtype=torch.uint8, pin_memory=True)
             out = None
             for _ in range(2):
-                out = analyze_jpeg_files(blobs, quality=QUALITY, device=dev)
-                host_records.copy_(out["records"], non_blocking=True)
+                out = analyze_jpeg_files(blobs, quality=quals[0], device=dev)
+                host_recs_f.copy_(out["records"], non_blocking=True)
             torch.cuda.synchronize()
-            same = bool(torch.equal(analyze_batch(out["rgb"], quality=QUALITY)["records"].cpu(), host_records))
+            same = bool(torch.equal(analyze_batch(out["rgb"], quality=quals[0])["records"].cpu(), host_recs_f))
+            Kf = max(3, min(K, 12))
+            barrier()
             t0 = time.perf_counter()
             for _ in range(Kf):
-                out = analyze_jpeg_files(blobs, quality=QUALITY, device=dev)
-                host_records.copy_(out["records"], non_blocking=True)
+                out = analyze_jpeg_files(blobs, quality=quals[0], device=dev)
+                host_recs_f.copy_(out["records"], non_blocking=True)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            files_leg = {"value": n_local * Kf / dt, "unit": UNIT, "steps": Kf,
+            dt_local = time.perf_counter() - t0
+            tt = torch.tensor([dt_local], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            files_leg = {"value": n_local * world * Kf / dt, "unit": UNIT, "steps": Kf,
                          "h2d_bytes_per_step": int(sum(len(b) for b in blobs)), "d2h_bytes_per_step": n_local * RECORD_BYTES,
-                         "input": f"{n_local} JPEG files (4:2:0, quality 95, mean {sum(len(b) for b in blobs) / n_local / 1e3:.0f} kB) "
-                                  "in one pinned host arena; header parsing on the host, wall clock",
+                         "input": f"{n_local} JPEG files per GPU (4:2:0, quality 95, mean {sum(len(b) for b in blobs) / n_local / 1e3:.0f} kB) "
+                                  "in one pinned host arena; header parsing on the host, wall clock, max over ranks",
                          "decode_status_ok": bool((out["status"] == 0).all().item()), "records_match_decoded_frames": same,
                          "files_written_by": "v5ela_jpeg_encode on the GPU (== cv2.imwrite's bytes), device-resident frames in, "
                                              f"{encode_fps:.0f} files/s (not part of the timed region)",
@@ -380,29 +520,49 @@ def run_native_arm(args):
 
     if rank == 0:
         peak, peak_src = load_peak()
-        value = total * K / (ms_max * 1e-3)
+        analyses = total * len(quals)
+        value = analyses * K / (ms_max * 1e-3)
         kernel_ms = fused_ms / max(fused_n, 1)
-        achieved = n_local * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+        achieved = n_local * bytes_per_frame / (kernel_ms * 1e-3) / 1e9 if n_local else 0.0
+        issue = load_profile_json("fused_kernel_issue.json") or {}
+        dram = load_profile_json("fused_kernel_dram.json") or {}
+        cur_hash = source_hash()
+        traffic = None
+        if dram.get("dram_bytes_per_frame") and (dram.get("height"), dram.get("width")) == (H, W):
+            traffic = float(dram["dram_bytes_per_frame"]) * n_local
+        e2e_frames = n_e2e * world
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": max(Wm, 3),
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic", "config": workload_config(n_gpus),
-            "e2e": {"value": total * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": n_local * 3 * H * W, "d2h_bytes_per_step": n_local * RECORD_BYTES,
-                    "steps": Ke, "records_match_device_path": ok_e2e,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "steps_requested": args.steps,
+            "warmup": warm, "ms_per_step": ms_max / K, "timed_region_s": ms_max * 1e-3, "higher_is_better": True,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(cid, world),
+            "e2e": {"value": e2e_frames * Ke / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": n_e2e * 3 * H * W, "d2h_bytes_per_step": n_e2e * RECORD_BYTES,
+                    "frames_per_step_per_gpu": n_e2e, "steps": Ke, "records_match_device_path": ok_e2e,
+                    "ceiling_frames_s": e2e_frames / (h2d_ms_max * 1e-3),
+                    "ceiling": "bare pinned cudaMemcpyAsync of the same frames, all ranks concurrently, max over ranks "
+                               f"({n_e2e * 3 * H * W / h2d_ms_max / 1e6:.1f} GB/s per GPU on the slowest rank)",
+                    "per_rank_ms": [round(float(x[0]) / Ke, 3) for x in allr],
+                    "per_rank_h2d_gbs": [round(n_e2e * 3 * H * W / float(x[1]) / 1e6, 1) for x in allr],
+                    "affinity": affinity,
                     "api": "v5ela_analyze_host (C ABI, pinned host buffers, chunked copy/compute overlap)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_ncu_traffic(), "kernel": "v5::ela_fused_kernel", "kernel_ms": kernel_ms,
-                         "kernel_launches_timed": int(fused_n), "bytes_per_launch": n_local * BYTES_PER_FRAME,
+                         "traffic": traffic, "kernel": "ela_fused_kernel", "kernel_ms": kernel_ms,
+                         "kernel_launches_timed": int(fused_n), "bytes_per_launch": n_local * bytes_per_frame,
                          "peak_source": peak_src,
-                         "note": "integer-issue bound, not HBM bound: ~%d exact int32 thread-instructions per pixel "
-                                 "(DESIGN.md 4.4); int_issue = ncu figures of the committed profile"
-                                 % round(32 * ((load_issue_stats() or {}).get("warp_instructions_per_pixel") or 3.83)),
-                         "kernel_instantiation": "ela_fused_kernel<FAST=true, TEXHIST=false> (width % 16 == 0, records only)",
-                         "int_issue": load_issue_stats()},
+                         "kernel_instantiation": f"ela_fused_kernel<{inst}> ({'width % 16 == 0, aligned, records only' if inst == 'fast' else inst}), "
+                                                 f"block stage '{handle.block_stage}'",
+                         "int_issue_frac": (issue.get("issue_slots_busy_pct") or 0) / 100.0 or None,
+                         "int_issue": issue,
+                         "profile_source_hash": issue.get("source_hash"), "build_source_hash": cur_hash,
+                         "profile_matches_build": issue.get("source_hash") == cur_hash,
+                         "note": "integer-issue / latency bound, not HBM bound: ~%d exact int32 thread-instructions per pixel (DESIGN.md 4.4); "
+                                 "traffic, int_issue_frac and int_issue are ncu figures of the committed profile (profiles/), valid for this "
+                                 "build only if profile_matches_build" % round(32 * (issue.get("warp_instructions_per_pixel") or 3.67))},
         }
+        if parity is not None:
+            line["parity"] = parity
         if files_leg is not None:
             line["e2e_from_jpeg_files"] = files_leg
         if cpu_baseline is not None:
@@ -419,8 +579,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration 1..5 (default 2)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="minimum length of the timed region (steps are added to reach it)")
     ap.add_argument("--impl", choices=("native", "reference"), default="native")
+    ap.add_argument("--block-stage", choices=("smem", "mma"), default=None, help="build of the fused kernel's block stage (default: library's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot-check")
+    ap.add_argument("--no-files", action="store_true", help="skip the JPEG-files leg of config 2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

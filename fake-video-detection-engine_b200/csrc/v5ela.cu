@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(256) ela_reduce_kernel(const v5ela_record *rec
 {
     const v5ela_record *src = recs + (long long)blockIdx.x * group;
     v5ela_record &dst = out[blockIdx.x];
-    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-        uint32_t s = 0;
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {        // 32-bit bins: a group of more than 2^32 - 1 pixels saturates
+        unsigned long long s = 0;
         for (int k = 0; k < group; k++) s += (&src[k].ela_hist[0][0])[i];
-        (&dst.ela_hist[0][0])[i] = s;
+        (&dst.ela_hist[0][0])[i] = s > 0xffffffffull ? 0xffffffffu : (uint32_t)s;
     }
     if (threadIdx.x < 8) {                 // ela_sum[3], ela_sumsq[3], tex_sumabs, tex_sumsq are 8 consecutive u64
         unsigned long long s = 0;

@@ -279,6 +279,10 @@ void parallel_for(int n, size_t bytes_hint, Fn fn)
 {
     int nt = (int)std::thread::hardware_concurrency();
     nt = nt > 8 ? 8 : nt;
+    if (const char *env = getenv("V5ELA_HOST_THREADS")) {       // several processes per host (one per GPU): share the cores out
+        const int v = atoi(env);
+        if (v >= 1 && v < nt) nt = v;
+    }
     if (nt > n) nt = n;
     if (nt <= 1 || bytes_hint < ((size_t)4 << 20)) {
         for (int i = 0; i < n; i++) fn(i);

@@ -30,7 +30,7 @@ def as_records(raw) -> np.ndarray:
 def combine(records: np.ndarray) -> np.ndarray:
     """Host mirror of v5ela_reduce_records: one record aggregating `records` (sums add, maxima max)."""
     out = np.zeros((), dtype=RECORD_DTYPE)
-    out["ela_hist"] = records["ela_hist"].sum(axis=0, dtype=np.uint64).astype(np.uint32)
+    out["ela_hist"] = np.minimum(records["ela_hist"].sum(axis=0, dtype=np.uint64), 0xFFFFFFFF).astype(np.uint32)   # saturating, like the kernel
     for k in ("ela_sum", "ela_sumsq", "tex_sumabs", "tex_sumsq"):
         out[k] = records[k].sum(axis=0, dtype=np.uint64)
     out["tex_maxabs"] = records["tex_maxabs"].max()

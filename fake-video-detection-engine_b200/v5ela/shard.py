@@ -24,10 +24,15 @@ def shard_videos(n_videos: int, frames_per_video: int, rank: int, world: int) ->
     return v0 * frames_per_video, v1 * frames_per_video
 
 
+_recv_cache: dict = {}
+
+
 def gather_records(local, total: int, dst: int = 0, group=None):
     """Gather per-rank record tensors (n_local, 3144) uint8 to rank `dst` in rank order -> (total, 3144) or None.
 
-    Ranks may hold different counts (shard_range); shorter shards are padded to the longest for the collective.
+    Ranks may hold different counts (shard_range); shorter shards are padded to the longest for the collective. The receive
+    block on `dst` is allocated once per (world, longest, device) and reused: with equal shards (every BASELINE.json configuration
+    on 1/2/4/8 GPUs) the result is a view of it — no allocation and no concatenation per step; it is overwritten by the next call.
     """
     import torch
     import torch.distributed as dist
@@ -41,10 +46,18 @@ def gather_records(local, total: int, dst: int = 0, group=None):
     if local.shape[0] != longest:
         send = torch.zeros((longest, RECORD_BYTES), dtype=torch.uint8, device=local.device)
         send[: local.shape[0]] = local
-    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    bufs = None
+    if rank == dst:
+        key = (world, longest, str(local.device), id(group))
+        block = _recv_cache.get(key)
+        if block is None:
+            block = _recv_cache[key] = torch.empty((world, longest, RECORD_BYTES), dtype=torch.uint8, device=local.device)
+        bufs = list(block.unbind(0))
     dist.gather(send.contiguous(), bufs, dst=dst, group=group)
     if rank != dst:
         return None
+    if all(hi - lo == longest for lo, hi in counts):
+        return block.view(world * longest, RECORD_BYTES)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, counts)], dim=0)
 
 

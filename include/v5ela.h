@@ -121,6 +121,8 @@ V5ELA_API int v5ela_enhance(v5ela_handle *h, const uint8_t *d_residual, const vo
 /*
  * Per-group aggregation of records (per-video features, BASELINE.json config 4): out[g] = sum of histograms and sums,
  * max of maxima over records [g*group, (g+1)*group). n must be a multiple of `group`. d_out: (n/group) records.
+ * The histogram bins stay 32-bit: a bin that would exceed 2^32 - 1 (groups of more than ~2071 frames of 1080p) saturates at that
+ * value instead of wrapping; the 64-bit sums are exact.
  */
 V5ELA_API int v5ela_reduce_records(v5ela_handle *h, const void *d_records, int n, int group, void *d_out, void *cuda_stream);
 

@@ -6,7 +6,8 @@
 
 Video v, frame k = gen_frame(frames*v + k, H, W, seed=v). Whole videos stay on one rank
 (v5ela.shard.shard_videos); every rank reduces its videos on the device and rank 0 gathers the per-video records.
-Rank 0 recomputes every video with the C oracle and requires byte-identical records. Prints one JSON line.
+Rank 0 recomputes every video with the C oracle (a pool of host processes forked before CUDA is touched, so that the full-size
+case — 64 x 32 x 1080p — costs seconds of box time) and requires byte-identical records. Prints one JSON line.
 """
 import argparse
 import json
@@ -19,7 +20,28 @@ for p in (ROOT, os.path.join(ROOT, "fake-video-detection-engine_b200")):
         sys.path.insert(0, p)
 
 
+def _oracle_video(job):
+    """One video through the C oracle on the host: its per-video record (bytes) and the records of its first frames."""
+    import v5ela
+    from oracle import c_oracle
+
+    v, frames, h, w = job
+    recs, _ = c_oracle.analyze(v5ela.gen_batch(frames * v, frames, h, w, seed=v), 90)
+    return v, v5ela.combine(recs).tobytes(), recs.tobytes() if v == 0 else b""
+
+
 def main():
+    import multiprocessing as mp
+
+    ap0 = argparse.ArgumentParser(add_help=False)
+    for name, dflt in (("--videos", 16), ("--frames", 8), ("--height", 270), ("--width", 480)):
+        ap0.add_argument(name, type=int, default=dflt)
+    a0, _ = ap0.parse_known_args()
+    pool = jobs = None
+    if int(os.environ.get("RANK", 0)) == 0:                     # before CUDA / NCCL exist in this process: fork is safe
+        pool = mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32))
+        jobs = pool.map_async(_oracle_video, [(v, a0.frames, a0.height, a0.width) for v in range(a0.videos)], chunksize=1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -48,21 +70,22 @@ def main():
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
-        from oracle import c_oracle
+        from v5ela.batch import get_handle
 
         got = v5ela.as_records(per_video)
+        oracle = {v: (agg, first) for v, agg, first in jobs.get(timeout=1800)}
+        pool.close()
         for v in range(a.videos):
-            recs, _ = c_oracle.analyze(v5ela.gen_batch(a.frames * v, a.frames, a.height, a.width, seed=v), 90)
-            want = v5ela.combine(recs)
-            if got[v].tobytes() != want.tobytes():
+            if got[v].tobytes() != oracle[v][0]:
                 ok = False
                 print(f"video {v}: per-video record differs from the oracle", file=sys.stderr)
         if per_frame is not None:
             gf = v5ela.as_records(per_frame)
-            recs0, _ = c_oracle.analyze(v5ela.gen_batch(0, a.frames, a.height, a.width, seed=0), 90)
-            ok = ok and gf[: a.frames].tobytes() == recs0.tobytes() and gf.shape[0] == a.videos * a.frames
+            ok = ok and gf[: a.frames].tobytes() == oracle[0][1] and gf.shape[0] == a.videos * a.frames
+        hd = get_handle(local)
         print(json.dumps({"check": "config4_per_video_gather", "world": world, "videos": a.videos, "frames_per_video": a.frames,
-                          "height": a.height, "width": a.width, "bit_exact_vs_oracle": ok}))
+                          "height": a.height, "width": a.width, "bit_exact_vs_oracle": ok, "videos_checked": a.videos,
+                          "instantiation": hd.last_instantiation, "block_stage": hd.block_stage}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

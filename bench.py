@@ -299,7 +299,7 @@ def run_native_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
 
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     lo, hi = local_range(cfg, rank, world)
     n_local = hi - lo
     total = cfg["frames"] * (world if cfg["scaling"] == "weak" else 1)
@@ -388,13 +388,13 @@ def run_native_arm(args):
     if rank == 0 and not args.no_parity and n_local:
         from oracle import c_oracle
 
-        step()
+        # `records` still holds what the last timed step wrote; nothing here may issue a collective (only rank 0 is in this branch)
         torch.cuda.synchronize()
         ok, checked = True, 0
         if group:                                               # video 0: device aggregate == combine(oracle records of its frames)
             host = frames[:group].cpu().numpy()
             orecs, _ = c_oracle.analyze(host, quals[0])
-            agg = as_records((gathered[0] if world > 1 else reduce_records(records[0], group, handle=handle))[:1])
+            agg = as_records(reduce_records(records[0][:group], group, handle=handle))
             ok = agg[0].tobytes() == combine(orecs).tobytes() and as_records(records[0][:group]).tobytes() == orecs.tobytes()
             checked = group
         else:
@@ -462,6 +462,7 @@ def run_native_arm(args):
     # decodes, analyses, and the records come back. Config 2 only.
     files_leg = None
     if cid == 2 and not args.no_files:
+        dt_local, Kf = -1.0, max(3, min(K, 12))                 # no collective inside the try: a failure on one rank must not hang the others
         try:
             from v5ela import jpeg
             from v5ela.batch import analyze_jpeg_files
@@ -494,19 +495,13 @@ def run_native_arm(args):
                 host_recs_f.copy_(out["records"], non_blocking=True)
             torch.cuda.synchronize()
             same = bool(torch.equal(analyze_batch(out["rgb"], quality=quals[0])["records"].cpu(), host_recs_f))
-            Kf = max(3, min(K, 12))
-            barrier()
             t0 = time.perf_counter()
             for _ in range(Kf):
                 out = analyze_jpeg_files(blobs, quality=quals[0], device=dev)
                 host_recs_f.copy_(out["records"], non_blocking=True)
             torch.cuda.synchronize()
             dt_local = time.perf_counter() - t0
-            tt = torch.tensor([dt_local], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            files_leg = {"value": n_local * world * Kf / dt, "unit": UNIT, "steps": Kf,
+            files_leg = {"value": None, "unit": UNIT, "steps": Kf,
                          "h2d_bytes_per_step": int(sum(len(b) for b in blobs)), "d2h_bytes_per_step": n_local * RECORD_BYTES,
                          "input": f"{n_local} JPEG files per GPU (4:2:0, quality 95, mean {sum(len(b) for b in blobs) / n_local / 1e3:.0f} kB) "
                                   "in one pinned host arena; header parsing on the host, wall clock, max over ranks",
@@ -517,6 +512,14 @@ def run_native_arm(args):
             del out
         except Exception as e:  # an extra figure must not take the headline down with it
             files_leg = {"error": repr(e)}
+            dt_local = -1.0
+        tt = torch.tensor([dt_local, -dt_local], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if float(tt[1]) > 0:                                    # some rank failed (its dt is -1)
+            files_leg = files_leg if "error" in files_leg else {"error": "the files leg failed on another rank"}
+        else:
+            files_leg["value"] = n_local * world * Kf / float(tt[0])
 
     if rank == 0:
         peak, peak_src = load_peak()

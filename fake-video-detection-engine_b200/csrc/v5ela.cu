@@ -22,6 +22,7 @@ namespace v5 {
 
 cudaError_t fused_prepare_smem() { return fused_prepare(); }
 int fused_launch_smem(v5_fused_args &a) { return fused_launch(a); }
+int fused_launch_ragged_smem(v5_ragged_args &a) { return fused_launch_ragged(a); }
 
 // One warp per (frame, channel): ela_sum = sum b*hist[b], ela_sumsq = sum b^2*hist[b], ela_max = highest non-empty bin.
 __global__ void __launch_bounds__(96) ela_finalize_kernel(v5ela_record *recs, int n)
@@ -87,6 +88,26 @@ __global__ void __launch_bounds__(256) ela_enhance_kernel(const uint8_t *__restr
     } else {
         for (long long b = i; b < bytes_per_frame; b += stride) dst[b] = lut[src[b]];
     }
+}
+
+// The same for a ragged batch: one (source, destination, byte count) entry per frame; frames without an enhanced map have bytes = 0.
+struct EnhDesc { const uint8_t *src; uint8_t *dst; long long bytes; };
+__global__ void __launch_bounds__(256) ela_enhance_ragged_kernel(const EnhDesc *tab, const v5ela_record *recs)
+{
+    __shared__ uint8_t lut[256];
+    const EnhDesc d = tab[blockIdx.y];
+    if (d.bytes == 0) return;
+    const v5ela_record &r = recs[blockIdx.y];
+    int m = max((int)r.ela_max[0], max((int)r.ela_max[1], (int)r.ela_max[2]));
+    if (m == 0) m = 1;
+    const float scale = (float)(255.0 / (double)m);
+    {
+        const float v = (float)threadIdx.x * scale;
+        lut[threadIdx.x] = (uint8_t)(v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (int)v));
+    }
+    __syncthreads();
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < d.bytes; b += (long long)gridDim.x * blockDim.x)
+        d.dst[b] = lut[d.src[b]];
 }
 
 // Per-video aggregation: out[g] = combine(records[g*group .. (g+1)*group)). One CTA per group, 786 32-bit words.
@@ -195,6 +216,10 @@ int v5ela_destroy(v5ela_handle *h)
     cudaFree(h->d_res);
     cudaFree(h->d_enh);
     cudaFree(h->d_rec);
+    if (h->ev_scratch) cudaEventDestroy(h->ev_scratch);
+    if (h->ev_table) cudaEventDestroy(h->ev_table);
+    if (h->h_table) cudaFreeHost(h->h_table);
+    cudaFree(h->d_table);
     cudaFree(h->d_ticket);
     cudaFree(h->d_lane_consts);
     cudaFree(h->tw_w);
@@ -243,6 +268,7 @@ int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, i
     if (n == 0) return V5ELA_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ScratchOrder order(h, st);                                  // the ticket counter is handle-owned
     if (!h->d_ticket) V5_CUDA(h, cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
     const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
     v5_fused_args a;
@@ -275,6 +301,127 @@ int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, i
     v5::ela_finalize_kernel<<<n, 96, 0, st>>>(static_cast<v5ela_record *>(d_records), n);
     V5_CUDA(h, cudaGetLastError());
     h->launches += 2;
+    return V5ELA_OK;
+}
+
+int v5ela_analyze_ragged(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *d_records, void *cuda_stream)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!frames_host || !d_records || n < 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged: bad pointer or count%s");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ScratchOrder order(h, st);                                  // ticket counter and frame table are handle-owned
+    if (!h->d_ticket) V5_CUDA(h, cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    const size_t desc_bytes = (v5_ragged_args::table_bytes(n) + 15) / 16 * 16, need = desc_bytes + sizeof(v5::EnhDesc) * (size_t)n;
+    if (h->table_cap < need) {
+        if (h->ev_table) cudaEventSynchronize(h->ev_table);
+        if (h->h_table) cudaFreeHost(h->h_table);
+        cudaFree(h->d_table);
+        h->h_table = h->d_table = nullptr;
+        h->table_cap = 0;
+        const size_t cap = need < 4096 ? 4096 : need * 2;
+        V5_CUDA(h, cudaMallocHost(&h->h_table, cap));
+        V5_CUDA(h, cudaMalloc(&h->d_table, cap));
+        h->table_cap = cap;
+    }
+    if (!h->ev_table) V5_CUDA(h, cudaEventCreateWithFlags(&h->ev_table, cudaEventDisableTiming));
+    V5_CUDA(h, cudaEventSynchronize(h->ev_table));              // the previous call's upload has left the staging buffer
+    const bool prof = h->profiling && h->prof_used + 2 <= h->prof_events.size();
+    v5_ragged_args a;
+    memset(&a, 0, sizeof(a));
+    a.frames = frames_host; a.n = n;
+    a.records = static_cast<v5ela_record *>(d_records);
+    a.quality = h->quality; a.seg_rows = h->seg_rows;
+    a.target_items = 2 * h->sm_count * h->ctas_per_sm;
+    a.max_ctas = h->sm_count * h->ctas_per_sm;
+    a.ticket = h->d_ticket; a.lane_consts = h->d_lane_consts;
+    a.table = h->h_table; a.d_table = h->d_table;
+    a.stream = st;
+    if (prof) { a.ev_start = h->prof_events[h->prof_used]; a.ev_stop = h->prof_events[h->prof_used + 1]; }
+    const bool use_mma = h->block_stage == V5ELA_BLOCKS_MMA;
+    a.check_only = 1;
+    int rc = use_mma ? v5m::fused_launch_ragged_mma(a) : v5::fused_launch_ragged_smem(a);
+    bool any_enh = false;
+    if (rc == 0) {
+        v5::EnhDesc *et = reinterpret_cast<v5::EnhDesc *>(static_cast<char *>(h->h_table) + desc_bytes);
+        for (int i = 0; i < n; i++) {
+            const v5ela_frame_desc &f = frames_host[i];
+            et[i].src = f.residual ? f.residual : f.enhanced;
+            et[i].dst = f.enhanced;
+            et[i].bytes = f.enhanced ? (long long)f.height * f.width * 3 : 0;
+            any_enh = any_enh || f.enhanced;
+        }
+        V5_CUDA(h, cudaMemcpyAsync(h->d_table, h->h_table, need, cudaMemcpyHostToDevice, st));
+        V5_CUDA(h, cudaEventRecord(h->ev_table, st));
+        V5_CUDA(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), st));
+        V5_CUDA(h, cudaMemsetAsync(d_records, 0, sizeof(v5ela_record) * (size_t)n, st));
+        a.check_only = 0;
+        rc = use_mma ? v5m::fused_launch_ragged_mma(a) : v5::fused_launch_ragged_smem(a);
+    }
+    if (rc == -1) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged: bad pointer, size or stride in a frame descriptor%s");
+    if (rc == -2) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged: batch too large%s");
+    if (rc > 0) return fail(h, V5ELA_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    h->last_inst = V5ELA_INST_GENERAL;
+    if (prof) h->prof_used += 2;
+    v5::ela_finalize_kernel<<<n, 96, 0, st>>>(static_cast<v5ela_record *>(d_records), n);
+    V5_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    if (any_enh) {
+        if (n > 65535) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged: more than 65535 frames with enhanced maps%s");
+        v5::ela_enhance_ragged_kernel<<<dim3(32, (unsigned)n), 256, 0, st>>>(
+            reinterpret_cast<const v5::EnhDesc *>(static_cast<const char *>(h->d_table) + desc_bytes), static_cast<const v5ela_record *>(d_records));
+        V5_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    return V5ELA_OK;
+}
+
+int v5ela_analyze_ragged_host(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *records_host)
+{
+    if (!h) return V5ELA_ERR_INVALID;
+    if (n == 0) return V5ELA_OK;
+    if (!frames_host || !records_host || n < 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged_host: bad pointer or count%s");
+    DeviceGuard guard(h->device);
+    if (!h->own_stream) V5_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->own_stream;
+    ScratchOrder order(h, st);
+    // device arena: per frame the pixels (rows packed), then the maps it asked for; every part 256-byte aligned
+    std::vector<v5ela_frame_desc> dev((size_t)n);
+    std::vector<size_t> off_in((size_t)n), off_res((size_t)n), off_enh((size_t)n);
+    size_t total = 0;
+    for (int i = 0; i < n; i++) {
+        const v5ela_frame_desc &f = frames_host[i];
+        if (!f.rgb || f.height <= 0 || f.width <= 0 || f.height > 65536 || f.width > 65536 || f.row_stride_bytes < (int64_t)3 * f.width)
+            return fail(h, V5ELA_ERR_INVALID, "v5ela_analyze_ragged_host: bad pointer, size or stride in a frame descriptor%s");
+        const size_t bytes = ((size_t)f.height * f.width * 3 + 255) / 256 * 256;
+        off_in[i] = total; total += bytes;
+        off_res[i] = total; total += (f.residual || f.enhanced) ? bytes : 0;
+        off_enh[i] = total; total += f.enhanced ? bytes : 0;
+    }
+    int rc;
+    if ((rc = ensure(h, (void **)&h->d_in, &h->d_in_cap, total))) return rc;
+    if ((rc = ensure(h, &h->d_rec, &h->d_rec_cap, sizeof(v5ela_record) * (size_t)n))) return rc;
+    for (int i = 0; i < n; i++) {
+        const v5ela_frame_desc &f = frames_host[i];
+        V5_CUDA(h, cudaMemcpy2DAsync(h->d_in + off_in[i], (size_t)3 * f.width, f.rgb, (size_t)f.row_stride_bytes, (size_t)3 * f.width,
+                                     (size_t)f.height, cudaMemcpyHostToDevice, st));
+        dev[i].rgb = h->d_in + off_in[i];
+        dev[i].height = f.height; dev[i].width = f.width;
+        dev[i].row_stride_bytes = (int64_t)3 * f.width;
+        dev[i].residual = (f.residual || f.enhanced) ? h->d_in + off_res[i] : nullptr;
+        dev[i].enhanced = f.enhanced ? h->d_in + off_enh[i] : nullptr;
+    }
+    rc = v5ela_analyze_ragged(h, dev.data(), n, h->d_rec, st);
+    if (rc) return rc;
+    V5_CUDA(h, cudaMemcpyAsync(records_host, h->d_rec, sizeof(v5ela_record) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < n; i++) {
+        const v5ela_frame_desc &f = frames_host[i];
+        const size_t bytes = (size_t)f.height * f.width * 3;
+        if (f.residual) V5_CUDA(h, cudaMemcpyAsync(f.residual, h->d_in + off_res[i], bytes, cudaMemcpyDeviceToHost, st));
+        if (f.enhanced) V5_CUDA(h, cudaMemcpyAsync(f.enhanced, h->d_in + off_enh[i], bytes, cudaMemcpyDeviceToHost, st));
+    }
+    V5_CUDA(h, cudaStreamSynchronize(st));
     return V5ELA_OK;
 }
 
@@ -348,6 +495,7 @@ int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int heig
     }
     cudaStream_t user = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
     cudaStream_t cs = h->copy_stream, ws = h->work_stream;
+    ScratchOrder order(h, user);                                // d_in / d_rec / d_res / d_enh and the two internal streams
     V5_CUDA(h, cudaEventRecord(h->ev_fork, user));
     V5_CUDA(h, cudaStreamWaitEvent(cs, h->ev_fork, 0));
     V5_CUDA(h, cudaStreamWaitEvent(ws, h->ev_fork, 0));
@@ -388,6 +536,7 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
         return fail(h, V5ELA_ERR_INVALID, "v5ela_spectrum: bad pointer, size or stride%s");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ScratchOrder order(h, st);                                  // twiddle tables, d_g / d_ms / d_minmax
     const int wh = width / 2 + 1;
     int rc;
     if (h->tw_w_n != width) {

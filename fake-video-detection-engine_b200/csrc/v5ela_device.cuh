@@ -80,6 +80,18 @@ struct QuantTab {
 
 namespace mma { struct LaneConsts; }
 
+// One frame of a ragged batch (v5ela_analyze_ragged): its own geometry, pointers and work decomposition. Built on the host,
+// read by the RAGGED instantiation's make_geo; uniform batches keep everything in KParams (the kernel-parameter constant bank).
+struct FrameDesc {
+    const uint8_t *rgb;
+    uint8_t *resid;             // optional
+    int64_t row_stride;
+    int32_t h, w, mw, mh;
+    int32_t n_strips, n_segs;
+    uint32_t work_base;         // first work item of this frame; items = n_strips * n_segs
+    uint32_t flags;             // bit 0: vec_ok, bit 1: resid_vec_ok
+};
+
 struct KParams {
     const uint8_t *rgb;
     int64_t frame_stride;
@@ -92,6 +104,7 @@ struct KParams {
     int n_strips, n_segs;       // work decomposition: strips x vertical segments per frame
     unsigned int *ticket;       // work-item counter (zeroed before every launch): CTAs draw items dynamically
     const mma::LaneConsts *lane_consts;   // 32 entries (v5ela_dctmma.cuh), device memory owned by the handle
+    const FrameDesc *frames;    // ragged batches only: n descriptors in device memory (then h, w, ... above are unused)
     int vec_ok;                 // 1: every band line start is 16-byte aligned in global memory (128-bit loads)
     int resid_vec_ok;           // 1: residual rows are 16-byte aligned (3*W % 16 == 0 and base aligned): 128-bit stores
     QuantTab q[2];              // [0] luma, [1] chroma — lives in the kernel parameter constant bank
@@ -376,6 +389,9 @@ struct alignas(16) Smem {
 struct Geo {
     const uint8_t *frame;       // first byte of this frame
     uint8_t *resid;             // first byte of this frame's residual map, or null
+    int64_t row_stride;         // the frame's geometry: copies of KParams' fields for a uniform batch (the compiler folds them
+    int h, w, mw, mh;           // back into constant-bank operands), the frame's own descriptor for a ragged one
+    int vec_ok, resid_vec_ok;
     int m0, m1;                 // strip MCU columns [m0, m1)
     int r0, r1;                 // segment MCU rows [r0, r1)
     int xb0;                    // pixel column of band smem column 0 (= 16*(m0-1), may be -16)
@@ -424,12 +440,12 @@ V5_DEV LoadGeo load_geo(const KParams &p, const Geo &g)
     LoadGeo L;
     L.xs = g.xb0 < 0 ? 0 : g.xb0;
     int xe = g.xb0 + 16 * g.band_mcus;
-    const int xpad_end = xe > 16 * p.mw ? 16 * p.mw : xe;       // last padded column (exclusive) inside this band
-    if (xe > p.w) xe = p.w;
+    const int xpad_end = xe > 16 * g.mw ? 16 * g.mw : xe;       // last padded column (exclusive) inside this band
+    if (xe > g.w) xe = g.w;
     L.nbytes = 3 * (xe - L.xs);
     L.dst0 = 3 * (L.xs - g.xb0);
-    L.npad3 = 3 * (xpad_end - p.w);                             // > 0 only in the strip that holds the right edge
-    L.nbulk = p.vec_ok ? (L.nbytes & ~15) : 0;
+    L.npad3 = 3 * (xpad_end - g.w);                             // > 0 only in the strip that holds the right edge
+    L.nbulk = g.vec_ok ? (L.nbytes & ~15) : 0;
     return L;
 }
 
@@ -445,8 +461,8 @@ V5_DEV void stage_prefetch(int tid, Smem &S, const KParams &p, const Geo &g, int
     async_proxy_fence();                                        // earlier generic accesses to this buffer are done
     if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t *>(bar), 16u * (uint32_t)L.nbulk);
     int y = 16 * r + tid;
-    if (y > p.h - 1) y = p.h - 1;
-    bulk_g2s(&S.rgb[rb(r)][tid][L.dst0], g.frame + (int64_t)y * p.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
+    if (y > g.h - 1) y = g.h - 1;
+    bulk_g2s(&S.rgb[rb(r)][tid][L.dst0], g.frame + (int64_t)y * g.row_stride + 3 * L.xs, (uint32_t)L.nbulk,
              reinterpret_cast<uint64_t *>(bar));
 }
 
@@ -466,11 +482,11 @@ V5_DEV void stage_load_rest(int tid, Smem &S, const KParams &p, const Geo &g, in
     if (done == L.nbytes && L.npad3 <= 0) return;
     for (int l = warp; l < 16; l += NT / 32) {                  // one warp per band line
         int y = 16 * r + l;
-        if (y > p.h - 1) y = p.h - 1;
-        const uint8_t *src = g.frame + (int64_t)y * p.row_stride + 3 * L.xs;
+        if (y > g.h - 1) y = g.h - 1;
+        const uint8_t *src = g.frame + (int64_t)y * g.row_stride + 3 * L.xs;
         for (int b = done + lane; b < L.nbytes; b += 32) dst[l][L.dst0 + b] = src[b];
         for (int b = lane; b < L.npad3; b += 32)
-            dst[l][3 * (p.w - g.xb0) + b] = g.frame[(int64_t)y * p.row_stride + 3 * (p.w - 1) + (b % 3)];
+            dst[l][3 * (g.w - g.xb0) + b] = g.frame[(int64_t)y * g.row_stride + 3 * (g.w - 1) + (b % 3)];
     }
 }
 
@@ -560,8 +576,8 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
 {
     // Chroma line j of this band averages frame rows (2jc, min(2jc+1, H-1)) with jc = min(8r+j, He/2-1): below the
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
-    const int last_cline = ((p.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
-    const int last_line = p.h - 1 - 16 * r;                     // local index of the last real pixel line
+    const int last_cline = ((g.h + 1) >> 1) - 1 - 8 * r;        // local index of the last real chroma line
+    const int last_line = g.h - 1 - 16 * r;                     // local index of the last real pixel line
     const uint8_t(*src)[RGB_PITCH] = S.rgb[rb(r)];
     bool waiting = defer;
     if (RGB_BUFS == 2 && !waiting)
@@ -573,7 +589,7 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
     for (int u = tid; u < 8 * 2 * BAND_MCUS; u += NT) {          // unit = 2 lines x 8 px
         const int li = u / (2 * BAND_MCUS), ox = u - li * (2 * BAND_MCUS);
         const int mcu = g.m0 - 1 + (ox >> 1);
-        if (ox >= 2 * g.band_mcus || mcu < 0 || mcu >= p.mw) continue;
+        if (ox >= 2 * g.band_mcus || mcu < 0 || mcu >= g.mw) continue;
         U2 y0, y1;
         uint32_t cb, cr;
         convert8x2<true, true>(&src[2 * li][24 * ox], &src[2 * li + 1][24 * ox], y0, y1, cb, cr);
@@ -721,7 +737,7 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
     if (blk < nl) {
         const int br = blk >= 2 * tw ? 1 : 0, bc = blk - br * 2 * tw;
         // blocks entirely below / right of the image are libjpeg "dummy" data: never visible, skip them
-        if (16 * r + 8 * br >= p.h || (!FAST && 16 * g.m0 + 8 * bc >= p.w)) return t;
+        if (16 * r + 8 * br >= g.h || (!FAST && 16 * g.m0 + 8 * bc >= g.w)) return t;
         const int row = ring16(r, 8 * br), col = 16 + 8 * bc;
         t.in = &S.yorig[row][col];
         t.out = &S.ydec[ringd(r, 8 * br)][col];
@@ -732,7 +748,7 @@ V5_DEV BlockTask block_task(int blk, Smem &S, const KParams &p, const Geo &g, in
         if (c >= 2 * g.band_mcus) return t;
         const int comp = c >= g.band_mcus ? 1 : 0, cbk = c - comp * g.band_mcus;
         const int mcu = g.m0 - 1 + cbk;
-        if (mcu < 0 || mcu >= p.mw) return t;
+        if (mcu < 0 || mcu >= g.mw) return t;
         t.q = S.qtab[1];
         t.in = &S.cenc[comp][0][8 * cbk];
         t.out = &S.cdec[comp][ring8(r, 0)][8 * cbk];
@@ -875,17 +891,17 @@ V5_DEV void stage_blocks_mma(int tid, Smem &S, const KParams &p, const Geo &g, i
     if (want_y) {
         int hi = 2 * tw;
         if (!FAST) {
-            const int inside = (p.w - 16 * g.m0 + 7) >> 3;             // luma blocks of this strip that hold image columns
+            const int inside = (g.w - 16 * g.m0 + 7) >> 3;             // luma blocks of this strip that hold image columns
             hi = inside < hi ? inside : hi;
         }
 #pragma unroll 1
         for (int br = 0; br < 2; br++) {
-            if (16 * r + 8 * br >= p.h) break;                         // block rows below the image: dummy data, never visible
+            if (16 * r + 8 * br >= g.h) break;                         // block rows below the image: dummy data, never visible
             blocks_section<Y_PITCH, FAST>(tid, K, &S.yorig[ring16(r, 8 * br)][16], &S.ydec[ringd(r, 8 * br)][16], S.qtab[0], tw, 0, hi);
         }
     }
     const int lo = g.m0 == 0 ? 1 : 0;                                  // halo MCU columns outside the image are not real blocks
-    const int hi = g.band_mcus < p.mw - g.m0 + 1 ? g.band_mcus : p.mw - g.m0 + 1;
+    const int hi = g.band_mcus < g.mw - g.m0 + 1 ? g.band_mcus : g.mw - g.m0 + 1;
 #pragma unroll 1
     for (int comp = 0; comp < 2; comp++)
         blocks_section<C_PITCH, false>(tid, K, &S.cenc[comp][0][0], &S.cdec[comp][ring8(r, 0)][0], S.qtab[1], (g.band_mcus + 1) >> 1, lo, hi);
@@ -963,7 +979,7 @@ V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc
     const int y = 16 * r + l;                                   // global pixel row
     const int gx0 = 16 * g.m0 + 8 * ox;                         // global pixel column of this unit
     const int col = 16 + 8 * ox;                                // band smem column
-    const int nvalid = p.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8; FAST: >= 8)
+    const int nvalid = g.w - gx0;                               // pixels k < nvalid are inside the image (may be > 8; FAST: >= 8)
 
     // ---- reconstruct (A.8), residual (A.9), histogram
     // R = clamp(Y + ((91881 cr' + 32768) >> 16)) == clamp(((Y << 16) + 32768 + 91881 cr') >> 16): one PRMT builds
@@ -981,8 +997,8 @@ V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc
     } else {
         // single-buffer layout: the band's RGB is gone from shared memory by now; these 24 bytes were fetched through L2
         // one iteration ago. A unit cut by the image edge (or an unaligned frame) must not read past its row.
-        const uint8_t *orig = g.frame + (int64_t)y * p.row_stride + 3 * gx0;
-        if (p.vec_ok && nvalid >= 8) {
+        const uint8_t *orig = g.frame + (int64_t)y * g.row_stride + 3 * gx0;
+        if (g.vec_ok && nvalid >= 8) {
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const U2 t = reinterpret_cast<const U2 *>(orig)[i];
@@ -1013,8 +1029,8 @@ V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc
     for (int i = 0; i < 6; i++)
         dw[i] = absdiff4(ow[i], pack4sat(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]));
     if (!FAST && g.resid) {
-        uint8_t *dst = g.resid + ((int64_t)y * p.w + gx0) * 3;
-        if (nvalid >= 8 && p.resid_vec_ok) {
+        uint8_t *dst = g.resid + ((int64_t)y * g.w + gx0) * 3;
+        if (nvalid >= 8 && g.resid_vec_ok) {
 #pragma unroll
             for (int i = 0; i < 3; i++) reinterpret_cast<U2 *>(dst)[i] = U2{dw[2 * i], dw[2 * i + 1]};
         } else {
@@ -1046,11 +1062,11 @@ V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc
 
     // ---- texture: Laplacian of the original luma, BORDER_REFLECT_101 (§8a)
     int lu = l - 1, ld = l + 1;
-    if (y == 0) lu = p.h > 1 ? l + 1 : l;
-    if (y == p.h - 1) ld = p.h > 1 ? l - 1 : l;
+    if (y == 0) lu = g.h > 1 ? l + 1 : l;
+    if (y == g.h - 1) ld = g.h > 1 ? l - 1 : l;
     const uint8_t *yc = &S.yorig[ring16(r, l)][col];
     const uint8_t *yu = &S.yorig[ring16(r, lu)][col], *yd2 = &S.yorig[ring16(r, ld)][col];
-    const int wide = FAST || p.w > 1;
+    const int wide = FAST || g.w > 1;
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
     {
         // e[0..9] = left neighbour, the 8 pixels, right neighbour, as three words; l + r - 4c is one or two dp4a per
@@ -1109,7 +1125,7 @@ V5_DEV void residual_unit(Smem &S, const KParams &p, const Geo &g, ThreadAcc &ac
     const int col = 16 + 8 * ox;                                // band smem column
 
     // ---- chroma upsample (A.7)
-    const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = ((p.w + 1) >> 1) - 1;
+    const int hc1 = ((g.h + 1) >> 1) - 1, wc1 = ((g.w + 1) >> 1) - 1;
     const int crow = y >> 1;
     int nrow = (y & 1) ? crow + 1 : crow - 1;
     nrow = nrow < 0 ? 0 : (nrow > hc1 ? hc1 : nrow);
@@ -1152,7 +1168,7 @@ template <bool TEXHIST>
 V5_DEV void residual_pair(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc, int r, int pi, int ox, bool v0, bool v1)
 {
     const int col = 16 + 8 * ox, ccol = col >> 1, gcx0 = (16 * g.m0 + 8 * ox) >> 1;
-    const int hc1 = ((p.h + 1) >> 1) - 1, wc1 = (p.w >> 1) - 1;
+    const int hc1 = ((g.h + 1) >> 1) - 1, wc1 = (g.w >> 1) - 1;
     int ja = pi - 1, jb = pi;                                   // chroma lines of this band: a nearer for the odd row, b for the even one
     if (8 * r + ja < 0) ja = jb;                                // row 0: the line above does not exist, libjpeg repeats line 0
     if (8 * r + jb > hc1) jb = ja;                              // last row of an even-height image: the line below repeats the last
@@ -1186,7 +1202,7 @@ V5_DEV void stage_residual_pairs(int tid, Smem &S, const KParams &p, const Geo &
 {
     const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
     const uint32_t inv = 65536u / (uint32_t)n8 + 1u;            // exact u / n8 for u < 8 * 60
-    const int ylo = 16 * g.r0, yhi = 16 * g.r1 < p.h ? 16 * g.r1 : p.h;
+    const int ylo = 16 * g.r0, yhi = 16 * g.r1 < g.h ? 16 * g.r1 : g.h;
     for (int u = tid; u < 8 * n8; u += NT) {
         const int pi = (int)(((uint32_t)u * inv) >> 16), ox = u - pi * n8;
         const int y0 = 16 * r + 2 * pi - 1;
@@ -1202,30 +1218,59 @@ V5_DEV void stage_residual(int tid, Smem &S, const KParams &p, const Geo &g, Thr
 {
     const int n8 = 2 * (g.m1 - g.m0);                           // 8-pixel units per line (<= 60)
     const uint32_t inv = 65536u / (uint32_t)n8 + 1u;            // exact u / n8 for u < 16 * 60
-    const int ylo = 16 * g.r0, yhi = 16 * g.r1 < p.h ? 16 * g.r1 : p.h;
+    const int ylo = 16 * g.r0, yhi = 16 * g.r1 < g.h ? 16 * g.r1 : g.h;
     for (int u = tid; u < 16 * n8; u += NT) {
         const int wl = (int)(((uint32_t)u * inv) >> 16), ox = u - wl * n8;
         const int l = wl - 1, y = 16 * r + l;
-        if (y < ylo || y >= yhi || (!FAST && 16 * g.m0 + 8 * ox >= p.w)) continue;
+        if (y < ylo || y >= yhi || (!FAST && 16 * g.m0 + 8 * ox >= g.w)) continue;
         residual_unit<FAST, TEXHIST>(S, p, g, acc, r, l, ox);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ work item set-up
+template <bool RAGGED>
 V5_DEV void make_geo(const KParams &p, int work, Geo &g, int &frame)
 {
-    const uint32_t per_frame = (uint32_t)(p.n_strips * p.n_segs);
-    frame = (int)((uint32_t)work / per_frame);
-    const uint32_t rem = (uint32_t)work - (uint32_t)frame * per_frame;
-    const uint32_t seg = rem / (uint32_t)p.n_strips, strip = rem - seg * (uint32_t)p.n_strips;
-    g.m0 = (int)((strip * (uint32_t)p.mw) / (uint32_t)p.n_strips);          // mw, mh <= 4096: no overflow
-    g.m1 = (int)(((strip + 1) * (uint32_t)p.mw) / (uint32_t)p.n_strips);
-    g.r0 = (int)((seg * (uint32_t)p.mh) / (uint32_t)p.n_segs);
-    g.r1 = (int)(((seg + 1) * (uint32_t)p.mh) / (uint32_t)p.n_segs);
+    uint32_t rem, n_strips, n_segs;
+    if (RAGGED) {
+        int lo = 0, hi = p.n - 1;                               // last frame whose work_base <= work
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.frames[mid].work_base <= (uint32_t)work) lo = mid;
+            else hi = mid - 1;
+        }
+        frame = lo;
+        const FrameDesc &d = p.frames[lo];
+        rem = (uint32_t)work - d.work_base;
+        n_strips = (uint32_t)d.n_strips;
+        n_segs = (uint32_t)d.n_segs;
+        g.h = d.h; g.w = d.w; g.mw = d.mw; g.mh = d.mh;
+        g.row_stride = d.row_stride;
+        g.vec_ok = (int)(d.flags & 1u);
+        g.resid_vec_ok = (int)((d.flags >> 1) & 1u);
+        g.frame = d.rgb;
+        g.resid = d.resid;
+    } else {
+        const uint32_t per_frame = (uint32_t)(p.n_strips * p.n_segs);
+        frame = (int)((uint32_t)work / per_frame);
+        rem = (uint32_t)work - (uint32_t)frame * per_frame;
+        n_strips = (uint32_t)p.n_strips;
+        n_segs = (uint32_t)p.n_segs;
+        g.h = p.h; g.w = p.w; g.mw = p.mw; g.mh = p.mh;
+        g.row_stride = p.row_stride;
+        g.vec_ok = p.vec_ok;
+        g.resid_vec_ok = p.resid_vec_ok;
+        g.frame = p.rgb + (int64_t)frame * p.frame_stride;
+        g.resid = p.residual ? p.residual + (int64_t)frame * p.h * p.w * 3 : nullptr;
+    }
+    const uint32_t seg = rem / n_strips, strip = rem - seg * n_strips;
+    g.m0 = (int)((strip * (uint32_t)g.mw) / n_strips);          // mw, mh <= 4096: no overflow
+    g.m1 = (int)(((strip + 1) * (uint32_t)g.mw) / n_strips);
+    g.r0 = (int)((seg * (uint32_t)g.mh) / n_segs);
+    g.r1 = (int)(((seg + 1) * (uint32_t)g.mh) / n_segs);
     g.xb0 = 16 * (g.m0 - 1);
     g.band_mcus = g.m1 - g.m0 + 2;
-    g.frame = p.rgb + (int64_t)frame * p.frame_stride;
-    g.resid = p.residual ? p.residual + (int64_t)frame * p.h * p.w * 3 : nullptr;
 }
+
 
 }  // namespace V5_NS

@@ -24,12 +24,32 @@ struct v5_fused_args {
     long long total;                // out: work items
 };
 
+#define V5_RAGGED_DESC_BYTES 56              // sizeof(FrameDesc), csrc/v5ela_device.cuh
+
+struct v5_ragged_args {
+    const v5ela_frame_desc *frames; // host array of n descriptors holding DEVICE pointers
+    int n;
+    v5ela_record *records;          // device, n records
+    int quality, seg_rows, target_items, max_ctas;
+    unsigned int *ticket;
+    const void *lane_consts;
+    void *table;                    // host staging for the kernel's frame table: table_bytes(n)
+    const void *d_table;            // its device copy (uploaded by the caller between the two calls)
+    cudaStream_t stream;
+    cudaEvent_t ev_start, ev_stop;
+    int check_only;
+    long long total;                // out (check_only pass): work items
+    static size_t table_bytes(int n) { return (size_t)V5_RAGGED_DESC_BYTES * (size_t)n; }
+};
+
 namespace v5 {
 cudaError_t fused_prepare_smem();           // v5ela.cu
 int fused_launch_smem(v5_fused_args &a);
+int fused_launch_ragged_smem(v5_ragged_args &a);
 }
 namespace v5m {
 cudaError_t fused_prepare_mma();            // v5ela_mma.cu
 int fused_launch_mma(v5_fused_args &a);
+int fused_launch_ragged_mma(v5_ragged_args &a);
 bool lane_consts_host(void *dst128x32);     // fills 32 x 128 bytes (mma::LaneConsts); false = constants do not fit (cannot happen)
 }

@@ -30,6 +30,10 @@ struct v5ela_handle {
     uint8_t *d_in = nullptr, *d_res = nullptr, *d_enh = nullptr;
     void *d_rec = nullptr;
     unsigned int *d_ticket = nullptr;
+    // ragged batches: the kernel's frame table (+ the enhancement kernel's table behind it), pinned host staging and device copy
+    void *h_table = nullptr, *d_table = nullptr;
+    size_t table_cap = 0;
+    cudaEvent_t ev_table = nullptr;        // the last upload out of h_table has completed
     void *d_lane_consts = nullptr;         // 32 x mma::LaneConsts: operand fragments of the tensor-core block stage (v5ela_dctmma.cuh)
     int block_stage = V5ELA_BLOCKS_DEFAULT; // which build of the fused kernel analyze launches (v5ela_set_block_stage)
     size_t d_in_cap = 0, d_res_cap = 0, d_enh_cap = 0, d_rec_cap = 0;
@@ -44,6 +48,11 @@ struct v5ela_handle {
     size_t d_gray_cap = 0, d_spec_cap = 0;
     uint16_t luma[64], chroma[64];
     struct v5jpeg_state *jpeg = nullptr;   // codec workspace, owned by v5jpeg.cu (created on first use)
+    // Scratch owned by the handle (ticket counter, host-path / spectrum / codec workspaces) is reused by every call. Calls on ONE
+    // stream are ordered by the stream; a call on another stream than the previous one first waits for that call's last launch.
+    cudaEvent_t ev_scratch = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
     char err[512] = {0};
 };
 
@@ -62,6 +71,26 @@ inline int fail(v5ela_handle *h, int code, const char *fmt, const char *detail =
         cudaError_t e_ = (call);                                                            \
         if (e_ != cudaSuccess) return fail((h), V5ELA_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
     } while (0)
+
+// RAII around an entry point that touches handle-owned scratch on stream `st` (see v5ela_handle::ev_scratch).
+struct ScratchOrder {
+    v5ela_handle *h;
+    cudaStream_t st;
+    ScratchOrder(v5ela_handle *handle, cudaStream_t stream) : h(handle), st(stream)
+    {
+        if (h->scratch_used && h->scratch_stream != st) cudaStreamWaitEvent(st, h->ev_scratch, 0);
+    }
+    ~ScratchOrder()
+    {
+        if (!h->ev_scratch && cudaEventCreateWithFlags(&h->ev_scratch, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventRecord(h->ev_scratch, st) == cudaSuccess) {
+            h->scratch_stream = st;
+            h->scratch_used = true;
+        }
+    }
+    ScratchOrder(const ScratchOrder &) = delete;
+    ScratchOrder &operator=(const ScratchOrder &) = delete;
+};
 
 struct DeviceGuard {
     int prev = -1;

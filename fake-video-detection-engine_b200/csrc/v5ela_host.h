@@ -27,6 +27,16 @@ inline void quant_tables(int quality, uint16_t luma[64], uint16_t chroma[64])
     }
 }
 
+// More, narrower strips for batches that cannot fill the GPU: scale the strip count by target / items, at least 4 MCUs per strip.
+inline int widen_strips(int n_strips, int mw, int64_t items, int64_t target_items)
+{
+    const int64_t factor = (target_items + items - 1) / (items > 0 ? items : 1);
+    int64_t ns = (int64_t)n_strips * factor;
+    const int cap = mw / 4 > 1 ? mw / 4 : 1;
+    if (ns > cap) ns = cap;
+    return ns < n_strips ? n_strips : (int)ns;
+}
+
 // Work decomposition: frames x strips (<= TW_MAX MCUs wide, balanced) x vertical segments of about `seg_rows` MCU rows.
 // seg_rows <= 0 picks the default: 17 rows (two chroma-only halo bands per segment = ~4 % extra work), shortened down to
 // 4 rows when the batch would otherwise give fewer than `target_items` work items (small batches, single crops), so
@@ -58,6 +68,10 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
             const int64_t want_segs = (target_items + columns - 1) / columns;
             seg_rows = (int)((p.mh + want_segs - 1) / want_segs);
             if (seg_rows < 4) seg_rows = 4;
+            // still too few items for the GPU (a handful of crops): narrower strips — down to 4 MCUs — shorten every band, and
+            // with it the latency of the call; the extra halo columns do not matter when most SMs would idle anyway
+            const int64_t items = columns * ((p.mh + seg_rows - 1) / seg_rows);
+            if (items < target_items) p.n_strips = widen_strips(p.n_strips, p.mw, items, target_items);
         }
     }
     p.n_segs = (p.mh + seg_rows - 1) / seg_rows;

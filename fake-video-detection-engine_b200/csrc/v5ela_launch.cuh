@@ -14,7 +14,7 @@ namespace V5_NS {
 static_assert(sizeof(KParams) <= 4096, "kernel parameters must fit the 4 KB parameter bank");
 static_assert(sizeof(Smem) <= (227 * 1024) / MIN_CTAS - 1024, "MIN_CTAS CTAs per SM must fit in shared memory");
 
-template <bool FAST, bool TEXHIST>
+template <bool FAST, bool TEXHIST, bool RAGGED = false>
 __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_constant__ KParams p, int total_work)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) ela_fused_kernel(const __grid_co
         __syncthreads();
         const int work = (int)S.next_work;
         if (work >= total_work) break;
-        process_work_item<FAST, TEXHIST>(S, p, work, acc_store);          // ends with a CTA barrier: next_work may be rewritten
+        process_work_item<FAST, TEXHIST, RAGGED>(S, p, work, acc_store);         // ends with a CTA barrier: next_work may be rewritten
     }
 }
 
@@ -44,6 +44,7 @@ inline cudaError_t fused_prepare()
     cudaError_t e = cudaFuncSetAttribute(ela_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ela_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ela_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ela_fused_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     return e;
 }
 
@@ -67,6 +68,81 @@ inline int fused_launch(v5_fused_args &a)
     if (a.inst == V5ELA_INST_TEXHIST) ela_fused_kernel<false, true><<<grid, NT, sizeof(Smem), a.stream>>>(p, (int)total);
     else if (a.inst == V5ELA_INST_FAST) ela_fused_kernel<true, false><<<grid, NT, sizeof(Smem), a.stream>>>(p, (int)total);
     else ela_fused_kernel<false, false><<<grid, NT, sizeof(Smem), a.stream>>>(p, (int)total);
+    const cudaError_t e = cudaGetLastError();
+    if (a.ev_stop) cudaEventRecord(a.ev_stop, a.stream);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+
+// Ragged batch: n frames of different sizes in one launch (v5ela_analyze_ragged). Fills `table` (host memory, n FrameDesc =
+// v5_ragged_args::table_bytes(n) bytes) for the caller to upload to a.d_table BEFORE the launch on the same stream: call with
+// check_only = 1 first (validates, fills the table and a.total), upload, then again with check_only = 0.
+inline int fused_launch_ragged(v5_ragged_args &a)
+{
+    static_assert(sizeof(FrameDesc) == V5_RAGGED_DESC_BYTES, "v5_ragged_args::table_bytes");
+    if (!a.frames || !a.records || a.n <= 0 || !a.table || a.quality < 1 || a.quality > 100) return -1;
+    FrameDesc *tab = static_cast<FrameDesc *>(a.table);
+    if (a.check_only) {
+        long long columns = 0;
+        for (int i = 0; i < a.n; i++) {
+            const v5ela_frame_desc &f = a.frames[i];
+            if (!f.rgb || f.height <= 0 || f.width <= 0 || f.height > 65536 || f.width > 65536 || (int64_t)f.height * f.width > 0x7fffffffLL ||
+                f.row_stride_bytes < (int64_t)3 * f.width)
+                return -1;
+            columns += ((f.width + 15) / 16 + TW_MAX - 1) / TW_MAX;
+        }
+        // segments of about 17 MCU rows, shortened (down to 4) when the batch would otherwise leave SMs idle
+        const long long want_segs = a.target_items > 0 ? (a.target_items + columns - 1) / columns : 1;
+        long long items4 = 0;                                   // work items with the default strips and segments shortened to >= 4 rows
+        for (int i = 0; i < a.n; i++) {
+            const int mw = (a.frames[i].width + 15) / 16, mh = (a.frames[i].height + 15) / 16;
+            long long sr = (mh + want_segs - 1) / want_segs;
+            sr = sr < 4 ? 4 : (sr > 17 ? 17 : sr);
+            items4 += (long long)((mw + TW_MAX - 1) / TW_MAX) * ((mh + sr - 1) / sr);
+        }
+        long long total = 0;
+        for (int i = 0; i < a.n; i++) {
+            const v5ela_frame_desc &f = a.frames[i];
+            FrameDesc &d = tab[i];
+            uint8_t *resid = f.residual ? f.residual : f.enhanced;                // an enhanced map alone: the residual is formed in place
+            d.rgb = f.rgb;
+            d.resid = resid;
+            d.row_stride = f.row_stride_bytes;
+            d.h = f.height; d.w = f.width;
+            d.mw = (f.width + 15) / 16; d.mh = (f.height + 15) / 16;
+            d.n_strips = (d.mw + TW_MAX - 1) / TW_MAX;
+            int seg_rows = a.seg_rows > 0 ? a.seg_rows : 17;
+            if (a.seg_rows <= 0 && (d.mh + seg_rows - 1) / seg_rows < want_segs) {
+                seg_rows = (int)((d.mh + want_segs - 1) / want_segs);
+                if (seg_rows < 4) seg_rows = 4;
+            }
+            d.n_segs = (d.mh + seg_rows - 1) / seg_rows;
+            if (a.seg_rows <= 0 && a.target_items > 0 && items4 < a.target_items) d.n_strips = widen_strips(d.n_strips, d.mw, items4, a.target_items);
+            if (total > 0x7fffffffLL) return -2;
+            d.work_base = (uint32_t)total;
+            total += (long long)d.n_strips * d.n_segs;
+            const bool vec = ((reinterpret_cast<uintptr_t>(f.rgb) | (uintptr_t)f.row_stride_bytes) & 15) == 0;
+            const bool rvec = resid && ((reinterpret_cast<uintptr_t>(resid) | (uintptr_t)(3 * f.width)) & 15) == 0;
+            d.flags = (vec ? 1u : 0u) | (rvec ? 2u : 0u);
+        }
+        if (total > 0x7fffffffLL) return -2;
+        a.total = total;
+        return 0;
+    }
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.records = a.records;
+    p.n = a.n;
+    p.ticket = a.ticket;
+    p.lane_consts = static_cast<const mma::LaneConsts *>(a.lane_consts);
+    p.frames = static_cast<const FrameDesc *>(a.d_table);
+    uint16_t ql[64], qc[64];
+    quant_tables(a.quality, ql, qc);
+    make_quant(ql, p.q[0]);
+    make_quant(qc, p.q[1]);
+    const int grid = a.total < a.max_ctas ? (int)a.total : a.max_ctas;
+    if (a.ev_start) cudaEventRecord(a.ev_start, a.stream);
+    ela_fused_kernel<false, false, true><<<grid, NT, sizeof(Smem), a.stream>>>(p, (int)a.total);
     const cudaError_t e = cudaGetLastError();
     if (a.ev_stop) cudaEventRecord(a.ev_stop, a.stream);
     return e == cudaSuccess ? 0 : (int)e;

@@ -127,12 +127,14 @@ inline void flush_global(int tid, Smem &S, v5ela_record *rec, uint32_t *tex_hist
 }
 #endif
 
-template <bool FAST, bool TEXHIST>
+// RAGGED: every frame has its own size and pointers (KParams::frames); only with the general instantiation.
+template <bool FAST, bool TEXHIST, bool RAGGED = false>
 V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *acc_store)
 {
+    static_assert(!RAGGED || (!FAST && !TEXHIST), "ragged batches take the general instantiation");
     Geo g;
     int frame;
-    make_geo(p, work, g, frame);
+    make_geo<RAGGED>(p, work, g, frame);
 
     V5_FOR_THREADS({
         for (int i = tid; i < 3 * 256; i += NT) (&S.hist[0][0])[i] = 0;
@@ -184,10 +186,10 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
     constexpr bool PAIRS = FAST && V5_PAIR_ROWS;             // two rows per residual unit (stage_residual_pairs)
     bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet
     for (int r = r_first; r <= g.r1; r++) {
-        const bool has_band = r < p.mh;
+        const bool has_band = r < g.mh;
         const bool want_y = r >= g.r0 && r < g.r1;
-        const bool next_band = r + 1 <= g.r1 && r + 1 < p.mh;
-        if (!has_band && 16 * r - 1 >= p.h) break;          // nothing left below the image
+        const bool next_band = r + 1 <= g.r1 && r + 1 < g.mh;
+        if (!has_band && 16 * r - 1 >= g.h) break;          // nothing left below the image
         if (has_band) {
             // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
             // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.

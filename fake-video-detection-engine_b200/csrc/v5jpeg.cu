@@ -106,7 +106,7 @@ int64_t v5ela_jpeg_bound(int height, int width, int channels)
     return (int64_t)v5j::enc_geo(height, width, channels).blocks * 416 + kHeaderMax;
 }
 
-int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, int width, int channels,
+static int v5ela_jpeg_encode_impl(v5ela_handle *h, const uint8_t *d_img, int n, int height, int width, int channels,
                       int64_t frame_stride_bytes, int64_t row_stride_bytes, int quality, uint8_t *d_out,
                       int64_t out_stride_bytes, int32_t *d_sizes, void *cuda_stream)
 {
@@ -119,6 +119,7 @@ int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, 
         return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_encode: bad pointer, size, stride, channel count or quality%s");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ScratchOrder order(h, st);                                  // the codec workspace is handle-owned
     v5jpeg_state *s;
     int rc;
     if ((rc = jpeg_state(h, &s))) return rc;
@@ -198,7 +199,7 @@ int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, 
     return V5ELA_OK;
 }
 
-int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, int n, int height, int width, int channels, int quality,
+static int v5ela_jpeg_encode_host_impl(v5ela_handle *h, const uint8_t *img_host, int n, int height, int width, int channels, int quality,
                            uint8_t *out_host, int64_t out_stride_bytes, int32_t *sizes_host)
 {
     if (!h) return V5ELA_ERR_INVALID;
@@ -250,7 +251,7 @@ int v5ela_jpeg_info(const uint8_t *file_host, int64_t len, int *height, int *wid
 
 /* n files at once: dims_out[3 i .. 3 i + 2] = height, width, channels of file i. Stops at the first unreadable file and returns
  * its status; *bad_index (optional) names it. */
-int v5ela_jpeg_info_batch(const uint8_t *const *files_host, const int64_t *lens, int n, int32_t *dims_out, int *bad_index)
+static int v5ela_jpeg_info_batch_impl(const uint8_t *const *files_host, const int64_t *lens, int n, int32_t *dims_out, int *bad_index)
 {
     if (!files_host || !lens || n < 0 || !dims_out) return V5ELA_ERR_INVALID;
     for (int i = 0; i < n; i++) {
@@ -322,7 +323,7 @@ struct DecPlan {                               // host-side description of one c
 
 extern "C" {
 
-int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *d_rgb,
+static int v5ela_jpeg_decode_impl(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *d_rgb,
                       const int64_t *rgb_offsets, uint8_t *d_gray, const int64_t *gray_offsets, int32_t *d_status,
                       void *cuda_stream)
 {
@@ -332,6 +333,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
         return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: bad pointer or count%s");
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ScratchOrder order(h, st);                                  // the codec workspace is handle-owned
     v5jpeg_state *s;
     int rc;
     if ((rc = jpeg_state(h, &s))) return rc;
@@ -356,7 +358,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
     for (int i = 0; i < n; i++) {
         if (!files_host[i] || lens[i] <= 0) return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: null or empty file%s");
         total_len += (size_t)lens[i];
-        all_pinned = all_pinned && is_pinned(files_host[i]);
+        all_pinned = all_pinned && is_pinned(files_host[i]) && is_pinned(files_host[i] + (lens[i] > 0 ? lens[i] - 1 : 0));   // first and last byte
     }
     parallel_for(n, total_len, [&](int i) { parse_rc[(size_t)i] = v5j::parse_file(files_host[i], (size_t)lens[i], info[(size_t)i]); });
     for (int i = 0; i < n; i++) {
@@ -402,15 +404,19 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
             plans.emplace_back();
             P = &plans.back();
         }
-        // Pinned files that follow each other in host memory (gap < 64 KB: headers, alignment padding) keep their relative
-        // distance on the device, so that the whole run goes up in one copy. scan_bytes = end of the used scan area.
+        // Pinned files that follow each other in host memory keep their relative distance on the device, so that the whole run
+        // goes up in one copy — which also copies the bytes between two scan segments: the next file's header (its first and
+        // last byte are known to be pinned, see all_pinned) and the padding between the files, which is only accepted when it is
+        // shorter than a page: every byte of it then shares a page with a byte of one of the two files, so the copy can touch
+        // neither unmapped nor foreign memory. Files further apart get a copy of their own. scan_bytes = end of the used scan area.
         size_t start = align_up(P->scan_bytes, 16);
         char contig = 0;
         if (all_pinned && !P->images.empty()) {
             const int pi = P->file_index.back();
             const uint8_t *prev_end = files_host[pi] + info[(size_t)pi].scan_off + info[(size_t)pi].scan_len;
             const uint8_t *cur = files_host[i] + F.scan_off;
-            if (cur >= prev_end && (size_t)(cur - prev_end) < ((size_t)64 << 10)) {
+            const uint8_t *prev_file_end = files_host[pi] + lens[pi];
+            if (cur >= prev_end && files_host[i] >= prev_file_end && (size_t)(files_host[i] - prev_file_end) < 4096) {
                 contig = 1;
                 start = (size_t)(P->images.back().scan_off + P->images.back().scan_len) + (size_t)(cur - prev_end);
             }
@@ -569,7 +575,7 @@ int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const i
     return V5ELA_OK;
 }
 
-int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *rgb_host,
+static int v5ela_jpeg_decode_host_impl(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *rgb_host,
                            const int64_t *rgb_offsets, uint8_t *gray_host, const int64_t *gray_offsets)
 {
     if (!h) return V5ELA_ERR_INVALID;
@@ -623,6 +629,49 @@ int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, co
             return fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode_host: entropy-coded data ends early or is corrupt%s", which);
         }
     return V5ELA_OK;
+}
+
+
+// ---- the exported entry points: nothing may unwind through the C ABI (std::vector / std::thread inside the implementations can throw)
+#define V5J_GUARD(h, call)                                                                       \
+    try {                                                                                        \
+        return call;                                                                             \
+    } catch (const std::bad_alloc &) {                                                           \
+        return fail((h), V5ELA_ERR_NOMEM, "out of host memory%s");                               \
+    } catch (const std::exception &e) {                                                          \
+        return fail((h), V5ELA_ERR_INVALID, "host-side failure: %s", e.what());                  \
+    } catch (...) {                                                                              \
+        return fail((h), V5ELA_ERR_INVALID, "host-side failure%s");                              \
+    }
+
+int v5ela_jpeg_encode(v5ela_handle *h, const uint8_t *d_img, int n, int height, int width, int channels, int64_t frame_stride_bytes,
+                      int64_t row_stride_bytes, int quality, uint8_t *d_out, int64_t out_stride_bytes, int32_t *d_sizes, void *cuda_stream)
+{
+    V5J_GUARD(h, v5ela_jpeg_encode_impl(h, d_img, n, height, width, channels, frame_stride_bytes, row_stride_bytes, quality, d_out,
+                                        out_stride_bytes, d_sizes, cuda_stream))
+}
+
+int v5ela_jpeg_encode_host(v5ela_handle *h, const uint8_t *img_host, int n, int height, int width, int channels, int quality,
+                           uint8_t *out_host, int64_t out_stride_bytes, int32_t *sizes_host)
+{
+    V5J_GUARD(h, v5ela_jpeg_encode_host_impl(h, img_host, n, height, width, channels, quality, out_host, out_stride_bytes, sizes_host))
+}
+
+int v5ela_jpeg_info_batch(const uint8_t *const *files_host, const int64_t *lens, int n, int32_t *dims_out, int *bad_index)
+{
+    V5J_GUARD(static_cast<v5ela_handle *>(nullptr), v5ela_jpeg_info_batch_impl(files_host, lens, n, dims_out, bad_index))
+}
+
+int v5ela_jpeg_decode(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *d_rgb,
+                      const int64_t *rgb_offsets, uint8_t *d_gray, const int64_t *gray_offsets, int32_t *d_status, void *cuda_stream)
+{
+    V5J_GUARD(h, v5ela_jpeg_decode_impl(h, files_host, lens, n, d_rgb, rgb_offsets, d_gray, gray_offsets, d_status, cuda_stream))
+}
+
+int v5ela_jpeg_decode_host(v5ela_handle *h, const uint8_t *const *files_host, const int64_t *lens, int n, uint8_t *rgb_host,
+                           const int64_t *rgb_offsets, uint8_t *gray_host, const int64_t *gray_offsets)
+{
+    V5J_GUARD(h, v5ela_jpeg_decode_host_impl(h, files_host, lens, n, rgb_host, rgb_offsets, gray_host, gray_offsets))
 }
 
 }  // extern "C"

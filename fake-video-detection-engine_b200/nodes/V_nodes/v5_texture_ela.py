@@ -92,32 +92,52 @@ def _write_jpeg(path, image, quality, device, gpu_codec):
         cv2.imwrite(path, image, [cv2.IMWRITE_JPEG_QUALITY, quality])
 
 
-def _gpu_artefacts(crop_path, rank, ela_dir, state):
-    """ELA + spectrum artefacts of one crop; returns (feature dict, ela path, fft path)."""
+def _gpu_artefacts(crops, ela_dir, state):
+    """ELA + spectrum artefacts of the selected crops. ``crops``: list of (rank, crop_path). All crops — whatever their sizes — go
+    through ONE ragged analysis call (one upload, one launch sequence, one download: ``v5ela_analyze_ragged_host``); a crop that
+    cannot be read is reported and left out, like any per-face failure of the reference (:140-144).
+    Returns {rank: (feature dict, ela path, fft path)}."""
     from v5ela import host as v5host
     from v5ela.records import features
 
     quality = int(state.get("v5_quality", 90))
     device = int(state.get("v5_device", 0))
     gpu_codec = bool(state.get("v5_gpu_codec", True))
-    rgb, gray = _read_crop(crop_path, device, gpu_codec)
-    if state.get("v5_keep_temp_jpeg", True):
-        _write_jpeg(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), rgb, quality, device, gpu_codec)
-
-    records, _, enhanced = v5host.analyze_frames_host(rgb[None], quality=quality, want_enhanced=True, device=device)
-    feats = features(records[0], rgb.shape[0] * rgb.shape[1])
-    feats["rank"] = rank
-    ela_path = os.path.join(ela_dir, f"ela_{rank}.jpg")
-    _write_jpeg(ela_path, enhanced[0], 75, device, gpu_codec)          # PIL's default quality (reference :81)
-
-    if state.get("v5_gpu_fft", True):
-        spectrum = v5host.spectrum_host(gray, device=device)
-    else:
-        log_mag = 20 * np.log(np.abs(np.fft.fftshift(np.fft.fft2(gray))) + 1)
-        spectrum = cv2.normalize(log_mag, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
-    fft_path = os.path.join(ela_dir, f"fft_{rank}.jpg")
-    _write_jpeg(fft_path, spectrum, 95, device, gpu_codec)              # OpenCV's default quality (reference :91)
-    return feats, ela_path, fft_path
+    debug = state.get("debug", False)
+    loaded = []
+    for rank, crop_path in crops:
+        try:
+            rgb, gray = _read_crop(crop_path, device, gpu_codec)
+            loaded.append((rank, rgb, gray))
+        except Exception as e:
+            print(f"Error analyzing face {rank}: {e}")
+            if debug:
+                traceback.print_exc()
+    out = {}
+    if not loaded:
+        return out
+    records, _, enhanced = v5host.analyze_ragged_host([rgb for _, rgb, _ in loaded], quality=quality, want_enhanced=True, device=device)
+    for j, (rank, rgb, gray) in enumerate(loaded):
+        try:
+            if state.get("v5_keep_temp_jpeg", True):
+                _write_jpeg(os.path.join(ela_dir, f"temp_ela_{rank}.jpg"), rgb, quality, device, gpu_codec)
+            feats = features(records[j], rgb.shape[0] * rgb.shape[1])
+            feats["rank"] = rank
+            ela_path = os.path.join(ela_dir, f"ela_{rank}.jpg")
+            _write_jpeg(ela_path, enhanced[j], 75, device, gpu_codec)      # PIL's default quality (reference :81)
+            if state.get("v5_gpu_fft", True):
+                spectrum = v5host.spectrum_host(gray, device=device)
+            else:
+                log_mag = 20 * np.log(np.abs(np.fft.fftshift(np.fft.fft2(gray))) + 1)
+                spectrum = cv2.normalize(log_mag, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+            fft_path = os.path.join(ela_dir, f"fft_{rank}.jpg")
+            _write_jpeg(fft_path, spectrum, 95, device, gpu_codec)          # OpenCV's default quality (reference :91)
+            out[rank] = (feats, ela_path, fft_path)
+        except Exception as e:
+            print(f"Error analyzing face {rank}: {e}")
+            if debug:
+                traceback.print_exc()
+    return out
 
 
 def _ask_model(client, image_paths):
@@ -168,13 +188,30 @@ def run(state: dict) -> dict:
     if client is None:
         print("Node V5: OPENAI_API_KEY not found. Skipping OpenAI analysis.")
 
-    verdicts, per_face = [], []
+    # the GPU work of all selected crops in one batch (the reference decodes, re-encodes and transforms them one by one, :56-91)
+    present = []
     for rank, detection in enumerate(chosen):
         try:
             crop_path = detection["faces"][0]["crop_path"]
-            if not os.path.exists(crop_path):
+            if os.path.exists(crop_path):
+                present.append((rank, crop_path))
+        except Exception as e:
+            print(f"Error analyzing face {rank}: {e}")
+    try:
+        artefacts = _gpu_artefacts(present, ela_dir, state)
+    except Exception as e:                                      # no library / no GPU: every face fails the way one would (:140-144)
+        artefacts = {}
+        for rank, _ in present:
+            print(f"Error analyzing face {rank}: {e}")
+        if debug:
+            traceback.print_exc()
+
+    verdicts, per_face = [], []
+    for rank, crop_path in present:
+        try:
+            if rank not in artefacts:
                 continue
-            feats, ela_path, fft_path = _gpu_artefacts(crop_path, rank, ela_dir, state)
+            feats, ela_path, fft_path = artefacts[rank]
             per_face.append(feats)
             if client is None:
                 continue

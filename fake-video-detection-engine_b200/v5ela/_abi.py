@@ -15,10 +15,16 @@ EXPORTS = (
     "v5ela_enhance", "v5ela_reduce_records", "v5ela_analyze_host", "v5ela_launch_count", "v5ela_profile_enable",
     "v5ela_profile_read", "v5ela_spectrum", "v5ela_spectrum_host", "v5ela_jpeg_bound", "v5ela_jpeg_encode",
     "v5ela_jpeg_encode_host", "v5ela_jpeg_info", "v5ela_jpeg_info_batch", "v5ela_jpeg_decode", "v5ela_jpeg_decode_host",
-    "v5ela_last_instantiation", "v5ela_set_block_stage", "v5ela_get_block_stage",
+    "v5ela_last_instantiation", "v5ela_set_block_stage", "v5ela_get_block_stage", "v5ela_analyze_ragged", "v5ela_analyze_ragged_host",
 )
 BLOCK_STAGES = {"smem": 0, "mma": 1}
 INSTANTIATIONS = {0: "general", 1: "fast", 2: "texhist", -1: None}
+
+
+class FrameDesc(ctypes.Structure):
+    """v5ela_frame_desc (include/v5ela.h): one frame of a ragged batch."""
+    _fields_ = [("rgb", ctypes.c_void_p), ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("row_stride_bytes", ctypes.c_int64),
+                ("residual", ctypes.c_void_p), ("enhanced", ctypes.c_void_p)]
 
 
 class V5ElaError(RuntimeError):
@@ -58,6 +64,8 @@ def load() -> ctypes.CDLL:
     lib.v5ela_get_quant_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16)]
     lib.v5ela_analyze.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp]
     lib.v5ela_analyze_ex.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp]
+    lib.v5ela_analyze_ragged.argtypes = [vp, ctypes.POINTER(FrameDesc), i32, vp, vp]
+    lib.v5ela_analyze_ragged_host.argtypes = [vp, ctypes.POINTER(FrameDesc), i32, vp]
     lib.v5ela_enhance.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.v5ela_reduce_records.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.v5ela_analyze_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
@@ -131,6 +139,14 @@ class Handle:
         else:
             self._check(self._lib.v5ela_analyze(self._h, d_rgb, n, h, w, frame_stride, row_stride, d_records,
                                                 d_residual or None, stream or None))
+
+    def analyze_ragged(self, descs, n: int, d_records: int, stream: int | None):
+        """descs: ctypes array of FrameDesc holding DEVICE pointers; one launch for frames of different sizes."""
+        self._check(self._lib.v5ela_analyze_ragged(self._h, descs, n, d_records, stream or None))
+
+    def analyze_ragged_host(self, descs, n: int, records_host: int):
+        """descs: ctypes array of FrameDesc holding HOST pointers; synchronous."""
+        self._check(self._lib.v5ela_analyze_ragged_host(self._h, descs, n, records_host))
 
     def enhance(self, d_residual: int, d_records: int, n: int, h: int, w: int, d_enhanced: int, stream: int | None):
         self._check(self._lib.v5ela_enhance(self._h, d_residual, d_records, n, h, w, d_enhanced, stream or None))

@@ -77,6 +77,71 @@ def analyze_batch(frames, quality: int = 90, want_residual: bool = False, want_e
     return out
 
 
+def analyze_ragged(frames, quality: int = 90, want_residual: bool = False, want_enhanced: bool = False, records_out=None, handle=None):
+    """The fused kernel over frames of DIFFERENT sizes in one launch (v5ela_analyze_ragged) — the reference node's real input: face
+    crops (v5_texture_ela.py:56-64), here as they lie on the device, e.g. strided views into decoded keyframes (v5ela.handoff).
+
+    frames : sequence of torch.uint8 CUDA tensors (H_i, W_i, 3), pixels dense (stride 3 / 1), any row stride, all on one device.
+    Returns ``records`` uint8 (N, 3144) and, when asked, lists ``residual`` / ``enhanced`` of (H_i, W_i, 3) tensors. Asynchronous on
+    torch's current stream; no per-frame launches and no host synchronisation.
+    """
+    import torch
+
+    n = len(frames)
+    if n == 0:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = {"records": torch.empty((0, RECORD_BYTES), dtype=torch.uint8, device=dev)}
+        if want_residual:
+            out["residual"] = []
+        if want_enhanced:
+            out["enhanced"] = []
+        return out
+    dev = frames[0].device
+    views = []
+    for f in frames:
+        if not isinstance(f, torch.Tensor) or f.dtype != torch.uint8 or not f.is_cuda or f.dim() != 3 or f.shape[-1] != 3:
+            raise ValueError("frames must be torch.uint8 CUDA tensors of shape (H, W, 3)")
+        if f.device != dev:
+            raise ValueError("all frames must live on one device")
+        if f.shape[0] == 0 or f.shape[1] == 0:
+            raise ValueError("empty frame in a ragged batch")
+        if f.stride(2) != 1 or f.stride(1) != 3:
+            f = f.contiguous()
+        views.append(f)
+    hd = handle or get_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    if hd.quality != quality:
+        hd.set_quality(quality)
+    records = records_out if records_out is not None else torch.empty((n, RECORD_BYTES), dtype=torch.uint8, device=dev)
+    out = {"records": records}
+    resid = enh = None
+    if want_residual:                                           # one arena per kind, the maps are views into it
+        sizes = [f.shape[0] * f.shape[1] * 3 for f in views]
+        offs = [0]
+        for s_ in sizes:
+            offs.append(offs[-1] + (s_ + 255) // 256 * 256)
+        arena = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+        resid = [arena[offs[i]:offs[i] + sizes[i]].view(views[i].shape[0], views[i].shape[1], 3) for i in range(n)]
+        out["residual"] = resid
+    if want_enhanced:
+        sizes = [f.shape[0] * f.shape[1] * 3 for f in views]
+        offs = [0]
+        for s_ in sizes:
+            offs.append(offs[-1] + (s_ + 255) // 256 * 256)
+        arena_e = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+        enh = [arena_e[offs[i]:offs[i] + sizes[i]].view(views[i].shape[0], views[i].shape[1], 3) for i in range(n)]
+        out["enhanced"] = enh
+    descs = (_abi.FrameDesc * n)()
+    for i, f in enumerate(views):
+        descs[i].rgb = f.data_ptr()
+        descs[i].height, descs[i].width = int(f.shape[0]), int(f.shape[1])
+        descs[i].row_stride_bytes = int(f.stride(0))
+        descs[i].residual = resid[i].data_ptr() if resid is not None else None
+        descs[i].enhanced = enh[i].data_ptr() if enh is not None else None
+    hd.analyze_ragged(descs, n, records.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    out["_keepalive"] = views                                   # contiguous copies (if any) must outlive the asynchronous launch
+    return out
+
+
 def reduce_records(records, group: int, handle=None):
     """Per-video aggregation on the device: (N, 3144) -> (N // group, 3144)."""
     import torch

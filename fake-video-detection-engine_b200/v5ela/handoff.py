@@ -28,6 +28,22 @@ def select_faces(boxes, frame_w: int, frame_h: int):
     return [(i, f) for i, f in enumerate(faces) if f["area"] >= frame_w * frame_h * 0.005]
 
 
+def _encode_checked(images, quality: int):
+    """jpeg.encode_batch with the overflow rule enforced: a file that did not fit the default capacity (sizes[i] > capacity, bytes
+    undefined) makes the whole group go again with the capacity that always fits (v5ela_jpeg_bound). Returns host (files, sizes)."""
+    from . import jpeg
+
+    files, sizes = jpeg.encode_batch(images, quality)
+    files_h, sizes_h = files.cpu(), sizes.cpu()
+    if bool((sizes_h > files_h.shape[1]).any()):
+        ch = 3 if images.dim() == 4 else 1
+        files, sizes = jpeg.encode_batch(images, quality, capacity=jpeg.bound(int(images.shape[1]), int(images.shape[2]), ch))
+        files_h, sizes_h = files.cpu(), sizes.cpu()
+        if bool((sizes_h > files_h.shape[1]).any()):
+            raise RuntimeError("JPEG encoder overflowed its bound capacity")
+    return files_h, sizes_h
+
+
 def face_detections_on_device(frames, frame_ids, boxes_per_frame, data_dir=None, fps: float = 1.0, write_files: bool = True,
                               quality: int = 90):
     """frames: uint8 CUDA tensor (N, H, W, 3), RGB. boxes_per_frame: per frame, the detector's boxes (see select_faces).
@@ -35,24 +51,51 @@ def face_detections_on_device(frames, frame_ids, boxes_per_frame, data_dir=None,
     Returns (face_detections, features): ``face_detections`` has V1's structure (v1…:168-180), with ``crop_path`` /
     ``keyframe_path`` pointing at JPEG files encoded on the GPU (cv2.imwrite's bytes; skipped when write_files is False);
     ``features`` maps (frame index, face index) -> the V5F v1 feature dict computed from the crop view on the device.
+    All crops of the batch — whatever their sizes — are analysed by ONE ragged launch (``analyze_ragged``) and their records come
+    back in one copy; the crop files are encoded one group of equally sized crops at a time (the encoder's batches are uniform).
     NOTE: V5 itself analyses the crop *file* after a JPEG round trip at quality 95; pass that decoded image instead when
     the reference's exact numbers are wanted — ``analyze_jpeg_files`` does that on the GPU.
     """
     import torch
 
-    from . import jpeg
-    from .batch import analyze_batch
+    from .batch import analyze_ragged
     from .records import as_records, features
 
     n, fh, fw, _ = frames.shape
-    detections, feats = [], {}
     faces_dir = keyframes_dir = None
+    kf_files = kf_sizes = None
     if write_files:
         faces_dir, keyframes_dir = os.path.join(data_dir, "faces"), os.path.join(data_dir, "keyframes")
         os.makedirs(faces_dir, exist_ok=True)
         os.makedirs(keyframes_dir, exist_ok=True)
-        kf_files, kf_sizes = jpeg.encode_batch(frames, 95)                  # cv2.imwrite default quality
-        kf_files, kf_sizes = kf_files.cpu(), kf_sizes.cpu()
+        kf_files, kf_sizes = _encode_checked(frames, 95)                    # cv2.imwrite default quality
+    # every crop of the batch: (frame index, face index, face, box, view)
+    crops = []
+    for k in range(n):
+        for i, face in select_faces(boxes_per_frame[k], fw, fh):
+            x1, y1, x2, y2 = crop_box(face, fw, fh)
+            if x2 > x1 and y2 > y1:
+                crops.append((k, i, face, (x1, y1, x2, y2), frames[k, y1:y2, x1:x2]))
+    feats = {}
+    if crops:
+        out = analyze_ragged([c[4] for c in crops], quality=quality)       # one launch, one download
+        recs = as_records(out["records"].cpu())
+        for j, (k, i, _, (x1, y1, x2, y2), _) in enumerate(crops):
+            feats[(k, i)] = features(recs[j], (y2 - y1) * (x2 - x1))
+    crop_bytes = {}
+    if write_files and crops:
+        groups = {}
+        for j, c in enumerate(crops):
+            groups.setdefault((c[4].shape[0], c[4].shape[1]), []).append(j)
+        for (_, _), members in groups.items():
+            batch = torch.stack([crops[j][4] for j in members])           # equally sized crops: one encoder batch
+            files_h, sizes_h = _encode_checked(batch, 95)
+            for m, j in enumerate(members):
+                crop_bytes[j] = files_h[m, :int(sizes_h[m])].numpy().tobytes()
+    detections = []
+    by_frame = {}
+    for j, c in enumerate(crops):
+        by_frame.setdefault(c[0], []).append(j)
     for k in range(n):
         frame_id = int(frame_ids[k])
         keyframe_path = None
@@ -61,20 +104,15 @@ def face_detections_on_device(frames, frame_ids, boxes_per_frame, data_dir=None,
             with open(keyframe_path, "wb") as fh_:
                 fh_.write(kf_files[k, :int(kf_sizes[k])].numpy().tobytes())
         in_frame = []
-        for i, face in select_faces(boxes_per_frame[k], fw, fh):
-            x1, y1, x2, y2 = crop_box(face, fw, fh)
-            view = frames[k:k + 1, y1:y2, x1:x2]
-            rec = analyze_batch(view, quality=quality)["records"]
-            feats[(k, i)] = features(as_records(rec.cpu())[0], (y2 - y1) * (x2 - x1))
+        for j in by_frame.get(k, []):
+            _, i, face, _, _ = crops[j]
             crop_path = None
             if write_files:
-                data, size = jpeg.encode_batch(view, 95)
                 crop_path = os.path.join(faces_dir, f"face_{frame_id:06d}_{i}.jpg")
                 with open(crop_path, "wb") as fh_:
-                    fh_.write(data[0, :int(size[0])].cpu().numpy().tobytes())
+                    fh_.write(crop_bytes[j])
             in_frame.append({"bbox": {"x": face["x"], "y": face["y"], "w": face["w"], "h": face["h"]},
                              "confidence": face["confidence"], "is_main": i == 0, "crop_path": crop_path})
         detections.append({"frame_id": frame_id, "timestamp": frame_id / fps if fps else 0.0, "faces": in_frame,
                            "keyframe_path": keyframe_path})
-    torch.cuda.synchronize(frames.device)
     return detections, feats

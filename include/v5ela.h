@@ -11,7 +11,10 @@
  * cross the boundary; v5ela_last_error() gives a handle-owned message. All image/record pointers are DEVICE
  * pointers owned by the caller unless the name says `host`. Calls are asynchronous on the given CUDA stream and do
  * not synchronise or allocate after the first call at a given geometry. A handle is bound to one device and is not
- * thread-safe; the library is (one handle per thread).
+ * thread-safe; the library is (one handle per thread). One thread may use its handle on several CUDA streams: the handle owns
+ * scratch memory (work-item counter, host-path / spectrum / codec workspaces) that every call reuses, so a call issued on another
+ * stream than the previous call first waits — on the device, cudaStreamWaitEvent, no host synchronisation — for that call's
+ * last launch. Calls on one stream are ordered by the stream itself. Caller-owned buffers are the caller's to order.
  */
 #ifndef V5ELA_H
 #define V5ELA_H
@@ -109,6 +112,30 @@ V5ELA_API int v5ela_analyze(v5ela_handle *h, const uint8_t *d_rgb, int n, int he
 V5ELA_API int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, int width,
                      int64_t frame_stride_bytes, int64_t row_stride_bytes,
                      void *d_records, uint8_t *d_residual, uint32_t *d_tex_hist, void *cuda_stream);
+
+/*
+ * The same analysis for a RAGGED batch — frames of different sizes in ONE launch. This is the reference node's real input: at
+ * most three face crops of different sizes per call (v5_texture_ela.py:42, 56-64), cut by V1 with its 20 % padding rule
+ * (v1_keyframes_facetrack.py:144-166). Every frame brings its own pointer, size and row stride; record i belongs to frame i.
+ *   frames_host : HOST array of n descriptors whose pointers are DEVICE pointers (frames may live anywhere: separate allocations,
+ *                 strided views into one keyframe, ...). residual / enhanced are optional per frame: tightly packed h*w*3 maps,
+ *                 `diff` (v5…:70) and `ImageEnhance.Brightness(diff).enhance(255.0 / max_diff)` (v5…:74-78); they may alias.
+ *   d_records   : n records, overwritten.
+ * The descriptor table goes to the device through a small pinned staging buffer inside the handle (the only host work besides
+ * filling it). Asynchronous on `cuda_stream`; launches: memsets, the fused kernel, the finalize kernel and — only when a frame
+ * asks for an enhanced map — one enhancement kernel for the whole batch.
+ */
+typedef struct v5ela_frame_desc {
+    const uint8_t *rgb;         /* uint8 HWC RGB */
+    int32_t height, width;
+    int64_t row_stride_bytes;   /* >= 3 * width */
+    uint8_t *residual;          /* optional */
+    uint8_t *enhanced;          /* optional */
+} v5ela_frame_desc;
+V5ELA_API int v5ela_analyze_ragged(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *d_records, void *cuda_stream);
+/* The same with HOST pointers in the descriptors and a HOST record array (what the drop-in node calls for its <= 3 crops): one
+ * packed upload, one launch sequence, one download; synchronises before returning. */
+V5ELA_API int v5ela_analyze_ragged_host(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *records_host);
 
 /*
  * Brightness enhancement of the residual map: `ImageEnhance.Brightness(diff).enhance(255.0 / max_diff)`

@@ -11,11 +11,14 @@
 #include "v5ela_workitem.cuh"
 #include "v5ela_host.h"
 
+static int g_target_items = 0;       // v5emu_set_target_items: the host's small-batch decomposition (short segments, narrow strips)
+extern "C" void v5emu_set_target_items(int t) { g_target_items = t; }
+
 extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t frame_stride, int64_t row_stride,
                              int quality, v5ela_record *records, uint8_t *residual, int seg_rows, uint32_t *tex_hist)
 {
     v5::KParams p;
-    if (v5::fill_params(p, rgb, n, h, w, frame_stride, row_stride, records, residual, quality, seg_rows) != 0) return -1;
+    if (v5::fill_params(p, rgb, n, h, w, frame_stride, row_stride, records, residual, quality, seg_rows, g_target_items) != 0) return -1;
     p.tex_hist = tex_hist;
     static v5::mma::LaneConsts lane_consts[32];
     if (!v5::mma::make_lane_consts(lane_consts)) return -2;
@@ -31,6 +34,51 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
         else if (v5::fast_path_ok(p)) v5::process_work_item<true, false>(*S, p, work, acc.data());
         else v5::process_work_item<false, false>(*S, p, work, acc.data());
     }
+    for (int i = 0; i < n; i++) v5::finalize_record(records[i]);
+    free(S);
+    return 0;
+}
+
+// The RAGGED instantiation: n frames of different sizes (tightly packed, one after the other in `rgb`), one work-item space.
+extern "C" int v5emu_analyze_ragged(const uint8_t *rgb, const int *hw, int n, int quality, v5ela_record *records, uint8_t *residual,
+                                    int seg_rows)
+{
+    std::vector<v5::FrameDesc> tab((size_t)n);
+    size_t off = 0;
+    uint32_t total = 0;
+    for (int i = 0; i < n; i++) {
+        const int h = hw[2 * i], w = hw[2 * i + 1];
+        v5::FrameDesc &d = tab[(size_t)i];
+        d.rgb = rgb + off;
+        d.resid = residual ? residual + off : nullptr;
+        d.row_stride = 3 * (int64_t)w;
+        d.h = h; d.w = w; d.mw = (w + 15) / 16; d.mh = (h + 15) / 16;
+        d.n_strips = (d.mw + v5::TW_MAX - 1) / v5::TW_MAX;
+        const int sr = seg_rows > 0 ? seg_rows : 17;
+        d.n_segs = (d.mh + sr - 1) / sr;
+        d.work_base = total;
+        total += (uint32_t)(d.n_strips * d.n_segs);
+        d.flags = (((uintptr_t)d.rgb | (uintptr_t)d.row_stride) & 15) == 0 ? 1u : 0u;
+        if (d.resid && (((uintptr_t)d.resid | (uintptr_t)(3 * w)) & 15) == 0) d.flags |= 2u;
+        off += (size_t)h * w * 3;
+    }
+    v5::KParams p;
+    memset(&p, 0, sizeof(p));
+    p.records = records;
+    p.n = n;
+    p.frames = tab.data();
+    static v5::mma::LaneConsts lane_consts[32];
+    if (!v5::mma::make_lane_consts(lane_consts)) return -2;
+    p.lane_consts = lane_consts;
+    uint16_t ql[64], qc[64];
+    v5::quant_tables(quality, ql, qc);
+    v5::make_quant(ql, p.q[0]);
+    v5::make_quant(qc, p.q[1]);
+    memset(records, 0, sizeof(v5ela_record) * (size_t)n);
+    v5::Smem *S = (v5::Smem *)aligned_alloc(16, sizeof(v5::Smem));
+    memset(S, 0xA5, sizeof(v5::Smem));
+    std::vector<v5::ThreadAcc> acc(v5::NT);
+    for (uint32_t work = 0; work < total; work++) v5::process_work_item<false, false, true>(*S, p, (int)work, acc.data());
     for (int i = 0; i < n; i++) v5::finalize_record(records[i]);
     free(S);
     return 0;

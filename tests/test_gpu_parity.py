@@ -257,6 +257,45 @@ def test_repeated_calls_are_deterministic():
         assert torch.equal(a, b)
 
 
+def test_one_handle_on_two_streams():
+    """A thread's cached handle used alternately on two CUDA streams (round-1 ADVICE): the handle-owned scratch — the work-item
+    ticket of the fused kernel, the codec and spectrum workspaces — is reused by every call, so a call on another stream has to
+    wait for the previous call's kernels. Long launches on one stream, short ones on the other, results against serial runs."""
+    import torch
+    import v5ela
+    from v5ela import jpeg
+
+    big = gen_batch_torch(0, 48, 720, 1280, seed=3)
+    small = gen_batch_torch(7, 3, 96, 160, seed=4)
+    gray = small[..., 1].contiguous()
+    ref_big = v5ela.analyze_batch(big)["records"].clone()
+    ref_small = v5ela.analyze_batch(small)["records"].clone()
+    ref_spec = v5ela.spectrum_batch(gray).clone()
+    ref_enc, ref_sizes = jpeg.encode_batch(small, 90)
+    ref_enc, ref_sizes = ref_enc.clone(), ref_sizes.clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for it in range(12):
+        with torch.cuda.stream(s1):
+            a = v5ela.analyze_batch(big)["records"]
+        with torch.cuda.stream(s2):
+            b = v5ela.analyze_batch(small)["records"]
+            sp = v5ela.spectrum_batch(gray) if it % 3 == 0 else None
+            enc = jpeg.encode_batch(small, 90) if it % 3 == 1 else None
+        outs.append((a, b, sp, enc))
+    torch.cuda.synchronize()
+    for a, b, sp, enc in outs:
+        assert torch.equal(a, ref_big) and torch.equal(b, ref_small)
+        if sp is not None:
+            assert torch.equal(sp, ref_spec)
+        if enc is not None:
+            assert torch.equal(enc[1], ref_sizes)
+            for i in range(3):
+                n = int(ref_sizes[i])
+                assert torch.equal(enc[0][i, :n], ref_enc[i, :n])
+
+
 def test_two_host_threads_with_their_own_handles():
     """The node may run next to V2/V3/V4 on LangGraph's worker threads: one handle per thread (thread-local in
     v5ela.batch / v5ela.host), concurrent calls, identical results."""

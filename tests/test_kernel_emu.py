@@ -127,6 +127,49 @@ def test_emulated_kernel_vs_reference_goldens(emu):
         assert record_matches_golden(recs[0], case) == []
 
 
+@pytest.mark.parametrize("seg", [0, 2])
+def test_emulated_ragged_instantiation_vs_oracle(emu, seg):
+    """v5ela_analyze_ragged's kernel instantiation: frames of different sizes share one work-item space (binary search over the
+    frame table per work item); every frame against the oracle."""
+    import ctypes
+
+    sizes = [(1, 1), (17, 33), (16, 16), (40, 48), (33, 497), (9, 976), (100, 1000), (2, 3)]
+    rng = np.random.default_rng(7)
+    frames = [gen_frame(i, h, w, 2) if i % 2 == 0 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(sizes)]
+    blob = np.concatenate([f.reshape(-1) for f in frames])
+    hw = np.array(sizes, np.int32).reshape(-1)
+    recs = np.zeros(len(sizes), RECORD_DTYPE)
+    res = np.zeros_like(blob)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    rc = emu.lib.v5emu_analyze_ragged(blob.ctypes.data_as(u8p), hw.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(sizes), 90,
+                                      recs.ctypes.data_as(ctypes.c_void_p), res.ctypes.data_as(u8p), seg)
+    assert rc == 0
+    off = 0
+    for i, f in enumerate(frames):
+        o = c_oracle.analyze_frame(f, 90)
+        assert recs[i].tobytes() == o["record"].tobytes(), sizes[i]
+        assert np.array_equal(res[off:off + f.size].reshape(f.shape), o["residual"]), sizes[i]
+        off += f.size
+
+
+@pytest.mark.parametrize("hw", [(257, 301), (40, 1000), (64, 96), (300, 48)])
+def test_emulated_small_batch_decomposition(emu, hw):
+    """Batches that cannot fill the GPU get short segments and narrow strips (csrc/v5ela_host.h fill_params / widen_strips: down to
+    4 MCU rows x 4 MCU columns per work item); same records and residual map as the default decomposition and the oracle."""
+    h, w = hw
+    frame = gen_frame(1, h, w, 7)
+    o = c_oracle.analyze_frame(frame, 90)
+    try:
+        emu.lib.v5emu_set_target_items(592)                  # 2 x 148 SMs x 2 CTAs
+        for want_residual in (True, False):
+            recs, res = emu(frame[None], 90, 0, want_residual=want_residual)
+            assert recs[0].tobytes() == o["record"].tobytes()
+            if want_residual:
+                assert np.array_equal(res[0], o["residual"])
+    finally:
+        emu.lib.v5emu_set_target_items(0)
+
+
 def adversarial_blocks_frame(rng=None):
     """A frame whose 8x8 blocks drive the intermediates of the round trip to their extremes: for every pair (u, v) the sign
     pattern of the 2-D basis function (u, v) at full swing (0 / 255) and its negative — these maximise the forward row / column

@@ -223,8 +223,22 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const uint8_t *__restrict
     extern __shared__ double2 fbuf[];
     const int y0 = 2 * blockIdx.x, y1 = y0 + 1;
     const uint8_t *src = gray + (int64_t)blockIdx.y * frame_stride;
-    for (int x = threadIdx.x; x < w; x += blockDim.x)
-        fbuf[x] = make_double2((double)src[(int64_t)y0 * row_stride + x], y1 < h ? (double)src[(int64_t)y1 * row_stride + x] : 0.0);
+    // all of a thread's pixels are requested before the first one is converted (memory-level parallelism: the kernel is latency-bound)
+    const uint8_t *r0 = src + (int64_t)y0 * row_stride, *r1 = src + (int64_t)(y1 < h ? y1 : y0) * row_stride;
+    for (int xb = 0; xb < w; xb += 4 * blockDim.x) {
+        uint8_t a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = xb + j * blockDim.x + threadIdx.x;
+            a[j] = x < w ? r0[x] : 0;
+            b[j] = x < w ? r1[x] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = xb + j * blockDim.x + threadIdx.x;
+            if (x < w) fbuf[x] = make_double2((double)a[j], y1 < h ? (double)b[j] : 0.0);
+        }
+    }
     __syncthreads();
     const double2 *res = stockham(fbuf, fbuf + w, 1, plan, tw);
     double2 *ga = g + ((int64_t)blockIdx.y * h + y0) * wh;
@@ -245,9 +259,20 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict
     if (threadIdx.x == 0) { smin = ~0ull; smax = 0ull; }
     const int v0 = blockIdx.x * cc;
     const double2 *src = g + (int64_t)blockIdx.y * h * wh;
-    for (int i = threadIdx.x; i < h * cc; i += blockDim.x) {
-        const int y = i / cc, c = i - y * cc;
-        fbuf[c * h + y] = v0 + c < wh ? src[(int64_t)y * wh + v0 + c] : make_double2(0.0, 0.0);
+    for (int ib = 0; ib < h * cc; ib += 4 * blockDim.x) {          // four loads in flight per thread before the first store
+        double2 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = ib + j * blockDim.x + threadIdx.x;
+            const int y = i / cc, c = i - y * cc;
+            t[j] = (i < h * cc && v0 + c < wh) ? src[(int64_t)y * wh + v0 + c] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = ib + j * blockDim.x + threadIdx.x;
+            const int y = i / cc, c = i - y * cc;
+            if (i < h * cc) fbuf[c * h + y] = t[j];
+        }
     }
     __syncthreads();
     const double2 *res = stockham(fbuf, fbuf + cc * h, cc, plan, tw);

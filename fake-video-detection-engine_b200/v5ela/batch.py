@@ -173,15 +173,16 @@ def spectrum_batch(gray, handle=None):
     return out
 
 
-def analyze_jpeg_files(files, quality: int = 90, device=0, want_residual: bool = False, want_enhanced: bool = False):
+def analyze_jpeg_files(files, quality: int = 90, device=0, want_residual: bool = False, want_enhanced: bool = False, handle=None):
     """Keyframes / crops as the reference holds them — JPEG files (bytes), all of one size — decoded on the GPU (pixel-identical
     to Image.open(..).convert('RGB'), v5_texture_ela.py:64) and analysed without the pixels ever crossing PCIe: only the
     compressed bytes go up and the records come down. Returns analyze_batch's dict plus ``rgb`` (the decoded frames) and
     ``status`` (int32 per file, 0 = ok)."""
     from . import jpeg
 
-    dec = jpeg.decode_batch(files, device=device, want_rgb=True)
-    out = analyze_batch(dec["rgb"], quality=quality, want_residual=want_residual, want_enhanced=want_enhanced)
+    dec = jpeg.decode_batch(files, device=device, want_rgb=True, handle=handle)
+    out = analyze_batch(dec["rgb"], quality=quality, want_residual=want_residual, want_enhanced=want_enhanced, handle=handle)
     out["rgb"] = dec["rgb"]
     out["status"] = dec["status"]
     return out
+

@@ -136,7 +136,7 @@ def decode_host(files, want_rgb: bool = True, want_gray: bool = False, device: i
     return out
 
 
-def decode_batch(files, device=0, want_rgb: bool = True, want_gray: bool = False):
+def decode_batch(files, device=0, want_rgb: bool = True, want_gray: bool = False, handle=None):
     """files: list of bytes (or uint8 arrays), all the same size -> {'rgb': uint8 CUDA tensor [N,H,W,3], 'gray': [N,H,W],
     'status': int32 [N]}, asynchronous on the current stream. Header parsing happens on the calling thread; pageable files are
     staged before the call returns, files that are views into pinned memory are read asynchronously (keep the arena alive)."""
@@ -157,7 +157,7 @@ def decode_batch(files, device=0, want_rgb: bool = True, want_gray: bool = False
     if want_gray:
         out["gray"] = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     keep, ptrs, lens = table
-    get_handle(dev.index or 0).jpeg_decode(ptrs, lens, n, out["rgb"].data_ptr() if want_rgb else None, None,
+    (handle or get_handle(dev.index or 0)).jpeg_decode(ptrs, lens, n, out["rgb"].data_ptr() if want_rgb else None, None,
                                            out["gray"].data_ptr() if want_gray else None, None, out["status"].data_ptr(),
                                            torch.cuda.current_stream(dev).cuda_stream)
     del keep

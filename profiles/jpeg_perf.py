@@ -55,6 +55,24 @@ def main():
         print(f"{h}x{w} q{q}: mean file {sz.mean() / 1e3:8.1f} kB | encode RGB {cnt / t_enc * 1e3:9.0f} img/s ({t_enc:7.2f} ms)"
               f" | encode gray q95 {cnt / t_enc_g * 1e3:9.0f} img/s | decode {cnt / t_dec_wall * 1e3:9.0f} img/s (wall clock per call incl. header"
               f" parsing and upload {t_dec_wall:7.2f} ms back to back; one call alone {t_dec:7.2f} ms; first call {t_first:7.1f} ms) status ok={int((out['status'] == 0).all())}")
+    # restart intervals (IMWRITE_JPEG_RST_INTERVAL, one interval per MCU row / per 8 MCUs): files OpenCV writes on request; the
+    # decoder takes them through huffman_rst_kernel (one thread per interval)
+    import cv2
+    for interval in (120, 8):
+        frames_np = v5ela.gen_batch(0, min(n, 32), 1080, 1920, seed=0)
+        blobs = [cv2.imencode(".jpg", np.ascontiguousarray(f[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, interval])[1].tobytes()
+                 for f in frames_np]
+        out = jpeg.decode_batch(blobs)
+        torch.cuda.synchronize()
+        ok = bool((out["status"] == 0).all()) and bool(np.array_equal(out["rgb"][0].cpu().numpy(),
+                                                                     cv2.imdecode(np.frombuffer(blobs[0], np.uint8), cv2.IMREAD_COLOR)[..., ::-1]))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            jpeg.decode_batch(blobs)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / 3 * 1e3
+        print(f"1080x1920 q90, restart interval {interval} MCUs ({(120 * 68 + interval - 1) // interval} intervals per file), {len(blobs)} files: decode "
+              f"{len(blobs) / t * 1e3:9.0f} img/s ({t:7.2f} ms per call, wall clock) pixels == OpenCV: {ok}")
     # the CPU libraries on this box, one thread, same work
     from PIL import Image
     import cv2

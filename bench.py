@@ -428,7 +428,10 @@ def run_native_arm(args):
     e2e_step()
     e1.record()
     barrier()
-    Ke = max(2, min(50, int(math.ceil(min(args.min_seconds, 1.0) * 1e3 / max(e0.elapsed_time(e1), 1e-3)))))
+    est_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:                                               # every rank must run the same number of steps: they end in a collective
+        dist.all_reduce(est_e, op=dist.ReduceOp.MAX)
+    Ke = max(2, min(50, int(math.ceil(min(args.min_seconds, 1.0) * 1e3 / max(float(est_e.item()), 1e-3)))))
     barrier()
     e0.record()
     for _ in range(Ke):

@@ -14,7 +14,6 @@ for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
   out=profiles/variants/lib_${name}.so
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
-       -Iinclude -I$C $flags -Xptxas -v -shared -o $out $C/v5ela.cu $C/v5jpeg.cu -lcudart -lpthread 2>&1 \
-    | grep -A2 "Function properties for _ZN2v516ela_fused_kernelILb1ELb0" | grep -E "registers|spill" | sed "s|^|$out <FAST>: |"
-  echo "$out: $(cuobjdump -sass -fun '_ZN2v516ela_fused_kernelILb1ELb0EEEvNS_7KParamsEi' $out 2>/dev/null | grep -cE '^\s+/\*[0-9a-f]{4}\*/') SASS instructions in <FAST>"
+       -Iinclude -I$C $flags -Xptxas -v -shared -o $out $C/v5ela.cu $C/v5ela_mma.cu $C/v5jpeg.cu -lcudart -lpthread 2>&1 \
+    | grep -A2 -E "Function properties for _ZN(2v5|3v5m)16ela_fused_kernelILb1ELb0ELb0" | grep -E "Function|registers|spill" | sed -E "s|.*_ZN(2v5\|3v5m)16ela.*|  build \1 <FAST>:|" | sed "s|^|$out |"
 done

@@ -551,9 +551,16 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
         h->tw_h_n = height;
         h->launches++;
     }
-    // frames per pass: keep the float64 workspace (24 bytes per half-spectrum sample) under ~1 GiB
+    // frames per pass: keep the float64 workspace (24 bytes per half-spectrum sample) under ~1 GiB. Smaller, L2-sized passes were
+    // measured and are SLOWER (profiles/r02/spectrum.txt: 64 MB -10 %, 32 MB -25 %): the passes are bound by their own latency chains,
+    // not by where the intermediate lives. V5ELA_SPEC_CHUNK_MB overrides (tuning knob).
     const size_t per_frame = (size_t)height * wh;
-    int chunk = (int)((size_t)(1u << 30) / (per_frame * 24));
+    size_t chunk_bytes = (size_t)1 << 30;
+    if (const char *env = getenv("V5ELA_SPEC_CHUNK_MB")) {
+        const long v = atol(env);
+        if (v >= 1 && v <= 4096) chunk_bytes = (size_t)v << 20;
+    }
+    int chunk = (int)(chunk_bytes / (per_frame * 24));
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
     if (chunk > 65535) chunk = 65535;

@@ -526,6 +526,18 @@ int v5ela_analyze_host(v5ela_handle *h, const uint8_t *rgb_host, int n, int heig
     return V5ELA_OK;
 }
 
+// threads per CTA of the FFT kernels: 256; 512 measured no faster (profiles/r02/spectrum.txt). V5ELA_FFT_THREADS overrides
+// (tuning knob: 128 / 256 / 512)
+static unsigned fft_threads(int points)
+{
+    if (const char *env = getenv("V5ELA_FFT_THREADS")) {
+        const int v = atoi(env);
+        if (v == 128 || v == 256 || v == 512) return (unsigned)v;
+    }
+    (void)points;
+    return 256u;
+}
+
 int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, int width, int64_t frame_stride_bytes,
                    int64_t row_stride_bytes, uint8_t *d_out, void *cuda_stream)
 {
@@ -574,7 +586,7 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
     const char *fft_env = getenv("V5ELA_FFT");
     const size_t rows_smem = sizeof(double2) * 2 * (size_t)width;
     int cc = (int)((size_t)(96u << 10) / (sizeof(double2) * 2 * (size_t)height));
-    cc = cc > 4 ? 4 : cc;
+    cc = cc >= 4 ? 4 : (cc >= 2 ? 2 : cc);                      // 1, 2 or 4 adjacent columns per CTA (the kernel shifts and masks)
     const size_t cols_smem = sizeof(double2) * 2 * (size_t)(cc > 0 ? cc : 1) * (size_t)height;
     const bool fast = !(fft_env && atoi(fft_env) == 0) && v5fft::make_plan(width, plan_w) && v5fft::make_plan(height, plan_h) &&
                       cc >= 1 && rows_smem <= (200u << 10) && cols_smem <= (200u << 10) && n <= 65535;
@@ -589,11 +601,11 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
         V5_CUDA(h, cudaMemsetAsync(h->d_minmax, 0, sizeof(unsigned long long) * 2 * (size_t)fn, st));
         V5_CUDA(h, cudaMemset2DAsync(h->d_minmax, 16, 0xff, 8, (size_t)fn, st));
         if (fast) {
-            v5fft::fft_rows_kernel<<<dim3((unsigned)((height + 1) / 2), (unsigned)fn), 256, rows_smem, st>>>(
+            v5fft::fft_rows_kernel<<<dim3((unsigned)((height + 1) / 2), (unsigned)fn), fft_threads(width), rows_smem, st>>>(
                 d_gray + (int64_t)f0 * frame_stride_bytes, frame_stride_bytes, row_stride_bytes, height, width, wh, plan_w, h->tw_w,
                 static_cast<double2 *>(h->d_g));
             V5_CUDA(h, cudaGetLastError());
-            v5fft::fft_cols_kernel<<<dim3((unsigned)((wh + cc - 1) / cc), (unsigned)fn), 256, cols_smem, st>>>(
+            v5fft::fft_cols_kernel<<<dim3((unsigned)((wh + cc - 1) / cc), (unsigned)fn), fft_threads(cc * height), cols_smem, st>>>(
                 static_cast<const double2 *>(h->d_g), height, wh, cc, plan_h, h->tw_h, static_cast<double *>(h->d_ms),
                 static_cast<unsigned long long *>(h->d_minmax));
             V5_CUDA(h, cudaGetLastError());
@@ -607,9 +619,11 @@ int v5ela_spectrum(v5ela_handle *h, const uint8_t *d_gray, int n, int height, in
                                                        static_cast<double *>(h->d_ms), static_cast<unsigned long long *>(h->d_minmax));
             V5_CUDA(h, cudaGetLastError());
         }
-        long long bx = ((long long)height * width + 255) / 256;
-        if (bx > 8LL * h->sm_count) bx = 8LL * h->sm_count;
-        v5fft::spectrum_image_kernel<<<dim3((unsigned)bx, 1, (unsigned)fn), 256, 0, st>>>(
+        // every CTA walks ~16 rows: the per-thread set-up (the double-precision 255 / (max - min)) is paid once per 16 pixels
+        const unsigned bx = (unsigned)((width + 255) / 256);
+        unsigned by = (unsigned)((height + 15) / 16);
+        by = by < 1 ? 1 : (by > 65535 ? 65535 : by);
+        v5fft::spectrum_image_kernel<<<dim3(bx, by, (unsigned)fn), 256, 0, st>>>(
             static_cast<const double *>(h->d_ms), static_cast<const unsigned long long *>(h->d_minmax), height, width, wh,
             d_out + (int64_t)f0 * height * width);
         V5_CUDA(h, cudaGetLastError());

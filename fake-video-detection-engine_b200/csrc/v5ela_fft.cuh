@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) dft_cols_kernel(const double2 *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Fast path for sizes whose prime factors are all in {2, 3, 5} (every common video size): mixed-radix Stockham
+// Fast path for sizes whose prime factors are all in {2, 3, 5} (every common video size): mixed-radix (5, 3, 4, 2) Stockham
 // autosort FFT in shared memory, float64. One stage of radix r over a sequence of current length n and stride s
 // (n * s == N): for p in [0, n/r), q in [0, s):
 //     a_t = x[q + s*(p + t*n/r)],  b_u = (sum_t a_t w_r^{t u}) * exp(-2 pi i p u s / N),  y[q + s*(r*p + u)] = b_u
@@ -137,20 +137,32 @@ struct FftPlan {
     int n;
     int nst;
     int radix[24];
+    uint32_t inv_s[24];         // floor(2^32 / s) + 1 for the stride s of every stage: idx / s == umulhi(idx, inv_s) for idx < 2^16
+    uint32_t inv_per_seq[24];   // the same for N / radix (butterflies per sequence)
 };
+
+// exact unsigned division of a < 2^16 by d in 2..2^16 through its reciprocal (error term a / 2^32 < 1 / d)
+__host__ __device__ __forceinline__ uint32_t recip_u16(uint32_t d) { return (uint32_t)(0x100000000ull / d) + 1u; }
+__device__ __forceinline__ int div_u16(int a, uint32_t inv) { return (int)__umulhi((uint32_t)a, inv); }
 
 // Host: factor n into 5s, 3s and 2s; returns false when another prime factor remains.
 inline bool make_plan(int n, FftPlan &plan)
 {
     plan.n = n;
     plan.nst = 0;
-    const int rs[3] = {5, 3, 2};
+    const int rs[4] = {5, 3, 4, 2};                             // radix 4 before 2: half the stages (barriers, shared-memory passes)
     for (int r : rs)
         while (n % r == 0 && plan.nst < 24) {
             plan.radix[plan.nst++] = r;
             n /= r;
         }
-    return n == 1;
+    int s = 1;
+    for (int st = 0; st < plan.nst; st++) {
+        plan.inv_s[st] = recip_u16((uint32_t)s);
+        plan.inv_per_seq[st] = recip_u16((uint32_t)(plan.n / plan.radix[st]));
+        s *= plan.radix[st];
+    }
+    return n == 1 && plan.n <= 65536;
 }
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -169,9 +181,10 @@ __device__ double2 *stockham(double2 *x, double2 *y, int nseq, const FftPlan &pl
     int n = N, s = 1;
     for (int st = 0; st < plan.nst; st++) {
         const int r = plan.radix[st], m = n / r, per_seq = N / r;
-        for (int wi = threadIdx.x; wi < nseq * per_seq; wi += blockDim.x) {
-            const int seq = wi / per_seq, idx = wi - seq * per_seq;
-            const int p = idx / s, q = idx - p * s;
+        const uint32_t inv_s = plan.inv_s[st], inv_ps = plan.inv_per_seq[st];
+        for (int wi = threadIdx.x; wi < nseq * per_seq; wi += blockDim.x) {     // wi < 4 * 32768: both divisions through reciprocals
+            const int seq = (nseq == 1 || per_seq == 1) ? (nseq == 1 ? 0 : wi) : div_u16(wi, inv_ps), idx = wi - seq * per_seq;
+            const int p = s == 1 ? idx : div_u16(idx, inv_s), q = idx - p * s;      // (the reciprocal of 1 does not fit 32 bits)
             const double2 *xi = x + seq * N + q + s * p;
             double2 *yo = y + seq * N + q + s * r * p;
             const int ms_ = s * m;                              // input stride between the r operands
@@ -179,6 +192,13 @@ __device__ double2 *stockham(double2 *x, double2 *y, int nseq, const FftPlan &pl
                 const double2 a0 = xi[0], a1 = xi[ms_];
                 yo[0] = cadd(a0, a1);
                 yo[s] = cmul(csub(a0, a1), tw[p * s]);
+            } else if (r == 4) {
+                const double2 a0 = xi[0], a1 = xi[ms_], a2 = xi[2 * ms_], a3 = xi[3 * ms_];
+                const double2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_neg_i(csub(a1, a3));
+                yo[0] = cadd(t0, t2);
+                yo[s] = cmul(cadd(t1, t3), tw[p * s]);
+                yo[2 * s] = cmul(csub(t0, t2), tw[2 * p * s]);
+                yo[3 * s] = cmul(csub(t1, t3), tw[3 * p * s]);
             } else if (r == 3) {
                 const double2 a0 = xi[0], a1 = xi[ms_], a2 = xi[2 * ms_];
                 const double2 t1 = cadd(a1, a2);
@@ -216,7 +236,7 @@ __device__ double2 *stockham(double2 *x, double2 *y, int nseq, const FftPlan &pl
 
 // Rows: two real rows ride in one complex transform (z = a + i b); the half spectra of both are separated with
 // A_k = (Z_k + conj(Z_{N-k}))/2, B_k = (Z_k - conj(Z_{N-k}))/(2i).
-__global__ void __launch_bounds__(256) fft_rows_kernel(const uint8_t *__restrict__ gray, int64_t frame_stride, int64_t row_stride,
+__global__ void __launch_bounds__(512) fft_rows_kernel(const uint8_t *__restrict__ gray, int64_t frame_stride, int64_t row_stride,
                                                        int h, int w, int wh, const __grid_constant__ FftPlan plan,
                                                        const double2 *__restrict__ tw, double2 *__restrict__ g)
 {
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const uint8_t *__restrict
 }
 
 // Columns: `cc` adjacent columns per CTA (cc * 16 contiguous bytes per row), transform, then |F|, 20 ln(|F|+1), min/max.
-__global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict__ g, int h, int wh, int cc,
+__global__ void __launch_bounds__(512) fft_cols_kernel(const double2 *__restrict__ g, int h, int wh, int cc,
                                                        const __grid_constant__ FftPlan plan, const double2 *__restrict__ tw,
                                                        double *__restrict__ ms, unsigned long long *__restrict__ minmax)
 {
@@ -259,18 +279,19 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict
     if (threadIdx.x == 0) { smin = ~0ull; smax = 0ull; }
     const int v0 = blockIdx.x * cc;
     const double2 *src = g + (int64_t)blockIdx.y * h * wh;
+    const int csh = cc == 4 ? 2 : (cc == 2 ? 1 : 0);              // cc is 1, 2 or 4 (host): i / cc and i % cc are a shift and a mask
     for (int ib = 0; ib < h * cc; ib += 4 * blockDim.x) {          // four loads in flight per thread before the first store
         double2 t[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = ib + j * blockDim.x + threadIdx.x;
-            const int y = i / cc, c = i - y * cc;
+            const int y = i >> csh, c = i & (cc - 1);
             t[j] = (i < h * cc && v0 + c < wh) ? src[(int64_t)y * wh + v0 + c] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = ib + j * blockDim.x + threadIdx.x;
-            const int y = i / cc, c = i - y * cc;
+            const int y = i >> csh, c = i & (cc - 1);
             if (i < h * cc) fbuf[c * h + y] = t[j];
         }
     }
@@ -279,10 +300,12 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict
     double *dst = ms + (int64_t)blockIdx.y * h * wh;
     unsigned long long lo = ~0ull, hi = 0ull;
     for (int i = threadIdx.x; i < h * cc; i += blockDim.x) {
-        const int u = i / cc, c = i - u * cc;
+        const int u = i >> csh, c = i & (cc - 1);
         if (v0 + c >= wh) continue;
         const double2 f = res[c * h + u];
-        const double m = 20.0 * log(hypot(f.x, f.y) + 1.0);
+        // |F| <= 255 H W < 2^33: the squares cannot overflow or underflow harmfully, so sqrt(re^2 + im^2) replaces hypot()'s
+        // scaling (same value to the last bit or two; the uint8 image has ~1.5 units of ms per grey level)
+        const double m = 20.0 * log(sqrt(fma(f.x, f.x, f.y * f.y)) + 1.0);
         dst[(int64_t)u * wh + v0 + c] = m;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
         lo = bits < lo ? bits : lo;
@@ -297,7 +320,8 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const double2 *__restrict
     }
 }
 
-// out[i][j] = u8(rint(ms_shifted[i][j] * scale + shift)), cv2.normalize(NORM_MINMAX, 0..255) + np.fft.fftshift
+// out[i][j] = u8(rint(ms_shifted[i][j] * scale + shift)), cv2.normalize(NORM_MINMAX, 0..255) + np.fft.fftshift.
+// grid (column blocks, rows, frames): no index divisions.
 __global__ void __launch_bounds__(256) spectrum_image_kernel(const double *__restrict__ ms, const unsigned long long *__restrict__ minmax,
                                                              int h, int w, int wh, uint8_t *__restrict__ out)
 {
@@ -307,19 +331,19 @@ __global__ void __launch_bounds__(256) spectrum_image_kernel(const double *__res
     const double shift = 0.0 - mn * scale;
     const double *src = ms + (int64_t)frame * h * wh;
     uint8_t *dst = out + (int64_t)frame * h * w;
-    const int64_t total = (int64_t)h * w;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / w), j = (int)(idx - (int64_t)i * w);
-        int u = i - h / 2, v = j - w / 2;                        // fftshift: y[i] = x[(i - n//2) mod n]
-        u = u < 0 ? u + h : u;
-        v = v < 0 ? v + w : v;
-        if (v >= wh) {                                           // Hermitian mirror: |F[u][v]| = |F[-u][-v]|
-            v = w - v;
-            u = u == 0 ? 0 : h - u;
+    for (int i = blockIdx.y; i < h; i += gridDim.y) {
+        int u0 = i - h / 2;                                      // fftshift: y[i] = x[(i - n//2) mod n]
+        u0 = u0 < 0 ? u0 + h : u0;
+        const int um = u0 == 0 ? 0 : h - u0;                     // Hermitian mirror row: |F[u][v]| = |F[-u][-v]|
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < w; j += gridDim.x * blockDim.x) {
+            int v = j - w / 2;
+            v = v < 0 ? v + w : v;
+            const int u = v >= wh ? um : u0;
+            v = v >= wh ? w - v : v;
+            double r = rint(__dadd_rn(__dmul_rn(src[(int64_t)u * wh + v], scale), shift));   // cvRound: ties to even
+            r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
+            dst[(int64_t)i * w + j] = (uint8_t)r;
         }
-        double r = rint(__dadd_rn(__dmul_rn(src[(int64_t)u * wh + v], scale), shift));   // cvRound: ties to even
-        r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
-        dst[idx] = (uint8_t)r;
     }
 }
 

@@ -698,4 +698,5 @@ int v5ela_set_block_stage(v5ela_handle *h, int mode)
 
 int v5ela_get_block_stage(const v5ela_handle *h) { return h ? h->block_stage : V5ELA_ERR_INVALID; }
 
+
 }  // extern "C"

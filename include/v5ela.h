@@ -256,8 +256,8 @@ V5ELA_API int v5ela_last_instantiation(const v5ela_handle *h);
  *   V5ELA_BLOCKS_SMEM  four threads per block, ISLOW butterflies in registers, two shared-memory transposes (kernel v10);
  *   V5ELA_BLOCKS_MMA   the four passes as int8 limb-split tensor-core contractions (mma.sync.m16n8k16, SASS IMMA), a warp per pair
  *                      of blocks, everything in registers (csrc/v5ela_dctmma.cuh): 17 % fewer instructions per pixel.
- * Which one is faster depends on the frame geometry; V5ELA_BLOCKS_DEFAULT is what a new handle uses. Results do
- * not depend on the choice.
+ * They run within 3 % of each other on every frame geometry measured (360p .. 4K, profiles/r02/variants.txt section 8; DESIGN.md
+ * 4.4 says why); V5ELA_BLOCKS_DEFAULT is what a new handle uses. Results do not depend on the choice.
  */
 #define V5ELA_BLOCKS_SMEM 0
 #define V5ELA_BLOCKS_MMA 1

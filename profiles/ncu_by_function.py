@@ -8,8 +8,9 @@ KERNEL = os.environ.get("V5_NCU_KERNEL", "ela_fused_kernelILb1ELb0")
 def line_map(so):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    dis = ""                                                 # one cubin per translation unit: the kernel is in one of them
+    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
     m, cur, infn = {}, None, False
     for ln in dis.splitlines():
         if ln.startswith(".text."):

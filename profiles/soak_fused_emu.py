@@ -1,7 +1,9 @@
 """CPU soak of the fused kernel's device code (tests/emu build, threads emulated per barrier phase) in the instantiations the
 host picks for records-only calls on widths that are a multiple of 16 (paired rows) and for everything else, and with the
 texture histogram: random sizes, segment lengths, qualities and contents against the C oracle. Development aid.
-usage: python profiles/soak_fused_emu.py [cases] [seed]"""
+usage: python profiles/soak_fused_emu.py [cases] [seed] [emulator build: 2cta | 2cta_mma | 2cta_mma_np2 | 3cta | 3cta_mma]
+The builds are the ones tests/test_kernel_emu.py compiles (run it once first). Every case also goes through the small-batch
+decomposition (short segments, narrow strips) when `seg` is 0, and the range counters of the block stage must stay at zero."""
 import ctypes, os, sys
 import numpy as np
 
@@ -10,7 +12,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.p
 from oracle import c_oracle, pil_oracle
 from v5ela.records import RECORD_DTYPE
 
-lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libv5ela_emu_2cta.so"))
+BUILD = sys.argv[3] if len(sys.argv) > 3 else "2cta"
+lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", f"libv5ela_emu_{BUILD}.so"))
+lib.v5emu_range_violations.restype = ctypes.c_longlong
 u8p = ctypes.POINTER(ctypes.c_uint8)
 lib.v5emu_analyze.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                               ctypes.c_void_p, u8p, ctypes.c_int, ctypes.c_void_p]
@@ -50,6 +54,7 @@ def main(cases=400, seed=1):
             f = np.repeat(rng.integers(0, 256, (h, w, 1), dtype=np.uint8), 3, axis=2)
         f = np.ascontiguousarray(f)
         o = c_oracle.analyze_frame(f, q)
+        lib.v5emu_set_target_items(592 if (seg == 0 and it % 2) else 0)
         mode = it % 3                                            # 0: records only (paired rows when w % 16 == 0), 1: + residual, 2: + tex_hist
         rec, res, th = emu(f, q, seg, mode == 1, mode == 2)
         ok = rec.tobytes() == o["record"].tobytes()
@@ -60,7 +65,7 @@ def main(cases=400, seed=1):
         if not ok:
             bad += 1
             print("MISMATCH", h, w, q, seg, kind, mode)
-    print(f"cases {cases} mismatches {bad}")
+    print(f"build {BUILD}: cases {cases} mismatches {bad} range violations {lib.v5emu_range_violations()}")
 
 
 if __name__ == "__main__":

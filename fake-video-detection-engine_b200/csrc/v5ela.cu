@@ -377,7 +377,20 @@ int v5ela_analyze_ragged(v5ela_handle *h, const v5ela_frame_desc *frames_host, i
     return V5ELA_OK;
 }
 
+static int analyze_ragged_host_impl(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *records_host);
+
 int v5ela_analyze_ragged_host(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *records_host)
+{
+    try {                                                       // std::vector below: nothing may unwind through the C ABI
+        return analyze_ragged_host_impl(h, frames_host, n, records_host);
+    } catch (const std::bad_alloc &) {
+        return fail(h, V5ELA_ERR_NOMEM, "out of host memory%s");
+    } catch (...) {
+        return fail(h, V5ELA_ERR_INVALID, "host-side failure%s");
+    }
+}
+
+static int analyze_ragged_host_impl(v5ela_handle *h, const v5ela_frame_desc *frames_host, int n, void *records_host)
 {
     if (!h) return V5ELA_ERR_INVALID;
     if (n == 0) return V5ELA_OK;

@@ -122,7 +122,8 @@ V5ELA_API int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int
  *                 `diff` (v5…:70) and `ImageEnhance.Brightness(diff).enhance(255.0 / max_diff)` (v5…:74-78); they may alias.
  *   d_records   : n records, overwritten.
  * The descriptor table goes to the device through a small pinned staging buffer inside the handle (the only host work besides
- * filling it). Asynchronous on `cuda_stream`; launches: memsets, the fused kernel, the finalize kernel and — only when a frame
+ * filling it; before refilling it the call waits, on the host, for the PREVIOUS ragged call's table upload — a few microseconds
+ * of copy, normally long finished). Otherwise asynchronous on `cuda_stream`; launches: memsets, the fused kernel, the finalize kernel and — only when a frame
  * asks for an enhanced map — one enhancement kernel for the whole batch.
  */
 typedef struct v5ela_frame_desc {

@@ -345,7 +345,10 @@ namespace V5_NS {
 //   RGB_BUFS == 1 (3 CTAs/SM): one RGB staging buffer (the TMA copy of band r+1 is issued as soon as band r has been
 //                  converted and lands during the block and residual stages), the residual stage re-reads the original
 //                  pixels from global memory (L2 hits: the band went through L2 moments ago), 24-line luma ring.
-constexpr int RGB_BUFS = MIN_CTAS >= 3 ? 1 : 2;
+#ifndef V5_RGB_BUFS
+#define V5_RGB_BUFS (MIN_CTAS >= 3 ? 1 : 2)
+#endif
+constexpr int RGB_BUFS = V5_RGB_BUFS;       // (a compile-time knob of its own for the CTA-shape experiments, profiles/r02/variants.txt)
 constexpr int RING = RGB_BUFS == 2 ? 32 : 24;   // yorig ring lines: 16 of the current band + 2 carried
 #ifndef V5_RINGD
 #define V5_RINGD (RGB_BUFS == 2 ? 32 : 24)

@@ -191,6 +191,9 @@ int v5ela_create(int device, v5ela_handle **out)
     }
     const char *env = getenv("V5ELA_SEG_ROWS");
     if (env) h->seg_rows = atoi(env);
+    env = getenv("V5ELA_DECOMP");                             // tuning knob: "rounds,tail_seg_rows,tail_eighths"
+    if (env && sscanf(env, "%d,%d,%d", &h->decomp[0], &h->decomp[1], &h->decomp[2]) == 3 && h->decomp[0] >= 1 && h->decomp[1] >= 4)
+        h->decomp_set = true;
     env = getenv("V5ELA_CTAS_PER_SM");                        // tuning knob: launch fewer persistent CTAs than fit
     if (env && atoi(env) >= 1 && atoi(env) <= v5::MIN_CTAS) h->ctas_per_sm = atoi(env);
     env = getenv("V5ELA_BLOCK_STAGE");                        // "mma" / "smem": default block stage of new handles (A/B runs)
@@ -280,6 +283,7 @@ int v5ela_analyze_ex(v5ela_handle *h, const uint8_t *d_rgb, int n, int height, i
     a.quality = h->quality; a.seg_rows = h->seg_rows;
     a.target_items = 2 * h->sm_count * h->ctas_per_sm;
     a.max_ctas = h->sm_count * h->ctas_per_sm;
+    a.tune = h->decomp_set ? h->decomp : nullptr;
     a.ticket = h->d_ticket; a.lane_consts = h->d_lane_consts;
     a.stream = st;
     if (prof) { a.ev_start = h->prof_events[h->prof_used]; a.ev_stop = h->prof_events[h->prof_used + 1]; }

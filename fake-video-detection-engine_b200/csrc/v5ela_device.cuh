@@ -102,6 +102,8 @@ struct KParams {
     int n, h, w;
     int mw, mh;                 // MCU columns / rows of the padded frame
     int n_strips, n_segs;       // work decomposition: strips x vertical segments per frame
+    int split_frame, n_segs_b;  // frames >= split_frame are cut into n_segs_b (shorter) segments: the tail of the launch (fill_params)
+    int work_split;             // first work item of the frames >= split_frame
     unsigned int *ticket;       // work-item counter (zeroed before every launch): CTAs draw items dynamically
     const mma::LaneConsts *lane_consts;   // 32 entries (v5ela_dctmma.cuh), device memory owned by the handle
     const FrameDesc *frames;    // ragged batches only: n descriptors in device memory (then h, w, ... above are unused)
@@ -1254,11 +1256,19 @@ V5_DEV void make_geo(const KParams &p, int work, Geo &g, int &frame)
         g.frame = d.rgb;
         g.resid = d.resid;
     } else {
-        const uint32_t per_frame = (uint32_t)(p.n_strips * p.n_segs);
-        frame = (int)((uint32_t)work / per_frame);
-        rem = (uint32_t)work - (uint32_t)frame * per_frame;
         n_strips = (uint32_t)p.n_strips;
-        n_segs = (uint32_t)p.n_segs;
+        if (work < p.work_split) {                              // long segments first ...
+            n_segs = (uint32_t)p.n_segs;
+            const uint32_t per_frame = n_strips * n_segs;
+            frame = (int)((uint32_t)work / per_frame);
+            rem = (uint32_t)work - (uint32_t)frame * per_frame;
+        } else {                                                // ... the last frames in short ones: the CTAs run dry close together
+            n_segs = (uint32_t)p.n_segs_b;
+            const uint32_t per_frame = n_strips * n_segs, w2 = (uint32_t)(work - p.work_split);
+            const uint32_t f2 = w2 / per_frame;
+            frame = p.split_frame + (int)f2;
+            rem = w2 - f2 * per_frame;
+        }
         g.h = p.h; g.w = p.w; g.mw = p.mw; g.mh = p.mh;
         g.row_stride = p.row_stride;
         g.vec_ok = p.vec_ok;

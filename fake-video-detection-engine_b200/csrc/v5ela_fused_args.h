@@ -15,6 +15,7 @@ struct v5_fused_args {
     uint8_t *residual;              // optional
     uint32_t *tex_hist;             // optional
     int quality, seg_rows, target_items, max_ctas;
+    const int *tune;                // optional decomposition knobs (fill_params)
     unsigned int *ticket;           // zeroed by the caller on the same stream
     const void *lane_consts;        // 32 x mma::LaneConsts in device memory
     cudaStream_t stream;

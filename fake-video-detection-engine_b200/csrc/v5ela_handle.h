@@ -16,6 +16,8 @@ struct v5ela_handle {
     int quality = 90;
     int sm_count = 0;
     int seg_rows = 0;                      // 0 = default
+    int decomp[3] = {0, 0, 0};             // V5ELA_DECOMP=a,b,c development knob (fill_params' tune); decomp_set = it was given
+    bool decomp_set = false;
     int ctas_per_sm = v5::MIN_CTAS;
     int64_t launches = 0;
     int last_inst = -1;                    // V5ELA_INST_* of the most recent fused-kernel launch

@@ -38,11 +38,11 @@ inline int widen_strips(int n_strips, int mw, int64_t items, int64_t target_item
 }
 
 // Work decomposition: frames x strips (<= TW_MAX MCUs wide, balanced) x vertical segments of about `seg_rows` MCU rows.
-// seg_rows <= 0 picks the default: 17 rows (two chroma-only halo bands per segment = ~4 % extra work), shortened down to
-// 4 rows when the batch would otherwise give fewer than `target_items` work items (small batches, single crops), so
-// that the whole GPU is used. Returns 0 or -1 on invalid arguments.
+// seg_rows <= 0 picks the default (see below: as few segments as keep the GPU supplied, short segments for the last frames);
+// total_work_items(p) is the number of work items of the launch. Returns 0 or -1 on invalid arguments.
 inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int64_t frame_stride, int64_t row_stride,
-                       v5ela_record *records, uint8_t *residual, int quality, int seg_rows, int target_items = 0)
+                       v5ela_record *records, uint8_t *residual, int quality, int seg_rows, int target_items = 0,
+                       const int *tune = nullptr)
 {
     if (!rgb || !records || n <= 0 || h <= 0 || w <= 0) return -1;
     if (row_stride < (int64_t)3 * w || (n > 1 && frame_stride < row_stride * (int64_t)h)) return -1;
@@ -61,20 +61,39 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
     p.mw = (w + 15) / 16;
     p.mh = (h + 15) / 16;
     p.n_strips = (p.mw + TW_MAX - 1) / TW_MAX;
+    p.split_frame = n;                                        // one regime unless decided otherwise below
     if (seg_rows <= 0) {
-        seg_rows = 17;
-        const int64_t columns = (int64_t)n * p.n_strips;        // work items per unit of n_segs
-        if (target_items > 0 && columns * ((p.mh + seg_rows - 1) / seg_rows) < target_items) {
-            const int64_t want_segs = (target_items + columns - 1) / columns;
+        seg_rows = 17;                                          // (no CTA count known: the emulator's default)
+        if (target_items > 0) {
+            // Longer segments are cheaper — every segment pays two chroma-only halo bands and one flush of its histograms — but the
+            // launch needs enough work items: the fewest segments per frame that still give >= 2 items per resident CTA
+            // (target_items = 2 per CTA), down to 4 MCU rows per segment. 256 x 1080p: whole-height strips, 1024 items.
+            // (Swept on a B200: profiles/r02/variants.txt section 10.)
+            // tune (development knob, V5ELA_DECOMP): {items per CTA wanted, tail segment rows, tail frames per CTA in 1/8 strips}
+            const int t_rounds = tune ? tune[0] : 2, t_seg_b = tune ? tune[1] : 8, t_tail8 = tune ? tune[2] : 4;
+            const int64_t ctas = (target_items + 1) / 2, columns = (int64_t)n * p.n_strips;
+            int64_t want_segs = (t_rounds * ctas + columns - 1) / columns;
+            if (want_segs < 1) want_segs = 1;
             seg_rows = (int)((p.mh + want_segs - 1) / want_segs);
             if (seg_rows < 4) seg_rows = 4;
+            const int64_t items = columns * ((p.mh + seg_rows - 1) / seg_rows);
             // still too few items for the GPU (a handful of crops): narrower strips — down to 4 MCUs — shorten every band, and
             // with it the latency of the call; the extra halo columns do not matter when most SMs would idle anyway
-            const int64_t items = columns * ((p.mh + seg_rows - 1) / seg_rows);
             if (items < target_items) p.n_strips = widen_strips(p.n_strips, p.mw, items, target_items);
+            // The tail: CTAs finish their last long item up to one item apart. The last frames — half an item per CTA worth of
+            // them — are cut into segments of 8 MCU rows instead, drawn after all the long ones.
+            const int seg_b = t_seg_b, segs_b = (p.mh + seg_b - 1) / seg_b;
+            const int64_t nb = (ctas * t_tail8 + 8 * p.n_strips - 1) / (8 * p.n_strips);
+            if (t_tail8 > 0 && seg_rows >= 2 * seg_b && nb < n) {
+                p.split_frame = (int)(n - nb);
+                p.n_segs_b = segs_b;
+            }
         }
     }
     p.n_segs = (p.mh + seg_rows - 1) / seg_rows;
+    if (p.split_frame >= n) p.n_segs_b = p.n_segs;
+    if ((long long)n * p.n_strips * (p.n_segs > p.n_segs_b ? p.n_segs : p.n_segs_b) > 0x7fffffffLL) return -1;   // work items are 32-bit
+    p.work_split = p.split_frame * p.n_strips * p.n_segs;
     p.vec_ok = ((reinterpret_cast<uintptr_t>(rgb) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15) == 0;
     p.resid_vec_ok = residual && ((reinterpret_cast<uintptr_t>(residual) | (uintptr_t)(3 * w)) & 15) == 0;
     uint16_t ql[64], qc[64];
@@ -82,6 +101,11 @@ inline int fill_params(KParams &p, const uint8_t *rgb, int n, int h, int w, int6
     make_quant(ql, p.q[0]);
     make_quant(qc, p.q[1]);
     return 0;
+}
+
+inline long long total_work_items(const KParams &p)
+{
+    return (long long)p.work_split + (long long)(p.n - p.split_frame) * p.n_strips * p.n_segs_b;
 }
 
 // Which instantiation of the fused kernel a call takes (v5ela_device.cuh, FAST): widths that are a multiple of the MCU

@@ -53,12 +53,12 @@ inline cudaError_t fused_prepare()
 inline int fused_launch(v5_fused_args &a)
 {
     KParams p;
-    if (fill_params(p, a.rgb, a.n, a.h, a.w, a.frame_stride, a.row_stride, a.records, a.residual, a.quality, a.seg_rows, a.target_items) != 0)
+    if (fill_params(p, a.rgb, a.n, a.h, a.w, a.frame_stride, a.row_stride, a.records, a.residual, a.quality, a.seg_rows, a.target_items, a.tune) != 0)
         return -1;
     p.tex_hist = a.tex_hist;
     p.ticket = a.ticket;
     p.lane_consts = static_cast<const mma::LaneConsts *>(a.lane_consts);
-    const long long total = (long long)a.n * p.n_strips * p.n_segs;
+    const long long total = total_work_items(p);
     if (total > 0x7fffffffLL) return -2;
     a.total = total;
     const int grid = total < a.max_ctas ? (int)total : a.max_ctas;
@@ -91,13 +91,15 @@ inline int fused_launch_ragged(v5_ragged_args &a)
                 return -1;
             columns += ((f.width + 15) / 16 + TW_MAX - 1) / TW_MAX;
         }
-        // segments of about 17 MCU rows, shortened (down to 4) when the batch would otherwise leave SMs idle
-        const long long want_segs = a.target_items > 0 ? (a.target_items + columns - 1) / columns : 1;
-        long long items4 = 0;                                   // work items with the default strips and segments shortened to >= 4 rows
+        // as few segments per frame as still give >= 2 work items per resident CTA (fill_params' rule), down to 4 MCU rows each
+        const long long ctas = (a.target_items + 1) / 2;
+        long long want_segs = a.target_items > 0 ? (2 * ctas + columns - 1) / columns : 4;
+        if (want_segs < 1) want_segs = 1;
+        long long items4 = 0;                                   // work items with the default strips and these segments
         for (int i = 0; i < a.n; i++) {
             const int mw = (a.frames[i].width + 15) / 16, mh = (a.frames[i].height + 15) / 16;
             long long sr = (mh + want_segs - 1) / want_segs;
-            sr = sr < 4 ? 4 : (sr > 17 ? 17 : sr);
+            sr = sr < 4 ? 4 : sr;
             items4 += (long long)((mw + TW_MAX - 1) / TW_MAX) * ((mh + sr - 1) / sr);
         }
         long long total = 0;
@@ -111,8 +113,8 @@ inline int fused_launch_ragged(v5_ragged_args &a)
             d.h = f.height; d.w = f.width;
             d.mw = (f.width + 15) / 16; d.mh = (f.height + 15) / 16;
             d.n_strips = (d.mw + TW_MAX - 1) / TW_MAX;
-            int seg_rows = a.seg_rows > 0 ? a.seg_rows : 17;
-            if (a.seg_rows <= 0 && (d.mh + seg_rows - 1) / seg_rows < want_segs) {
+            int seg_rows = a.seg_rows;
+            if (seg_rows <= 0) {
                 seg_rows = (int)((d.mh + want_segs - 1) / want_segs);
                 if (seg_rows < 4) seg_rows = 4;
             }

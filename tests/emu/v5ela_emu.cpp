@@ -11,6 +11,9 @@
 #include "v5ela_workitem.cuh"
 #include "v5ela_host.h"
 
+static int g_last_split = -1, g_last_segs_b = -1, g_last_segs = -1;   // the decomposition of the most recent v5emu_analyze call
+extern "C" int v5emu_last_split_frame(void) { return g_last_split; }
+extern "C" int v5emu_last_segments(int tail) { return tail ? g_last_segs_b : g_last_segs; }
 static int g_target_items = 0;       // v5emu_set_target_items: the host's small-batch decomposition (short segments, narrow strips)
 extern "C" void v5emu_set_target_items(int t) { g_target_items = t; }
 
@@ -20,6 +23,7 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
     v5::KParams p;
     if (v5::fill_params(p, rgb, n, h, w, frame_stride, row_stride, records, residual, quality, seg_rows, g_target_items) != 0) return -1;
     p.tex_hist = tex_hist;
+    g_last_split = p.split_frame; g_last_segs = p.n_segs; g_last_segs_b = p.n_segs_b;
     static v5::mma::LaneConsts lane_consts[32];
     if (!v5::mma::make_lane_consts(lane_consts)) return -2;
     p.lane_consts = lane_consts;
@@ -28,7 +32,7 @@ extern "C" int v5emu_analyze(const uint8_t *rgb, int n, int h, int w, int64_t fr
     v5::Smem *S = (v5::Smem *)aligned_alloc(16, sizeof(v5::Smem));
     memset(S, 0xA5, sizeof(v5::Smem));                       // poison: uninitialised reads must not matter
     std::vector<v5::ThreadAcc> acc(v5::NT);
-    const int total = n * p.n_strips * p.n_segs;
+    const int total = (int)v5::total_work_items(p);
     for (int work = 0; work < total; work++) {
         if (p.tex_hist) v5::process_work_item<false, true>(*S, p, work, acc.data());         // the choice the C ABI makes
         else if (v5::fast_path_ok(p)) v5::process_work_item<true, false>(*S, p, work, acc.data());

@@ -170,6 +170,24 @@ def test_emulated_small_batch_decomposition(emu, hw):
         emu.lib.v5emu_set_target_items(0)
 
 
+def test_emulated_two_regime_decomposition(emu):
+    """A batch with plenty of work is cut into long segments (whole-height strips) except for its last frames, which get short
+    segments so that the launch's tail is short (csrc/v5ela_host.h fill_params: split_frame / n_segs_b): every frame of both
+    regimes against the oracle."""
+    frames = np.stack([gen_frame(i, 300, 32, 3) for i in range(40)])          # 19 MCU rows: long = 1 segment of 19, short = 3 segments of <= 8
+    orecs, oresid = c_oracle.analyze(frames, 90, want_residual=True)
+    try:
+        emu.lib.v5emu_set_target_items(16)                   # 8 "CTAs": 40 columns >= 3 x 8 -> long segments; the last 4 frames short
+        for want_residual in (True, False):
+            recs, res = emu(frames, 90, 0, want_residual=want_residual)
+            assert recs.tobytes() == orecs.tobytes()
+            if want_residual:
+                assert np.array_equal(res, oresid)
+            assert emu.lib.v5emu_last_split_frame() == 36 and emu.lib.v5emu_last_segments(0) == 1 and emu.lib.v5emu_last_segments(1) == 3
+    finally:
+        emu.lib.v5emu_set_target_items(0)
+
+
 def adversarial_blocks_frame(rng=None):
     """A frame whose 8x8 blocks drive the intermediates of the round trip to their extremes: for every pair (u, v) the sign
     pattern of the 2-D basis function (u, v) at full swing (0 / 255) and its negative — these maximise the forward row / column

@@ -350,7 +350,7 @@ static int v5ela_jpeg_decode_impl(v5ela_handle *h, const uint8_t *const *files_h
 
     // ---- parse every file; unique Huffman table sets and quantisation table pairs
     std::vector<v5j::FileInfo> info((size_t)n);
-    std::vector<v5j::DecTabSet> tabsets;
+    std::vector<v5j::HuffSpecSet> specsets;                    // distinct table sets of the call (usually one): decoder tables are built for these only
     std::vector<std::vector<uint16_t>> qsets;
     std::vector<int> tab_of((size_t)n), q_of((size_t)n), parse_rc((size_t)n);
     size_t total_len = 0;
@@ -370,12 +370,12 @@ static int v5ela_jpeg_decode_impl(v5ela_handle *h, const uint8_t *const *files_h
                        ? fail(h, V5ELA_ERR_UNSUPPORTED, "v5ela_jpeg_decode: not an 8-bit baseline one-component / 4:2:0 / 4:2:2 / 4:4:4 JPEG%s", which)
                        : fail(h, V5ELA_ERR_INVALID, "v5ela_jpeg_decode: corrupt JPEG headers%s", which);
         }
-        v5j::DecTabSet ts;
+        v5j::HuffSpecSet ts;                                    // (HuffSpec has no padding bytes and parse_file zeroes what it does not fill)
         ts.dc[0] = info[i].dc[0]; ts.dc[1] = info[i].dc[1]; ts.ac[0] = info[i].ac[0]; ts.ac[1] = info[i].ac[1];
         int found = -1;
-        for (size_t k = 0; k < tabsets.size() && found < 0; k++)
-            if (!memcmp(&tabsets[k], &ts, sizeof(ts))) found = (int)k;
-        if (found < 0) { tabsets.push_back(ts); found = (int)tabsets.size() - 1; }
+        for (size_t k = specsets.size(); k-- > 0 && found < 0;)
+            if (!memcmp(&specsets[k], &ts, sizeof(ts))) found = (int)k;
+        if (found < 0) { specsets.push_back(ts); found = (int)specsets.size() - 1; }
         tab_of[i] = found;
         std::vector<uint16_t> q(128);
         memcpy(q.data(), info[i].qt[0], 128);
@@ -386,6 +386,9 @@ static int v5ela_jpeg_decode_impl(v5ela_handle *h, const uint8_t *const *files_h
         if (found < 0) { qsets.push_back(q); found = (int)qsets.size() - 1; }
         q_of[i] = found;
     }
+
+    std::vector<v5j::DecTabSet> tabsets(specsets.size());
+    for (size_t k = 0; k < specsets.size(); k++) v5j::make_tabset(specsets[k], tabsets[k]);   // (parse_file has validated every table)
 
     // ---- chunks of files whose workspace stays under ~8 GiB (a 1080p file needs ~11 MB: coefficients, planes, streams)
     std::vector<DecPlan> plans(1);
@@ -537,6 +540,10 @@ static int v5ela_jpeg_decode_impl(v5ela_handle *h, const uint8_t *const *files_h
         v5j::SubInfo *d_sub_info = static_cast<v5j::SubInfo *>(s->d_sub_info);
         uint32_t *d_sub_block0 = static_cast<uint32_t *>(s->d_sub_block0);
         const char *force = getenv("V5ELA_HUFF_PATH");                    // tests: "one" / "three" force a path
+        if (const char *fp = getenv("V5ELA_HUFF_PARTS")) {                 // experiments: parts per file of the three-launch path
+            const int v = atoi(fp);
+            if (v >= 1 && v <= 16) parts = (unsigned)v > P.max_windows ? P.max_windows : (unsigned)v;
+        }
         // nothing to gain from splitting when there is no room for two parts per file, or no file has more than one window
         const bool one_launch = force ? force[0] == 'o' : (h->sm_count / cn < 2 || P.max_windows < 2);
         if (one_launch) {

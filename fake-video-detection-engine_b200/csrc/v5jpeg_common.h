@@ -154,31 +154,77 @@ V5J_HOSTDEV uint32_t pack_symbol(int sym, int len, bool is_dc)
     return (uint32_t)len | ((uint32_t)size << 8) | ((uint32_t)zinc << 16) | ((uint32_t)(len + size) << 24);
 }
 
+// What a file's DHT segments say about one table (T.81 B.2.4.2): 276 bytes. FileInfo keeps these; the decoder tables below
+// (6.5 KB each) are only built for the DISTINCT table sets of a call (v5jpeg.cu), not per file.
+struct HuffSpec {
+    uint8_t bits[16];        // number of codes of length 1..16
+    uint8_t vals[256];       // symbols in code order; entries past n are zero
+    uint16_t n;
+    uint16_t is_dc;
+};
+
+constexpr int DEC_LOOK_BITS = 9;
+constexpr int DEC_LONG_ENTRIES = 1024;
 struct DecTable {
-    uint32_t look[512];
+    uint32_t look[1 << DEC_LOOK_BITS];
+    // Second level: codes longer than DEC_LOOK_BITS bits. A canonical code orders its words by length, so every such code,
+    // left-justified to 16 bits, lies in [long_base, 0xffff]; when that range has at most DEC_LONG_ENTRIES values (Annex K
+    // tables: 640 for AC, 128 for DC) lng[window16 - long_base] is the action for it and decoding a long code is one more
+    // load — no walk over the lengths, which every lane of a warp paid for whenever one of them met a long code (2 % of the
+    // symbols of a quality-95 file: half of all warp steps). long_base = 0x10000: range too large, maxcode[] is walked.
+    uint32_t lng[DEC_LONG_ENTRIES];
+    uint32_t long_base;
     int32_t maxcode[18];     // maxcode[len] for len 1..16; -1 = no codes of that length
     int32_t valoff[17];      // symbol index = valoff[len] + code
     uint8_t vals[256];
     uint32_t is_dc;
 };
 
-inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nvals, bool is_dc, DecTable &t)
+// Codes of more than DEC_LOOK_BITS bits by the walk of T.81 F.2.2.3 (only the top 16 bits of the window matter). Codes that do
+// not exist decode as symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
+V5J_HOSTDEV uint32_t dec_long_action(const DecTable &t, uint32_t win)
 {
-    memset(&t, 0, sizeof(t));
+    for (int l = DEC_LOOK_BITS + 1; l <= 16; l++) {
+        const int32_t code = (int32_t)(win >> (32 - l));
+        if (code <= t.maxcode[l]) return pack_symbol(t.vals[(t.valoff[l] + code) & 0xff], l, t.is_dc != 0);
+    }
+    return pack_symbol(0, 16, t.is_dc != 0);
+}
+
+// The canonical code of (bits, vals) is well formed: no length oversubscribed, no more symbols than `nvals`.
+inline bool huff_spec_ok(const uint8_t bits[16], int nvals)
+{
     if (nvals > 256) return false;
-    memcpy(t.vals, vals, (size_t)nvals);
-    t.is_dc = is_dc ? 1u : 0u;
     int k = 0;
     int32_t code = 0;
     for (int len = 1; len <= 16; len++) {
         const int cnt = bits[len - 1];
+        if (cnt && (code + cnt > (1 << len) || k + cnt > nvals)) return false;
+        code = (code + cnt) << 1;
+        k += cnt;
+    }
+    return true;
+}
+
+inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nvals, bool is_dc, DecTable &t)
+{
+    memset(&t, 0, sizeof(t));
+    if (!huff_spec_ok(bits, nvals)) return false;
+    memcpy(t.vals, vals, (size_t)nvals);
+    t.is_dc = is_dc ? 1u : 0u;
+    t.long_base = 0x10000u;
+    int k = 0;
+    int32_t code = 0;
+    for (int len = 1; len <= 16; len++) {
+        if (len == DEC_LOOK_BITS + 1 && code < (1 << len) && 0x10000 - (code << (16 - len)) <= DEC_LONG_ENTRIES)
+            t.long_base = (uint32_t)code << (16 - len);      // first word a longer code can have, left-justified
+        const int cnt = bits[len - 1];
         if (cnt) {
-            if (code + cnt > (1 << len) || k + cnt > nvals) return false;
             t.valoff[len] = k - code;
-            if (len <= 9)
+            if (len <= DEC_LOOK_BITS)
                 for (int i = 0; i < cnt; i++) {
-                    const int first = (code + i) << (9 - len);
-                    for (int f = 0; f < (1 << (9 - len)); f++) t.look[first + f] = pack_symbol(vals[k + i], len, is_dc);
+                    const int first = (code + i) << (DEC_LOOK_BITS - len);
+                    for (int f = 0; f < (1 << (DEC_LOOK_BITS - len)); f++) t.look[first + f] = pack_symbol(vals[k + i], len, is_dc);
                 }
             code += cnt;
             k += cnt;
@@ -189,8 +235,10 @@ inline bool make_dec_table(const uint8_t bits[16], const uint8_t *vals, int nval
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    for (uint32_t w = t.long_base; w < 0x10000u; w++) t.lng[w - t.long_base] = dec_long_action(t, w << 16);
     return true;
 }
+inline bool make_dec_table(const HuffSpec &h, DecTable &t) { return make_dec_table(h.bits, h.vals, h.n, h.is_dc != 0, t); }
 
 enum { JPEG_OK = 0, JPEG_CORRUPT = -1, JPEG_UNSUPPORTED = -2 };
 
@@ -199,7 +247,7 @@ struct FileInfo {
     int hs = 1, vs = 1;       // luma sampling factors = luma blocks per MCU across / down (chroma is always 1 x 1)
     int restart = 0;          // restart interval in MCUs (DRI), 0 = none
     uint16_t qt[2][64];       // natural order: [0] the luma component's table, [1] the chroma components' (same for both)
-    DecTable dc[2], ac[2];    // [0] luma, [1] chroma
+    HuffSpec dc[2], ac[2];    // [0] luma, [1] chroma (decoder tables: make_dec_table, once per distinct set)
     size_t scan_off = 0, scan_len = 0;   // entropy-coded segment inside the file (stuffed bytes included, EOI excluded)
 };
 
@@ -308,8 +356,16 @@ inline int parse_file(const uint8_t *d, size_t len, FileInfo &F, bool headers_on
         if (!qt_ok[tq[c]] || !huff[0][td[c]].ok || !huff[1][ta[c]].ok) return JPEG_CORRUPT;
         if (headers_only) continue;
         memcpy(F.qt[c], qt[tq[c]], sizeof(F.qt[c]));
-        if (!make_dec_table(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].n, true, F.dc[c])) return JPEG_CORRUPT;
-        if (!make_dec_table(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].n, false, F.ac[c])) return JPEG_CORRUPT;
+        for (int cls = 0; cls < 2; cls++) {
+            const Raw &r = huff[cls][cls ? ta[c] : td[c]];
+            if (!huff_spec_ok(r.bits, r.n)) return JPEG_CORRUPT;
+            HuffSpec &hsp = cls ? F.ac[c] : F.dc[c];
+            memset(&hsp, 0, sizeof(hsp));
+            memcpy(hsp.bits, r.bits, 16);
+            memcpy(hsp.vals, r.vals, (size_t)r.n);
+            hsp.n = (uint16_t)r.n;
+            hsp.is_dc = cls ? 0 : 1;
+        }
     }
     if (!headers_only && F.ncomp == 1) {
         memcpy(F.qt[1], F.qt[0], sizeof(F.qt[0]));

@@ -29,6 +29,7 @@
 #include "v5jpeg_common.h"
 
 namespace v5j {
+using v5::U4;
 
 #ifndef V5J_HUFF_NT
 #define V5J_HUFF_NT 1024
@@ -46,6 +47,15 @@ constexpr uint32_t SUB_BITS = V5J_SUB_BITS;   // bits per subsequence (> 31: a s
 struct DecTabSet {                         // Huffman tables of one file: [0] luma, [1] chroma
     DecTable dc[2], ac[2];
 };
+struct HuffSpecSet {                       // the same as the files' DHT segments give them (FileInfo): what calls are de-duplicated on
+    HuffSpec dc[2], ac[2];
+};
+inline bool make_tabset(const HuffSpecSet &h, DecTabSet &T)
+{
+    bool ok = true;
+    for (int c = 0; c < 2; c++) ok = make_dec_table(h.dc[c], T.dc[c]) && make_dec_table(h.ac[c], T.ac[c]) && ok;
+    return ok;
+}
 
 struct DecImage {
     int32_t h, w, ncomp;
@@ -93,11 +103,21 @@ struct SubInfo {
 
 V5_HOSTDEV bool same_state(const SubState &a, const SubState &b) { return a.p == b.p && a.c == b.c && a.z == b.z; }
 
-// Where the decoder reads the stream from. window(p) = the 32 stream bits that start at bit position p, most significant
-// first. The stream buffer is padded with zero bytes, so reading a little past the end is harmless.
+V5_HOSTDEV uint32_t window_of(uint32_t hi, uint32_t lo, uint32_t sh)           // the 32 bits that start sh bits into hi:lo
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, sh);
+#else
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+}
+
+// Where the decoder reads the stream from: 32-bit words, most significant bit first. word(w) = stream bits 32w .. 32w+31;
+// a decoder walks the words in order with a cursor (open at word w, then next() = the word after the one handed out last).
+// The stream buffer is padded with zero bytes, so reading a little past the end is harmless.
 struct ByteStream {                        // plain bytes in (global) memory
     const uint8_t *data;
-    V5_HOSTDEV uint32_t word(uint32_t w) const     // stream bits 32w .. 32w+31, most significant first
+    V5_HOSTDEV uint32_t word(uint32_t w) const
     {
 #ifdef __CUDA_ARCH__
         return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(data) + w), 0, 0x0123);
@@ -106,44 +126,42 @@ struct ByteStream {                        // plain bytes in (global) memory
         return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
 #endif
     }
-    V5_HOSTDEV uint32_t window(uint32_t p) const
-    {
-#ifdef __CUDA_ARCH__
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(data) + (p >> 5);
-        const uint32_t hi = __byte_perm(__ldg(w), 0, 0x0123), lo = __byte_perm(__ldg(w + 1), 0, 0x0123);
-        return __funnelshift_l(lo, hi, p & 31);
-#else
-        const uint8_t *b = data + (p >> 3);
-        const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | b[4];
-        return (uint32_t)(v >> (8 - (p & 7)));
-#endif
-    }
+    V5_HOSTDEV uint32_t window(uint32_t p) const { return window_of(word(p >> 5), word((p >> 5) + 1), p & 31u); }   // 32 bits from bit p
+    struct Cursor { uint32_t w; };
+    V5_HOSTDEV uint32_t open(Cursor &c, uint32_t w) const { c.w = w; return word(w); }
+    V5_HOSTDEV uint32_t next(Cursor &c) const { return word(++c.w); }
 };
 
 // One window of the stream staged in shared memory as big-endian 32-bit words. Thread t works on words 32t .. 32t+31 (its
-// subsequence) and the threads of a warp tend to sit at similar offsets inside their subsequences, so word w is stored at
-// row w / 32, column (w + row) mod 32: equal offsets in 32 different subsequences fall into 32 different banks.
+// subsequence, then the ones after it) and the threads of a warp tend to sit at similar offsets inside their subsequences.
+// Word c of subsequence r is stored at c * STAGE_PITCH + r with STAGE_PITCH = HUFF_NT + 1 = 1 (mod 32): its bank is
+// (c + r) mod 32, so equal offsets in 32 consecutive subsequences fall into 32 different banks, and so do the 32 consecutive
+// words of one subsequence when the window is staged. A cursor is the slot of the word handed out last: the next word is
+// STAGE_PITCH further on, or at the top of the next column when the subsequence ends — no index arithmetic per symbol.
 constexpr int SUB_WORDS = (int)(SUB_BITS / 32);
 constexpr int WINDOW_WORDS = HUFF_NT * SUB_WORDS;
-constexpr int STAGE_WORDS = WINDOW_WORDS + SUB_WORDS;                      // + one row: a symbol may end just past the window
-V5_HOSTDEV int stage_slot(uint32_t w)
+constexpr int STAGE_PITCH = HUFF_NT + 1;                                   // + one subsequence: a symbol may end just past the window
+constexpr int STAGE_WORDS = STAGE_PITCH * SUB_WORDS;
+static_assert((SUB_WORDS & (SUB_WORDS - 1)) == 0, "stage_slot: SUB_WORDS must be a power of two");   // (banks: HUFF_NT a multiple of 32)
+V5_HOSTDEV int stage_slot(uint32_t w)      // w: word index inside the window, < STAGE_WORDS
 {
-    // rotate each subsequence's row of SUB_WORDS words by its row number (SUB_WORDS is a power of two)
-    return (int)((w & ~(uint32_t)(SUB_WORDS - 1)) | ((w + w / SUB_WORDS) & (uint32_t)(SUB_WORDS - 1)));
+    return (int)((w & (uint32_t)(SUB_WORDS - 1)) * (uint32_t)STAGE_PITCH + w / (uint32_t)SUB_WORDS);
 }
 struct StagedStream {
     const uint32_t *words;                 // STAGE_WORDS entries
-    uint32_t base_word;                    // stream word index of words[stage_slot(0)]
+    uint32_t base_word;                    // stream word index of words[stage_slot(0)], a multiple of SUB_WORDS
     V5_HOSTDEV uint32_t word(uint32_t w) const { return words[stage_slot(w - base_word)]; }
-    V5_HOSTDEV uint32_t window(uint32_t p) const
+    struct Cursor { const uint32_t *q; };  // the word handed out last
+    V5_HOSTDEV uint32_t open(Cursor &c, uint32_t w) const
     {
-        const uint32_t w = (p >> 5) - base_word;
-        const uint32_t hi = words[stage_slot(w)], lo = words[stage_slot(w + 1)];
-#ifdef __CUDA_ARCH__
-        return __funnelshift_l(lo, hi, p & 31);
-#else
-        return (p & 31) ? (hi << (p & 31)) | (lo >> (32 - (p & 31))) : hi;
-#endif
+        c.q = words + stage_slot(w - base_word);
+        return *c.q;
+    }
+    V5_HOSTDEV uint32_t next(Cursor &c) const
+    {
+        // the last word of a subsequence sits in the last row of the layout: its successor is the first word of the next column
+        c.q += c.q >= words + (SUB_WORDS - 1) * STAGE_PITCH ? 1 - (SUB_WORDS - 1) * STAGE_PITCH : STAGE_PITCH;
+        return *c.q;
     }
 };
 // thread t of nt: copies the window that starts at stream word base_word (stream: bytes, padded with zeros up to pad_bytes)
@@ -164,53 +182,118 @@ V5_HOSTDEV void stage_window(int t, int nt, uint32_t *words, const uint8_t *stre
     }
 }
 
-// One Huffman symbol from the window, as the packed action word of v5jpeg_common.h (pack_symbol). Codes that do not exist
-// decode as symbol 0 with length 16 (libjpeg also substitutes zero for corrupt data; progress is guaranteed either way).
+// One Huffman symbol from the window, as the packed action word of v5jpeg_common.h (pack_symbol): codes of up to 9 bits from
+// the first table, longer ones from the second (one more load), tables whose long codes span too many windows by the walk.
 V5_HOSTDEV uint32_t huff_action(const DecTable &t, uint32_t win)
 {
-    const uint32_t look = t.look[win >> 23];
+    const uint32_t look = t.look[win >> (32 - DEC_LOOK_BITS)];
     if (look) return look;
-    for (int l = 10; l <= 16; l++) {
-        const int32_t code = (int32_t)(win >> (32 - l));
-        if (code <= t.maxcode[l]) return pack_symbol(t.vals[(t.valoff[l] + code) & 0xff], l, t.is_dc != 0);
-    }
-    return pack_symbol(0, 16, t.is_dc != 0);
+    const uint32_t k = (win >> 16) - t.long_base;                       // look == 0 implies window16 >= the first long code
+    if (k < (uint32_t)DEC_LONG_ENTRIES) return t.lng[k];
+    return dec_long_action(t, win);
 }
 
 // Decodes from state `s` until the bit position reaches `limit`; returns the number of blocks completed. WRITE: stores
 // every non-zero AC coefficient of block (block0 + completed) at coef[block * 64 + zigzag index] and its DC difference at dc[block];
 // blocks >= max_blocks (trailing padding bits decoded as symbols) are dropped.
-template <bool WRITE, class Src>
+// The write pass assembles the head of every block — zigzag positions 0..BLK_HEAD-1, where most non-zero coefficients are — on
+// chip and stores it as ONE full 32-byte sector when the block ends, instead of one 2-byte store per coefficient: each of
+// those is a 32-byte request to the memory system (a partial write to a line the zero fill left long ago: fetched again,
+// merged, written back), and at quality 95 a block has 18 of them. The L1 -> crossbar request port was what bounded the write
+// pass (75 % busy, 48 % of the kernel's time). Thread t owns BLK_HEAD int16 in shared memory as two 128-bit words,
+// BlockHead::q[0][t] and q[1][t]. A block that starts or ends in another subsequence is shared with that subsequence's
+// thread, so only blocks that lie wholly inside the span are assembled; the two partial ones use plain stores.
+constexpr int BLK_HEAD = 16;
+struct BlockHead {
+    U4 q[2][HUFF_NT];
+};
+
+template <bool WRITE, class Src, bool HEADS = false>
 V5_HOSTDEV uint32_t decode_span(const Src &stream, SubState &s, uint32_t limit, const DecTabSet &T, int bpm, int16_t *coef,
-                                int16_t *dc, int64_t block0, int64_t max_blocks)
+                                int16_t *dc, int64_t block0, int64_t max_blocks, BlockHead *heads = nullptr, int t = 0)
 {
     // One loop body for DC and AC symbols, selects instead of branches: the threads of a warp sit at unrelated places of
     // their blocks, and every divergent path would be paid for by all of them.
     // The table hands back what to do (pack_symbol): value bits to read, how far the zigzag index moves (end of block: 64).
+    // The stream words under the bit position travel in registers (a symbol moves the position by less than 32 bits, so at
+    // most one new word is needed per symbol), and the word after them is fetched one crossing ahead.
     uint32_t p = s.p, done = 0;
     int c = s.c, z = s.z;
-    while (p < limit) {
-        const int comp = (bpm > 1 && c >= bpm - 2) ? 1 : 0;              // an MCU ends with its Cb and Cr block
-        const bool is_dc = z == 0;
-        const DecTable &tab = is_dc ? T.dc[comp] : T.ac[comp];
-        const uint32_t win = stream.window(p);
+    if (p >= limit) return 0;
+    typename Src::Cursor cur;
+    uint32_t hi = stream.open(cur, p >> 5), lo = stream.next(cur), ahead = stream.next(cur);
+    uint32_t sh = p & 31u;                                             // bit offset of p inside hi
+    const int first_chroma = bpm > 1 ? bpm - 2 : bpm;                  // an MCU ends with its Cb and Cr block
+    // &T.ac[k] - &T.dc[k] is the same for both k: one pointer (the DC table of the block's component) is kept, it changes at
+    // block ends only
+    const char *tdc = reinterpret_cast<const char *>(&T.dc[c >= first_chroma ? 1 : 0]);
+    constexpr int AC_FWD = (int)(2 * sizeof(DecTable)), CHROMA_FWD = (int)sizeof(DecTable);
+    // write pass: `room` blocks from block0 on may be stored (trailing pad bits can decode into phantom blocks past the image);
+    // cblk / cdc follow the current block
+    const uint32_t room = WRITE ? (uint32_t)(max_blocks > block0 ? max_blocks - block0 : 0) : 1u;
+    int16_t *cblk = WRITE ? coef + block0 * 64 : nullptr, *cdc = WRITE ? dc + block0 : nullptr;
+    bool whole = HEADS && z == 0;                                       // the current block began inside this span
+    int16_t *head = HEADS ? reinterpret_cast<int16_t *>(&heads->q[0][t]) : nullptr;
+    constexpr int HEAD_Q1 = (int)(sizeof(U4) / 2) * HUFF_NT;            // int16 distance from q[0][t] to q[1][t]
+    do {
+        const DecTable &tab = *reinterpret_cast<const DecTable *>(tdc + (z ? AC_FWD : 0));
+        const uint32_t win = window_of(hi, lo, sh);
         const uint32_t act = huff_action(tab, win);
-        const int len = (int)(act & 31u), sz = (int)((act >> 8) & 15u), zinc = (int)((act >> 16) & 127u), total = (int)(act >> 24);
-        const int pos = z + zinc - 1;                                    // where a value lands: DC 0, AC z + run
-        if (WRITE && sz && pos < 64 && block0 + done < max_blocks) {
-            const int v = (int)((win << len) >> (32 - sz));
-            // DC differences go to their own dense array (one int16 per block): the prefix sums that turn them into values
-            // then touch 2 bytes per block instead of one 128-byte line
-            int16_t *dst = is_dc ? dc + (block0 + done) : coef + (block0 + done) * 64 + pos;
-            *dst = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+        const int zinc = (int)((act >> 16) & 127u), total = (int)(act >> 24);
+        if (WRITE) {
+            const int len = (int)(act & 31u), sz = (int)((act >> 8) & 15u);
+            const int pos = z + zinc - 1;                                // where a value lands: DC 0, AC z + run
+            if (sz && pos < 64 && done < room) {
+                int v = (int)((win << len) >> (32 - sz));
+                v = v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v;
+                // DC differences go to their own dense array (one int16 per block): the prefix sums that turn them into values
+                // then touch 2 bytes per block instead of one 128-byte line
+                if (z == 0) *cdc = (int16_t)v;
+                else if (HEADS && whole && pos < BLK_HEAD) head[(pos & 7) + (pos >> 3) * HEAD_Q1] = (int16_t)v;
+                else cblk[pos] = (int16_t)v;
+            }
         }
         z += zinc;
         p += (uint32_t)total;
-        if (z >= 64) {
-            z = 0;
-            c = c + 1 == bpm ? 0 : c + 1;
-            done++;
+        sh += (uint32_t)total;
+        // end of block — as selects: some lane of the warp is at one in almost every step
+        const bool eob = z >= 64;
+        if (HEADS && eob) {
+            if (whole && done < room) {
+                U4 *dst = reinterpret_cast<U4 *>(cblk);
+                dst[0] = heads->q[0][t];
+                dst[1] = heads->q[1][t];
+                heads->q[0][t] = U4{0u, 0u, 0u, 0u};
+                heads->q[1][t] = U4{0u, 0u, 0u, 0u};
+            }
+            whole = true;
         }
+        if (WRITE) {
+            cblk += eob ? 64 : 0;
+            cdc += eob ? 1 : 0;
+        }
+        z = eob ? 0 : z;
+        done += eob ? 1u : 0u;
+        c += eob ? 1 : 0;
+        c = c == bpm ? 0 : c;
+        tdc = reinterpret_cast<const char *>(&T.dc[0]) + (c >= first_chroma ? CHROMA_FWD : 0);
+        if (sh >= 32u) {
+            hi = lo;
+            lo = ahead;
+            ahead = stream.next(cur);
+        }
+        sh &= 31u;
+    } while (p < limit);
+    if (HEADS && whole && z != 0) {
+        // the span ends inside a block: the next subsequence's thread writes the rest of it, so what has been assembled goes
+        // out coefficient by coefficient
+        if (done < room)
+            for (int k = 1; k < BLK_HEAD; k++) {
+                const int16_t v = head[(k & 7) + (k >> 3) * HEAD_Q1];
+                if (v) cblk[k] = v;
+            }
+        heads->q[0][t] = U4{0u, 0u, 0u, 0u};
+        heads->q[1][t] = U4{0u, 0u, 0u, 0u};
     }
     s.p = p;
     s.c = (uint16_t)c;
@@ -276,6 +359,7 @@ struct HuffJob {
     int64_t max_blocks;
     int16_t *coef;
     int16_t *dc;                           // DC differences (later values), one per block
+    BlockHead *heads;                      // write pass: per-thread block heads (shared memory, all zero between passes), or null
 };
 
 V5_HOSTDEV uint32_t sub_limit(const HuffJob &J, uint32_t j)
@@ -323,7 +407,7 @@ V5_HOSTDEV void huff_phase_write(int t, HuffWindow &W, const HuffJob &J, const D
     const uint32_t j = w0 + (uint32_t)t;
     if (j >= J.nsub) return;
     SubState st = t == 0 ? W.carry : W.info[t - 1].s;
-    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)block0, J.max_blocks);
+    decode_span<true, StagedStream, true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)block0, J.max_blocks, J.heads, t);
 }
 
 // ---- small batches: a file's windows spread over several CTAs -------------------------------------------------------------
@@ -368,7 +452,7 @@ V5_HOSTDEV void huff_write_sub(int t, const HuffJob &J, const DecTabSet &T, uint
     SubState st;
     if (j == 0) { st.p = 0; st.c = 0; st.z = 0; }
     else st = sub_info[j - 1].s;
-    decode_span<true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)sub_block0[j], J.max_blocks);
+    decode_span<true, StagedStream, true>(J.staged, st, sub_limit(J, j), T, J.bpm, J.coef, J.dc, (int64_t)sub_block0[j], J.max_blocks, J.heads, t);
 }
 
 // ------------------------------------------------------------------------------------------------- DC prediction
@@ -673,6 +757,7 @@ struct HuffSmem {
     uint32_t warp_sums[33];
     uint32_t n_live;
     uint16_t live[HUFF_NT];                // subsequences still walking (rounds >= 2)
+    BlockHead heads;                       // write pass: the head of the block every thread is assembling (zero when idle)
 };
 
 // Large batches (at least one file per SM): the whole job in one launch, one CTA per file — synchronise a window, scan, write
@@ -693,6 +778,8 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
         for (int i = t; i < (int)(sizeof(DecTabSet) / 4); i += HUFF_NT) dst[i] = src[i];
     }
+    S.heads.q[0][t] = U4{0u, 0u, 0u, 0u};
+    S.heads.q[1][t] = U4{0u, 0u, 0u, 0u};
     HuffJob J;
     J.stream = streams + im.stream_off;
     J.staged.words = S.words;
@@ -704,6 +791,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_kernel(const DecIm
     J.max_blocks = im.blocks;
     J.coef = coef + im.coef_off * 64;
     J.dc = dc + im.coef_off;
+    J.heads = &S.heads;
     if (t == 0) {
         S.W.carry.p = 0;
         S.W.carry.c = 0;
@@ -769,6 +857,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_sync_kernel(const 
     J.max_blocks = im.blocks;
     J.coef = nullptr;
     J.dc = nullptr;
+    J.heads = nullptr;
     const uint32_t windows = window_count(J.nsub), parts = part_count(J.nsub, gridDim.x);
     if (blockIdx.x >= parts || windows == 0 || im.restart > 0) return;
     const uint32_t w_first = part_first(blockIdx.x, parts, windows), w_end = part_first(blockIdx.x + 1, parts, windows);
@@ -884,6 +973,7 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_write_kernel(const
     J.max_blocks = im.blocks;
     J.coef = coef + im.coef_off * 64;
     J.dc = dc + im.coef_off;
+    J.heads = &S.heads;
     const uint32_t w0 = blockIdx.x * (uint32_t)HUFF_NT;
     if (w0 >= J.nsub || im.restart > 0) return;
     {
@@ -891,6 +981,8 @@ __global__ void __launch_bounds__(HUFF_NT, HUFF_CTAS) huffman_write_kernel(const
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
         for (int i = t; i < (int)(sizeof(DecTabSet) / 4); i += HUFF_NT) dst[i] = src[i];
     }
+    S.heads.q[0][t] = U4{0u, 0u, 0u, 0u};
+    S.heads.q[1][t] = U4{0u, 0u, 0u, 0u};
     J.staged.base_word = w0 * (uint32_t)SUB_WORDS;
     stage_window(t, HUFF_NT, S.words, J.stream, J.staged.base_word, J.stream_words);
     __syncthreads();

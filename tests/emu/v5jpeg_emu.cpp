@@ -148,7 +148,7 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     const uint32_t total_bits = (uint32_t)stream.size() * 8;
     stream.resize(stream.size() + 32, 0);
     DecTabSet *T = new DecTabSet();
-    T->dc[0] = F->dc[0]; T->dc[1] = F->dc[1]; T->ac[0] = F->ac[0]; T->ac[1] = F->ac[1];
+    for (int c = 0; c < 2; c++) { make_dec_table(F->dc[c], T->dc[c]); make_dec_table(F->ac[c], T->ac[c]); }
     std::vector<int16_t> coef((size_t)im.blocks * 64, 0);
     std::vector<uint32_t> staged(STAGE_WORDS, 0xA5A5A5A5u);
     HuffJob J;
@@ -163,6 +163,9 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
     J.coef = coef.data();
     std::vector<int16_t> dcv((size_t)im.blocks, 0);
     J.dc = dcv.data();
+    BlockHead *heads = new BlockHead();                                     // (all zero: what the kernels establish before the write pass)
+    memset(heads, 0, sizeof(*heads));
+    J.heads = heads;
 #ifndef V5J_EMU_PARTS
 #define V5J_EMU_PARTS 0
 #endif
@@ -182,7 +185,7 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
         }
         if (rounds_out) *rounds_out = 0;
         const int rc2 = emu_finish(im, *F, coef, dcv, false, rgb_out, gray_out, coef_out);
-        delete T; delete F;
+        delete T; delete F; delete heads;
         return rc2 ? rc2 : (ok ? 0 : -3);
     }
 #if V5J_EMU_PARTS == 0
@@ -282,8 +285,10 @@ extern "C" int v5jemu_decode(const uint8_t *data, int64_t len, uint8_t *rgb_out,
 #endif
     if (rounds_out) *rounds_out = max_rounds;
     const int rc2 = emu_finish(im, *F, coef, dcv, true, rgb_out, gray_out, coef_out);
-    delete W; delete T; delete F;
-    return rc2 ? rc2 : (ok ? 0 : -3);
+    bool heads_clean = true;                                                // every write pass must leave the block heads zeroed
+    for (size_t i = 0; i < sizeof(BlockHead); i++) heads_clean = heads_clean && reinterpret_cast<const uint8_t *>(heads)[i] == 0;
+    delete W; delete T; delete F; delete heads;
+    return rc2 ? rc2 : (ok ? (heads_clean ? 0 : -4) : -3);
 }
 
 extern "C" int v5jemu_info(const uint8_t *data, int64_t len, int *h, int *w, int *ncomp)
@@ -293,4 +298,16 @@ extern "C" int v5jemu_info(const uint8_t *data, int64_t len, int *h, int *w, int
     if (!rc) { *h = F->h; *w = F->w; *ncomp = F->ncomp; }
     delete F;
     return rc;
+}
+
+// huff_action of the decoder table built from (bits, vals) for `count` 32-bit windows; returns the table's long_base
+// (0x10000 = the long codes are walked), -1 for a table make_dec_table refuses.
+extern "C" int v5jemu_huff_actions(const uint8_t *bits, const uint8_t *vals, int nvals, int is_dc, const uint32_t *windows, int count, uint32_t *actions)
+{
+    DecTable *t = new DecTable();
+    if (!make_dec_table(bits, vals, nvals, is_dc != 0, *t)) { delete t; return -1; }
+    for (int i = 0; i < count; i++) actions[i] = huff_action(*t, windows[i]);
+    const int lb = (int)t->long_base;
+    delete t;
+    return lb;
 }

@@ -36,6 +36,8 @@ def _build(tag, defs):
     lib.v5jemu_encode.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, u8p, ctypes.c_int64, i16p]
     lib.v5jemu_decode.argtypes = [u8p, ctypes.c_int64, u8p, u8p, i16p, ctypes.POINTER(ctypes.c_int)]
     lib.v5jemu_info.argtypes = [u8p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int)] * 3
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    lib.v5jemu_huff_actions.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, u32p, ctypes.c_int, u32p]
     return lib
 
 
@@ -284,3 +286,86 @@ def test_header_that_promises_more_than_the_data_holds_is_refused(emu):
         emu_decode(emu, bytes(data))
     with pytest.raises(ValueError):
         emu_decode(emu, buf.getvalue()[:len(buf.getvalue()) // 8 + 700])      # truncated early: too few bits for the blocks
+
+
+def _canonical(bits, vals):
+    """(length, code) -> symbol of the canonical Huffman code of a DHT segment (T.81 Annex C), independently of the C code."""
+    out, code, k = {}, 0, 0
+    for ln in range(1, 17):
+        for _ in range(bits[ln - 1]):
+            out[(ln, code)] = vals[k]
+            code += 1
+            k += 1
+        code <<= 1
+    return out
+
+
+def _expected_action(codes, is_dc, win16):
+    """What the decoder does with a window whose first 16 bits are win16 (v5jpeg_common.h pack_symbol)."""
+    for ln in range(1, 17):
+        sym = codes.get((ln, win16 >> (16 - ln)))
+        if sym is not None:
+            break
+    else:
+        sym, ln = 0, 16                                    # not a code: symbol 0, 16 bits
+    if is_dc:
+        size, zinc = min(sym, 15), 1
+    else:
+        size = sym & 15
+        zinc = (sym >> 4) + 1 if size else (16 if (sym >> 4) == 15 else 64)
+    return ln | (size << 8) | (zinc << 16) | ((ln + size) << 24)
+
+
+def _dht_tables(jpeg_bytes):
+    """[(is_dc, bits, vals)] of a file's DHT segments."""
+    d, i, out = jpeg_bytes, 2, []
+    while d[i + 1] != 0xDA:
+        seg_len = (d[i + 2] << 8) | d[i + 3]
+        if d[i + 1] == 0xC4:
+            j = i + 4
+            while j < i + 2 + seg_len:
+                bits = list(d[j + 1:j + 17])
+                n = sum(bits)
+                out.append((d[j] >> 4 == 0, bits, list(d[j + 17:j + 17 + n])))
+                j += 17 + n
+        i += 2 + seg_len
+    return out
+
+
+def test_two_level_huffman_table_equals_canonical_code_for_every_window():
+    """The decoder's table (look[] for codes of <= 9 bits, lng[] for the longer ones when they span <= 1024 windows, the
+    maxcode walk otherwise) against the canonical code, for ALL 65536 leading 16-bit windows: Annex K tables, the optimised
+    tables Pillow writes for several images, and synthetic tables whose long codes span more than 1024 windows (walk)."""
+    lib = _build("full", [])
+    rng = np.random.default_rng(5)
+    tables = []
+    for q, kw in ((90, {}), (95, {"optimize": True}), (30, {"optimize": True}), (100, {"optimize": True})):
+        buf = io.BytesIO()
+        img = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8) if q != 30 else golden_frame(SMALL[0])
+        Image.fromarray(img).save(buf, "JPEG", quality=q, **kw)
+        tables += _dht_tables(buf.getvalue())
+    # synthetic: 2 codes of 2 bits, 1 of 3 bits, then 200 codes of 12 bits (range 65536 - 0xA000 > 1024: walked), and a flat 8-bit code with one free word
+    b = [0] * 16
+    b[1], b[2], b[11] = 2, 1, 200
+    tables.append((False, b, list(range(1, 204))))
+    b = [0] * 16
+    b[7] = 255                                          # windows 0xFFxx are not codes
+    tables.append((False, b, list(range(255))))
+    b = [0] * 16
+    b[0], b[9], b[15] = 1, 3, 40                        # 1 code of 1 bit, 3 of 10 bits, 40 of 16: long codes start at 0x8000 (walked)
+    tables.append((False, b, list(range(16, 60))))
+    wins = (np.arange(65536, dtype=np.uint32) << 16) | rng.integers(0, 65536, 65536).astype(np.uint32)
+    acts = np.zeros(65536, dtype=np.uint32)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    seen_walk = seen_lng = 0
+    for is_dc, bits, vals in tables:
+        barr, varr = np.array(bits, dtype=np.uint8), np.array(vals + [0], dtype=np.uint8)
+        lb = lib.v5jemu_huff_actions(_u8(barr), _u8(varr), len(vals), int(is_dc), wins.ctypes.data_as(u32p), 65536, acts.ctypes.data_as(u32p))
+        assert lb >= 0
+        seen_walk += lb == 0x10000 and any(bits[9:])
+        seen_lng += lb < 0x10000
+        codes = _canonical(bits, vals)
+        exp = np.array([_expected_action(codes, is_dc, w) for w in range(65536)], dtype=np.uint32)
+        bad = np.nonzero(acts != exp)[0]
+        assert bad.size == 0, (is_dc, bits, hex(int(bad[0])), hex(int(acts[bad[0]])), hex(int(exp[bad[0]])))
+    assert seen_walk >= 2 and seen_lng >= 8

@@ -358,6 +358,21 @@ constexpr int RING = RGB_BUFS == 2 ? 32 : 24;   // yorig ring lines: 16 of the c
 constexpr int RINGD = V5_RINGD;         // ydec ring lines (16 + 1 carried); a power of two where shared memory allows: the
                                         // ring index is computed per 8-pixel unit
 
+// Two-phase band loop for the width-multiple-of-16 instantiations (v5ela_workitem.cuh): the residual stage of band r-1 and the
+// conversion of band r share one barrier-delimited phase, the block stage of band r is the other — two CTA barriers per band
+// instead of three. What the conversion of band r overwrites while the residual stage of band r-1 still reads it is kept aside
+// during the block stage before: luma lines 14, 15 of band r-2 (ycarry), and RGB line 15 is carried then as well.
+// Measured 2.3-2.7 % SLOWER than three phases with either block stage (profiles/r02/variants.txt section 12: the request for band r+1
+// can only be issued one block stage ahead instead of a whole band, and the long mixed phase schedules worse) and therefore off: a
+// compile-time variant like the split barrier, kept bit-exact by the emulator tests.
+#ifndef V5_FUSE2
+#define V5_FUSE2 0
+#endif
+#ifndef V5_PAIR_ROWS
+#define V5_PAIR_ROWS 1
+#endif
+constexpr bool FUSE2_OK = V5_FUSE2 && RGB_BUFS == 2 && V5_PAIR_ROWS && RING == 32;
+
 struct alignas(16) Smem {
     QEntry qtab[2][64];                 // [0] luma, [1] chroma: copied from the kernel parameters once per work item (tensor-core
                                         // block stage: in mma::qswz_pos order, unbias minus the limb offset)
@@ -376,6 +391,7 @@ struct alignas(16) Smem {
                                         // 36-word block stride = conflict-free scattered stores and 128-bit loads
 #endif
     uint8_t yorig[RING][Y_PITCH];       // luma of the original; band r line l at [(16r + l) mod RING]
+    uint8_t ycarry[FUSE2_OK ? 2 : 1][FUSE2_OK ? Y_PITCH : 16];   // two-phase band loop only: lines 14 and 15 of the band before the one the residual stage works on
     uint8_t ydec[RINGD][Y_PITCH];       // luma after the JPEG round trip; band r line l at [(16r + l) mod RINGD]
     uint8_t cenc[2][8][C_PITCH];        // downsampled Cb/Cr of the current band (input of the block stage)
     uint8_t cdec[2][16][C_PITCH];       // decoded Cb/Cr; band r chroma line j at [8*(r&1) + j]
@@ -577,7 +593,7 @@ V5_DEV void convert_wait_done(int tid, Smem &S, const KParams &p, const Geo &g, 
     if (prefetch_next) stage_prefetch(tid, S, p, g, r + 1);
 }
 
-V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int r, ThreadAcc &acc, bool defer, bool prefetch_next)
+V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int r, ThreadAcc &acc, bool defer, bool prefetch_next, bool copy_carry = true)
 {
     // Chroma line j of this band averages frame rows (2jc, min(2jc+1, H-1)) with jc = min(8r+j, He/2-1): below the
     // image the DOWNSAMPLED last row is replicated, which differs from the luma rule (replicate row H-1) when H is even.
@@ -585,7 +601,7 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
     const int last_line = g.h - 1 - 16 * r;                     // local index of the last real pixel line
     const uint8_t(*src)[RGB_PITCH] = S.rgb[rb(r)];
     bool waiting = defer;
-    if (RGB_BUFS == 2 && !waiting)
+    if (RGB_BUFS == 2 && !waiting && copy_carry)
         for (int i = tid; i < RGB_PITCH / 16; i += NT)          // keep line 15 for the next iteration's residual stage
             reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
 #if defined(V5_CONVERT_UNROLL) && V5_CONVERT_UNROLL
@@ -622,6 +638,19 @@ V5_DEV void stage_convert(int tid, Smem &S, const KParams &p, const Geo &g, int 
         if (RGB_BUFS == 2)
             for (int i = tid; i < RGB_PITCH / 16; i += NT)
                 reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[i] = reinterpret_cast<const U4 *>(src[15])[i];
+    }
+}
+
+// Two-phase band loop, during the block stage of band r: RGB line 15 of band r (if it exists) for the residual stage of band r+1,
+// luma lines 14, 15 of band r-1 for the residual stage of band r — which runs while band r+1 is converted over them.
+V5_DEV void stage_carries(int tid, Smem &S, int r, bool has_band)
+{
+    constexpr int NRGB = RGB_PITCH / 16, NY = Y_PITCH / 16;
+    if (tid < NRGB) {
+        if (has_band) reinterpret_cast<U4 *>(S.rgb_carry[r & 1])[tid] = reinterpret_cast<const U4 *>(S.rgb[rb(r)][15])[tid];
+    } else if (FUSE2_OK && tid < NRGB + 2 * NY) {
+        const int k = tid - NRGB, line = k >= NY ? 1 : 0, i = k - line * NY;
+        reinterpret_cast<U4 *>(S.ycarry[FUSE2_OK ? line : 0])[FUSE2_OK ? i : 0] = reinterpret_cast<const U4 *>(S.yorig[ring16(r - 1, 14 + line)])[i];
     }
 }
 
@@ -1069,8 +1098,12 @@ V5_DEV void residual_row(Smem &S, const KParams &p, const Geo &g, ThreadAcc &acc
     int lu = l - 1, ld = l + 1;
     if (y == 0) lu = g.h > 1 ? l + 1 : l;
     if (y == g.h - 1) ld = g.h > 1 ? l - 1 : l;
-    const uint8_t *yc = &S.yorig[ring16(r, l)][col];
-    const uint8_t *yu = &S.yorig[ring16(r, lu)][col], *yd2 = &S.yorig[ring16(r, ld)][col];
+    // (two-phase band loop: lines -2 and -1, the last two of the band before, were kept aside — the ring half they lived in is being
+    // converted over)
+    constexpr bool CARRY = FAST && FUSE2_OK;
+    const uint8_t *yc = CARRY && l < 0 ? &S.ycarry[CARRY ? l + 2 : 0][CARRY ? col : 0] : &S.yorig[ring16(r, l)][col];
+    const uint8_t *yu = CARRY && lu < 0 ? &S.ycarry[CARRY ? lu + 2 : 0][CARRY ? col : 0] : &S.yorig[ring16(r, lu)][col];
+    const uint8_t *yd2 = CARRY && ld < 0 ? &S.ycarry[CARRY ? ld + 2 : 0][CARRY ? col : 0] : &S.yorig[ring16(r, ld)][col];
     const int wide = FAST || g.w > 1;
     uint32_t sabs = 0, ssq = 0, mx = acc.tex_maxabs;
     {

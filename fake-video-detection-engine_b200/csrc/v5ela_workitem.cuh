@@ -48,21 +48,28 @@ namespace V5_NS {
     }                                        \
     __syncthreads();
 #else
+// V5_EMU_REVERSE: the emulated threads of a phase run last to first — any order must give the same result, and the two orders
+// together catch a buffer that one thread of a phase overwrites while another still reads it, whichever of them has the lower index.
+#if defined(V5_EMU_REVERSE) && V5_EMU_REVERSE
+#define V5_EMU_TID_LOOP(step) for (int tid = NT - (step); tid >= 0; tid -= (step))
+#else
+#define V5_EMU_TID_LOOP(step) for (int tid = 0; tid < NT; tid += (step))
+#endif
 #define V5_FOR_EACH_WARP(...)                        \
-    for (int tid = 0; tid < NT; tid += 32) {         \
+    V5_EMU_TID_LOOP(32) {                            \
         __VA_ARGS__;                                 \
     }
 #define V5_FOR_THREADS_NOSYNC(...) V5_FOR_THREADS(__VA_ARGS__)
 #define V5_BLOCK_TASK(t)
 #define V5_GET_TASK(t) const BlockTask t = block_task_of<FAST>(tid, S, p, g, r, want_y, round)
 #define V5_FOR_WARP(...)                     \
-    for (int tid = 0; tid < NT; tid++) {     \
+    V5_EMU_TID_LOOP(1) {                     \
         ThreadAcc &acc = acc_store[tid];     \
         (void)acc;                           \
         __VA_ARGS__;                         \
     }
 #define V5_FOR_THREADS(...)                  \
-    for (int tid = 0; tid < NT; tid++) {     \
+    V5_EMU_TID_LOOP(1) {                     \
         ThreadAcc &acc = acc_store[tid];     \
         (void)acc;                           \
         __VA_ARGS__;                         \
@@ -184,56 +191,103 @@ V5_DEV void process_work_item(Smem &S, const KParams &p, int work, ThreadAcc *ac
 #define V5_PAIR_ROWS 1
 #endif
     constexpr bool PAIRS = FAST && V5_PAIR_ROWS;             // two rows per residual unit (stage_residual_pairs)
-    bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet
-    for (int r = r_first; r <= g.r1; r++) {
-        const bool has_band = r < g.mh;
-        const bool want_y = r >= g.r0 && r < g.r1;
-        const bool next_band = r + 1 <= g.r1 && r + 1 < g.mh;
-        if (!has_band && 16 * r - 1 >= g.h) break;          // nothing left below the image
-        if (has_band) {
-            // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
-            // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
-            if (rest) {                                     // ragged right edge / unaligned frames only
-                V5_FOR_THREADS(stage_load_rest(tid, S, p, g, r, bulk))
-            }
-            // every thread waits for the bulk copy itself, so no CTA barrier is needed before the conversion
+    constexpr bool FUSE = FAST && FUSE2_OK;                  // two-phase band loop (v5ela_device.cuh)
+    static_assert(!FUSE || (PAIRS && NT >= RGB_PITCH / 16 + 2 * (Y_PITCH / 16)), "two-phase band loop: pairs, and one thread per carried 16 bytes");
+    if (FUSE) {
+        // phase 1: residual stage of the band before (`pend`) + conversion of band r; phase 2: carries, request for band r+1 (its
+        // buffer was last read by the residual stage just finished) and the block stage of band r.
+        int pend = -1;
+        for (int r = r_first; r <= g.r1; r++) {
+            const bool has_band = r < g.mh;
+            const bool want_y = r >= g.r0 && r < g.r1;
+            const bool next_band = r + 1 <= g.r1 && r + 1 < g.mh;
+            if (!has_band && 16 * r - 1 >= g.h) break;      // nothing left below the image
             V5_FOR_THREADS({
-                const bool defer = SPLIT && pending;         // the other RGB buffer may still be read: prefetch after the wait
-                if (!defer && RGB_BUFS == 2 && bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
-                if (bulk) {
+                if (pend >= 0) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, pend);
+                if (has_band) {
                     mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[rb(r)]), (acc.phase >> rb(r)) & 1u);
                     acc.phase ^= 1u << rb(r);
+                    stage_convert(tid, S, p, g, r, acc, false, false, false);
                 }
-                stage_convert(tid, S, p, g, r, acc, defer, defer && bulk && next_band);
             })
-            pending = false;
-            // single staging buffer: band r has been consumed by every warp (barrier above), fetch band r+1 over it now
-            if (RGB_BUFS == 1 && bulk && next_band) {
-                V5_FOR_WARP(stage_prefetch(tid, S, p, g, r + 1))
-            }
-#if V5_MMA_BLOCKS
-            V5_FOR_EACH_WARP(stage_blocks_mma<FAST>(tid, S, p, g, r, want_y))
-#else
-            const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
-            for (int round = 0; round < rounds; round++) {
-                V5_BLOCK_TASK(t)
-                V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_fwd(tid, S, t))
-                V5_FOR_WARP(V5_GET_TASK(t); blocks_cols(tid, S, t, acc.col))
-                V5_FOR_WARP(V5_GET_TASK(t); blocks_cols_store(tid, S, t, acc.col))
-                V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_inv(tid, S, t))
-            }
-            V5_FOR_THREADS((void)0)
-#endif
-        }
-        if (SPLIT && next_band) {
+            pend = r;
             V5_FOR_THREADS_NOSYNC({
-                if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r);
-                else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r);
-                mbar_arrive(reinterpret_cast<uint64_t *>(&S.done_bar));
+                if (next_band) stage_prefetch(tid, S, p, g, r + 1);
+                stage_carries(tid, S, r, has_band);
             })
-            pending = true;
-        } else {
-            V5_FOR_THREADS(if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r); else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
+            if (has_band) {
+#if V5_MMA_BLOCKS
+                V5_FOR_EACH_WARP(stage_blocks_mma<FAST>(tid, S, p, g, r, want_y))
+#else
+                const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
+                for (int round = 0; round < rounds; round++) {
+                    V5_BLOCK_TASK(t)
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_fwd(tid, S, t))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_cols(tid, S, t, acc.col))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_cols_store(tid, S, t, acc.col))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_inv(tid, S, t))
+                }
+                V5_FOR_THREADS((void)0)
+#endif
+            } else {
+                V5_FOR_THREADS((void)0)
+            }
+        }
+        if (pend >= 0) {
+            V5_FOR_THREADS(stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, pend))
+        }
+    } else {
+        bool pending = false;                                   // an arrive on done_bar that nobody has waited for yet
+        for (int r = r_first; r <= g.r1; r++) {
+            const bool has_band = r < g.mh;
+            const bool want_y = r >= g.r0 && r < g.r1;
+            const bool next_band = r + 1 <= g.r1 && r + 1 < g.mh;
+            if (!has_band && 16 * r - 1 >= g.h) break;          // nothing left below the image
+            if (has_band) {
+                // Band r was requested one iteration ago; request band r+1 into the other buffer (free since the residual
+                // stage of iteration r-1), fetch what the bulk copy does not cover, then wait for band r.
+                if (rest) {                                     // ragged right edge / unaligned frames only
+                    V5_FOR_THREADS(stage_load_rest(tid, S, p, g, r, bulk))
+                }
+                // every thread waits for the bulk copy itself, so no CTA barrier is needed before the conversion
+                V5_FOR_THREADS({
+                    const bool defer = SPLIT && pending;         // the other RGB buffer may still be read: prefetch after the wait
+                    if (!defer && RGB_BUFS == 2 && bulk && next_band) stage_prefetch(tid, S, p, g, r + 1);
+                    if (bulk) {
+                        mbar_wait(reinterpret_cast<uint64_t *>(&S.full_bar[rb(r)]), (acc.phase >> rb(r)) & 1u);
+                        acc.phase ^= 1u << rb(r);
+                    }
+                    stage_convert(tid, S, p, g, r, acc, defer, defer && bulk && next_band);
+                })
+                pending = false;
+                // single staging buffer: band r has been consumed by every warp (barrier above), fetch band r+1 over it now
+                if (RGB_BUFS == 1 && bulk && next_band) {
+                    V5_FOR_WARP(stage_prefetch(tid, S, p, g, r + 1))
+                }
+#if V5_MMA_BLOCKS
+                V5_FOR_EACH_WARP(stage_blocks_mma<FAST>(tid, S, p, g, r, want_y))
+#else
+                const int rounds = (blocks_in_band(g, want_y) + NT / 4 - 1) / (NT / 4);
+                for (int round = 0; round < rounds; round++) {
+                    V5_BLOCK_TASK(t)
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_fwd(tid, S, t))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_cols(tid, S, t, acc.col))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_cols_store(tid, S, t, acc.col))
+                    V5_FOR_WARP(V5_GET_TASK(t); blocks_rows_inv(tid, S, t))
+                }
+                V5_FOR_THREADS((void)0)
+#endif
+            }
+            if (SPLIT && next_band) {
+                V5_FOR_THREADS_NOSYNC({
+                    if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r);
+                    else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r);
+                    mbar_arrive(reinterpret_cast<uint64_t *>(&S.done_bar));
+                })
+                pending = true;
+            } else {
+                V5_FOR_THREADS(if (PAIRS) stage_residual_pairs<TEXHIST>(tid, S, p, g, acc, r); else stage_residual<FAST, TEXHIST>(tid, S, p, g, acc, r))
+            }
         }
     }
 

@@ -16,12 +16,15 @@ from v5ela.synth import gen_frame
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_rows_split", "2cta_mma", "2cta_mma_np2", "3cta_mma"])
+@pytest.fixture(scope="module", params=["2cta", "3cta", "2cta_rows_split", "2cta_mma", "2cta_mma_np2", "3cta_mma", "2cta_rev", "2cta_mma_rev", "2cta_fuse2", "2cta_fuse2_rev"])
 def emu(request):
     """The default layout (2 CTAs/SM, double-buffered RGB), the -DV5_MIN_CTAS=3 single-buffer layout, and the default layout
     with the two compile-time variants of the width-multiple-of-16 instantiation flipped (one row per residual unit instead
     of two, split barrier on); "_mma": the tensor-core block stage (csrc/v5ela_dctmma.cuh, the library's second build of the
-    kernel) with the m16n8k16 fragment layout emulated lane by lane, one or two pairs of blocks in flight per warp."""
+    kernel) with the m16n8k16 fragment layout emulated lane by lane, one or two pairs of blocks in flight per warp; "_rev": the
+    emulated threads of every barrier-delimited phase run last to first (a read-after-overwrite inside a phase shows up in one of the two
+    orders); "_fuse2": the two-phase band loop (-DV5_FUSE2=1, a compile-time variant: the residual stage of one band and the conversion
+    of the next in the same phase), in both orders."""
     variant = request.param
     so = os.path.join(HERE, "emu", f"libv5ela_emu_{variant}.so")
     src = os.path.join(HERE, "emu", "v5ela_emu.cpp")
@@ -30,8 +33,12 @@ def emu(request):
     deps.append(__file__)
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         extra = ["-DV5_PAIR_ROWS=0", "-DV5_SPLIT_BARRIER=1"] if variant.endswith("rows_split") else []
+        if "_fuse2" in variant:
+            extra += ["-DV5_FUSE2=1"]
+        if variant.endswith("_rev"):
+            extra += ["-DV5_EMU_REVERSE=1"]
         if "_mma" in variant:
-            extra += ["-DV5_MMA_BLOCKS=1", "-DV5_MMA_NP=2" if variant.endswith("np2") else "-DV5_MMA_NP=1"]
+            extra += ["-DV5_MMA_BLOCKS=1", "-DV5_MMA_NP=2" if "np2" in variant else "-DV5_MMA_NP=1"]
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", f"-DV5_MIN_CTAS={variant[0]}", *extra,
                                "-I", os.path.join(ROOT, "include"), "-I", csrc, src, "-o", so])
     lib = ctypes.CDLL(so)

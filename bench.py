@@ -343,7 +343,8 @@ def run_native_arm(args):
     est = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(est, op=dist.ReduceOp.MAX)
-    K = max(args.steps, int(math.ceil(args.min_seconds * 1e3 / max(float(est.item()), 1e-3))))
+    # (+5 %: a single step timed alone runs a little slower than the steps of the timed region, and the region must not end up short)
+    K = max(args.steps, int(math.ceil(1.05 * args.min_seconds * 1e3 / max(float(est.item()), 1e-3))))
     K = min(K, 200000 if not small else 4000)                   # L2-sized inputs: one event pair and one flush per step
 
     # ---- device-resident throughput (value) + fused-kernel duration (roofline), clocks sampled during the region

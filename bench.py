@@ -102,14 +102,14 @@ def workload_config(cid: int, n_gpus: int) -> dict:
 
 
 def source_hash() -> str:
-    """sha256 over the CUDA sources the library is built from (what a profile has to match to describe this build)."""
-    h = hashlib.sha256()
-    csrc = os.path.join(PKG, "csrc")
-    for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            with open(os.path.join(csrc, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
-    return h.hexdigest()[:16]
+    """Hash over the CUDA sources the library is built from, comments and white space removed (profiles/source_hash.py): what a
+    profile has to match to describe this build."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("v5_source_hash", os.path.join(ROOT, "profiles", "source_hash.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.source_hash(os.path.join(PKG, "csrc"))
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference arm

@@ -130,7 +130,8 @@ inline std::vector<uint8_t> file_header(int h, int w, int ncomp, const uint16_t 
 
 // ---------------------------------------------------------------------------------------------------- decoder tables
 // Huffman decoding by a window of the next stream bits: look[window >> 23] resolves codes of <= 9 bits in one step, longer
-// codes walk maxcode[] (T.81 F.2.2.3). What comes back is not the raw symbol but what the decoder does with it, packed:
+// codes take a second table (DecTable::lng) or, for tables whose long codes span too many windows, walk maxcode[] (T.81
+// F.2.2.3). What comes back is not the raw symbol but what the decoder does with it, packed:
 //   bits  0..4   code length
 //   bits  8..11  size   = number of value bits that follow the code (0 = none)
 //   bits 16..22  zinc   = how far the zigzag index moves: DC 1; AC run + 1; ZRL (F0) 16; end of block 64

@@ -13,7 +13,8 @@
 //                   leave their subsequence. Every thread then keeps decoding into the following subsequences until its
 //                   exit state equals the one recorded there, overwriting the record otherwise; when nobody moves, every
 //                   recorded state is the true one. A prefix sum of the blocks completed per subsequence gives every thread
-//                   its output position and a last pass decodes again, this time writing coefficients. Windows of 1024
+//                   its output position and a last pass decodes again, this time writing coefficients (the head of every
+//                   block assembled in shared memory and stored as one full sector, BlockHead). Windows of 1024
 //                   subsequences are processed in order by the same CTA, carrying the exact state from one to the next.
 //   huffman_rst_kernel  files with restart intervals only: every interval starts in a known state, one thread each
 //   dc_kernel       one CTA per file: DC differences -> DC values (prefix sum per component, T.81 F.2.2.1) on a dense
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(1024) unstuff_kernel(const DecImage *images, c
 }
 
 struct HuffSmem {
-    uint32_t words[STAGE_WORDS];           // the window's share of the stream (128 KB + one row)
+    uint32_t words[STAGE_WORDS];           // the window's share of the stream (128 KB + one subsequence)
     DecTabSet T;
     HuffWindow W;
     uint32_t warp_sums[33];

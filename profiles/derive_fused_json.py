@@ -23,16 +23,10 @@ def main(rep, label, extra=None):
         return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
     rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-    import hashlib
+    from source_hash import source_hash as _sh                      # the same function bench.py uses (comments and white space do not count)
 
-    def source_hash():                       # the same function as bench.py's (not imported: bench.py redirects stdout on import)
-        hh = hashlib.sha256()
-        csrc = os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc")
-        for name in sorted(os.listdir(csrc)):
-            if name.endswith((".cu", ".cuh", ".h")):
-                with open(os.path.join(csrc, name), "rb") as f:
-                    hh.update(name.encode() + b"\0" + f.read())
-        return hh.hexdigest()[:16]
+    def source_hash():
+        return _sh(os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc"))
 
     sh = os.environ.get("V5_PROFILE_SOURCE_HASH") or source_hash()
     dram = {"kernel": "v5::ela_fused_kernel", "source": label, "source_hash": sh, "frames_per_launch": N, "height": H, "width": W,

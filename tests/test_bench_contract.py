@@ -40,3 +40,23 @@ def test_native_arm_needs_a_gpu():
                        capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and p.stdout.strip() == ""
     assert "no CUDA device" in p.stderr
+
+
+def test_profile_source_hash_ignores_comments_and_matches_the_committed_profile():
+    """bench.py says whether the ncu figures it quotes (roofline.traffic, int_issue) describe the build it timed by comparing a
+    hash of csrc/ with the one stamped into profiles/fused_kernel_*.json. The hash ignores comments and white space, changes with
+    any token, and the committed profiles carry the hash of the committed sources."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("v5_source_hash", os.path.join(ROOT, "profiles", "source_hash.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a = 'int f(int x) { return x /* not a comment in "s" */ + 1; }  // tail\nconst char *s = "a // b /* c */";\n'
+    b = 'int f(int x)\n{\n    return x + 1;\n}\nconst char *s = "a // b /* c */";'
+    assert mod.strip_code(a).strip() == mod.strip_code(b).strip()
+    assert mod.strip_code(a) != mod.strip_code(a.replace("+ 1", "+ 2"))
+    assert mod.strip_code(a) != mod.strip_code(a.replace('"a // b', '"a / b'))
+    h = mod.source_hash(os.path.join(ROOT, "fake-video-detection-engine_b200", "csrc"))
+    for name in ("fused_kernel_dram.json", "fused_kernel_issue.json"):
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            assert json.load(f)["source_hash"] == h, f"{name}: re-capture (profiles/final_run_r02.sh) and profiles/derive_fused_json.py after a kernel change"

@@ -369,3 +369,27 @@ def test_two_level_huffman_table_equals_canonical_code_for_every_window():
         bad = np.nonzero(acts != exp)[0]
         assert bad.size == 0, (is_dc, bits, hex(int(bad[0])), hex(int(acts[bad[0]])), hex(int(exp[bad[0]])))
     assert seen_walk >= 2 and seen_lng >= 8
+
+
+def test_malformed_huffman_tables_are_refused_by_the_parser():
+    """A DHT segment whose code lengths oversubscribe the code space (three codes of one bit) or promise more symbols than it
+    carries must make parse_file fail (JPEG_CORRUPT = -1) — the decoder tables are only built later, once per distinct table set,
+    and rely on the parser having checked every file's tables."""
+    lib = _build("full", [])
+    buf = io.BytesIO()
+    Image.fromarray(golden_frame(SMALL[0])).save(buf, "JPEG", quality=80)
+    good = bytearray(buf.getvalue())
+    i = good.index(b"\xff\xc4")                                     # first DHT segment: marker, length (2), Tc/Th (1), 16 counts
+    rgb = np.zeros((SMALL[0]["h"], SMALL[0]["w"], 3), np.uint8)
+
+    def rc_of(data):
+        arr = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        return lib.v5jemu_decode(_u8(arr), len(arr), _u8(rgb), None, None, None)
+
+    assert rc_of(good) == 0
+    bad = bytearray(good)
+    bad[i + 5] = 3                                                  # three codes of length 1
+    assert rc_of(bad) == -1
+    bad = bytearray(good)
+    bad[i + 5 + 15] = 200                                           # 200 more codes of length 16 than the segment has symbols for
+    assert rc_of(bad) == -1
